@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- atom-force-evals/s (and saddle searches/hour) of the batched EAM hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's B200 path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU EAM.cpp
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): examples/akmc-al -- 385 Al atoms
+(128 fixed), box 22.845 x 22.845 x 64 A, in-tree EAM Al row (rc 5.555 A), 256 concurrent walkers
+per GPU, positions jittered U(-0.05, 0.05) A per walker.  One "step" = one batched energy+force
+evaluation of all walkers of a rank (256 x 385 atom-force-evals).  Walkers are independent, so
+ranks shard them with no collective on the data path (weak scaling: 256 walkers per GPU).
+
+Timed region of `value`: inputs resident in HBM, L2 flushed before every step (a 512 MiB memset
+outside the CUDA events), CUDA events on the launching stream around each step's kernels, summed
+over the K steps, max over ranks.  `e2e`: the same metric through B200Potential.forceBatch with
+host buffers (H2D + kernels + D2H inside the timed region).  The saddle-search leg runs the whole
+device-resident dimer/LBFGS search of 256 walkers once and reports searches/hour.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from eon_b200 import workloads as WL  # noqa: E402
+
+N_WALKERS = 256
+JITTER = 0.05
+N_POSITION_SETS = 4
+SEARCH_ROW_Z = 79  # the in-tree Au row: see DESIGN.md "Search workload"
+A0_AU = 4.092320738309691  # equilibrium fcc lattice constant of the in-tree EAM Au row (oracle)
+
+
+def eam_flops(ordered_pairs: float, atoms: float) -> float:
+    """flops_EAM = 107 * P_o + 40 * N (exp = 20 flop convention)."""
+    return 107.0 * ordered_pairs + 40.0 * atoms
+
+
+def eam_min_bytes(ordered_pairs: float, atoms: float) -> float:
+    """read R 24 + write F 24 + 2 passes x 4 B per neighbour index + 16 B rho/F' per atom."""
+    return 64.0 * atoms + 8.0 * ordered_pairs
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            tok = [t.strip() for t in r.split(",")]
+            if len(tok) < 7:
+                continue
+            try:
+                sm.append(float(tok[0]))
+                smax.append(float(tok[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, tok[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ------------------------------------------------------------------------------------------------------
+# inputs
+def force_workload(first_walker: int):
+    s = WL.load_structure("akmc_al.json")
+    sets = [WL.jitter(s.positions, N_WALKERS, JITTER, seed=1000 * k + first_walker, fixed=None)
+            for k in range(N_POSITION_SETS)]
+    return s, np.stack(sets)  # [SETS][W][N][3]
+
+
+def search_workload():
+    """akmc-al geometry scaled to the lattice constant of the in-tree EAM Au row; all atoms Z = 79."""
+    s = WL.load_structure("akmc_al.json")
+    scale = A0_AU / 4.05
+    s.positions = s.positions * scale
+    s.cell = s.cell * scale
+    s.atomic_nrs = np.full_like(s.atomic_nrs, SEARCH_ROW_Z)
+    return s, scale
+
+
+SEARCH_PARAMS = dict(opt_method=1, opt_converged_force=1e-4, opt_max_iterations=1000, minmode_method=0,
+                     saddle_max_energy=10.0, saddle_max_iterations=1000)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arms (the only place outside tests/ and smoke() that touches oracle/)
+def cpu_force_baseline(struct, positions, budget_s: float, use_reference: bool):
+    """Time the reference's CPU EAM on a bounded sample of the same walkers, one thread per host core."""
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    kind = "reference" if (use_reference and O.ref_eam_available()) else "port"
+    if kind == "reference":
+        def one(w):
+            O.ref_eam_force(positions[w % len(positions)], struct.atomic_nrs, struct.cell)
+    else:
+        pot = O.potential(O.POT_EAM)
+
+        def one(w):
+            O.force(pot, positions[w % len(positions)], struct.atomic_nrs, struct.cell)
+    t0 = time.perf_counter()
+    one(0)
+    t1 = max(time.perf_counter() - t0, 1e-6)
+    per_core = max(2, int(budget_s / t1))
+    n_evals = per_core * cores
+    with ThreadPoolExecutor(cores) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(one, range(n_evals), chunksize=max(1, per_core // 4)))
+        dt = time.perf_counter() - t0
+    rate = n_evals * struct.n_atoms / dt
+    return {"value": rate, "unit": "atom-force-evals/s", "cores": cores, "kind": kind,
+            "sample": f"{n_evals} single-walker evaluations of the {struct.n_atoms}-atom akmc-al cell "
+                      f"({'EAM.cpp compiled from the reference tree, O(N^2) loop' if kind == 'reference' else 'oracle restatement of EAM.cpp'}), "
+                      f"{cores} threads, {dt:.1f} s"}, dt, n_evals
+
+
+def run_reference(args):
+    rank, local_rank, world = dist_env()
+    if rank != 0:
+        return 0
+    struct, sets = force_workload(0)
+    positions = sets[0]
+    per_step_budget = 4.0
+    times = []
+    evals = 0
+    info = None
+    for step in range(args.warmup + args.steps):
+        info, dt, n = cpu_force_baseline(struct, positions, per_step_budget if step >= args.warmup else 0.5, True)
+        if step >= args.warmup:
+            times.append(dt)
+            evals += n
+    total = sum(times)
+    value = evals * struct.n_atoms / total
+    line = {"impl": "reference", "metric": "atom-force-evals/sec", "value": value, "unit": "atom-force-evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "examples/akmc-al (385 Al atoms, in-tree EAM Al row), bounded sample per step",
+                       "walkers_per_gpu": N_WALKERS, "n_atoms": struct.n_atoms},
+            "cpu_baseline": dict(info, value=value),
+            "e2e": {"value": value, "unit": "atom-force-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_search_baseline(struct, Rmin, E0, n_walkers: int):
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    pot = O.potential(O.POT_EAM_NL, conservative=True)
+    prm = O.search_params(**SEARCH_PARAMS)
+    cfg = dict(WL.AKMC_AL)
+    R, M = [], []
+    for k in range(n_walkers):
+        a, b = WL.displace(struct, Rmin, struct.n_atoms - 1, cfg["radius"] * A0_AU / 4.05, cfg["magnitude"], cfg["seed"] + k)
+        R.append(a)
+        M.append(b)
+
+    def one(k):
+        res, _, _ = O.saddle_search(pot, prm, R[k], struct.atomic_nrs, struct.fixed, struct.cell, M[k], E0)
+        return res.status, res.force_calls, res.energy
+
+    with ThreadPoolExecutor(cores) as ex:
+        t0 = time.perf_counter()
+        out = list(ex.map(one, range(n_walkers)))
+        dt = time.perf_counter() - t0
+    good = sum(1 for o in out if o[0] == 0)
+    return {"searches_per_hour": good / dt * 3600.0, "completed": n_walkers, "status_good": good, "cores": cores,
+            "kind": "port (oracle dimer/LBFGS over the cell-list EAM variant)", "seconds": dt,
+            "force_calls": int(sum(o[1] for o in out))}, out
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    from eon_b200 import B200Potential, Walkers, search_params
+
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+        return float(t.item())
+
+    first = rank * N_WALKERS
+    struct, sets = force_workload(first)
+    N, W = struct.n_atoms, N_WALKERS
+    pot = B200Potential("eam", device=local_rank, skin=args.skin)
+    d_R = torch.from_numpy(sets.reshape(N_POSITION_SETS, W, 3 * N)).to(dev)
+    d_Z = torch.from_numpy(np.broadcast_to(struct.atomic_nrs, (W, N)).copy()).to(dev)
+    d_box = torch.from_numpy(np.broadcast_to(struct.cell.reshape(9), (W, 9)).copy()).to(dev)
+    d_F = torch.empty((W, 3 * N), dtype=torch.float64, device=dev)
+    d_U = torch.empty((W,), dtype=torch.float64, device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step(k):
+        pot.forceBatchDevice(W, N, d_R[k % N_POSITION_SETS].data_ptr(), d_Z.data_ptr(), d_F.data_ptr(), d_U.data_ptr(),
+                             d_box.data_ptr(), sync=True)
+        nl_ms, f_ms = pot.last_force_ms()
+        return nl_ms + f_ms
+
+    for k in range(max(3, args.warmup)):
+        step(k)
+    stats = pot.nl_stats()
+    pairs_per_step = float(stats["ordered_pairs"])
+    # FP64 roofline denominator, measured live (MEASURED_PEAKS.json has no FP64 figure)
+    fp64_peak = pot.measure_fp64_peak(5)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = pot.kernelLaunches
+    barrier()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    rebuilt = 0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        dev_ms += step(k)
+        rebuilt += pot.nl_stats()["rebuilt"]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = pot.kernelLaunches - launches0
+    clocks = sampler.stop()
+    dev_ms_max = reduce_max(dev_ms)
+    units = reduce_sum(float(W) * N * args.steps)
+    value = units / (dev_ms_max * 1e-3)
+
+    # hot-L2 variant (no flush) and a fresh-list variant (skin 0: cell-list rebuild on every step)
+    t_hot = 0.0
+    for k in range(args.steps):
+        t_hot += step(k)
+    pot0 = B200Potential("eam", device=local_rank, skin=0.0)
+    for k in range(3):
+        pot0.forceBatchDevice(W, N, d_R[k % N_POSITION_SETS].data_ptr(), d_Z.data_ptr(), d_F.data_ptr(), d_U.data_ptr(),
+                              d_box.data_ptr(), sync=True)
+    t_fresh = 0.0
+    for k in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        pot0.forceBatchDevice(W, N, d_R[k % N_POSITION_SETS].data_ptr(), d_Z.data_ptr(), d_F.data_ptr(), d_U.data_ptr(),
+                              d_box.data_ptr(), sync=True)
+        a, b = pot0.last_force_ms()
+        t_fresh += a + b
+    pot0.close()
+
+    # e2e: host buffers through the plugin call (H2D + kernels + D2H inside the timed region)
+    h_R = [np.ascontiguousarray(sets[k].reshape(W, 3 * N)) for k in range(N_POSITION_SETS)]
+    for k in range(2):
+        pot.forceBatch(W, N, h_R[k % N_POSITION_SETS], struct.atomic_nrs, struct.cell.reshape(9))
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        pot.forceBatch(W, N, h_R[k % N_POSITION_SETS], struct.atomic_nrs, struct.cell.reshape(9))
+    torch.cuda.synchronize()
+    e2e_s = reduce_max(time.perf_counter() - t0)
+    e2e_value = units / e2e_s
+    h2d = W * (3 * N * 8 + (3 * N % 2) * 8 + N * 4 + 72)
+    d2h = W * (3 * N * 8 + (3 * N % 2) * 8 + 8)
+
+    # roofline of the dominant kernel (k_force_batch): algorithmic flops / measured kernel time
+    ms_kernel = dev_ms / args.steps
+    flops = eam_flops(pairs_per_step, W * N)
+    achieved = flops / (ms_kernel * 1e-3) / 1e12
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    hbm_achieved = eam_min_bytes(pairs_per_step, W * N) / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "fp64", "kernel": "k_force_batch", "achieved": achieved, "peak": fp64_peak / 1e12,
+                "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": None,
+                "peak_source": "DFMA microbenchmark k_dfma_peak measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
+                "algorithmic_flops_per_launch": flops, "ordered_pairs_per_launch": pairs_per_step,
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                        "peak_source": hbm_src}}
+
+    # device-resident saddle searches (secondary metric)
+    search = None
+    if not args.no_search:
+        s2, scale = search_workload()
+        spot = B200Potential("eam", device=local_rank, skin=args.skin, conservative=True)
+        wk = Walkers(spot, s2.atomic_nrs, s2.fixed, s2.cell, np.broadcast_to(s2.positions.reshape(1, -1), (W, 3 * N)).copy())
+        wk.relax(search_params(opt_method=1, opt_converged_force=1e-4))
+        hmin = wk.harvest()
+        Rmin, E0 = hmin.positions[0], float(hmin.energies[0])
+        cfg = dict(WL.AKMC_AL)
+        R = np.empty((W, N, 3))
+        M = np.empty((W, N, 3))
+        for k in range(W):
+            R[k], M[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"], cfg["seed"] + first + k)
+        wk.set(positions=R, modes=M)
+        prm = search_params(**SEARCH_PARAMS)
+        l0 = spot.kernelLaunches
+        barrier()
+        wk.saddle_search(prm, E0)
+        ms = reduce_max(wk.last_ms)
+        h = wk.harvest(geometry=False)
+        good = reduce_sum(float((h.status == 0).sum()))
+        fcalls = reduce_sum(float(h.force_calls.sum()))
+        search = {"searches_per_hour": good / (ms * 1e-3) * 3600.0, "unit": "status-0 saddle searches/hour",
+                  "walkers": int(W * world), "status_good": int(good), "ms": ms,
+                  "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(h.status, return_counts=True))},
+                  "force_calls": int(fcalls), "atom_force_evals_per_s": fcalls * N / (ms * 1e-3),
+                  "gpu_launches": int(spot.kernelLaunches - l0),
+                  "config": "akmc-al geometry scaled to a0 of the in-tree EAM Au row, dimer (cg rotation) + LBFGS 1e-4, "
+                            "displace radius 5.0 / magnitude 0.2 around the adatom"}
+        if rank == 0 and not args.no_cpu:
+            cpu_s, _ = cpu_search_baseline(s2, Rmin, E0, max(8, os.cpu_count() or 1))
+            search["cpu_baseline"] = cpu_s
+        wk.close()
+        spot.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _, _ = cpu_force_baseline(struct, sets[0], 1.0, True)
+
+    if rank == 0:
+        line = {"metric": "atom-force-evals/sec", "value": value, "unit": "atom-force-evals/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "examples/akmc-al: 385 Al atoms (128 fixed), in-tree EAM Al row, "
+                                       f"{W} walkers per GPU, jitter U(-{JITTER},{JITTER}) A, {N_POSITION_SETS} position sets",
+                           "walkers_per_gpu": W, "n_atoms": N, "l2": "flushed before every step (512 MiB memset outside the events)",
+                           "neighbour_list": f"Verlet skin {args.skin} A, cached; lists rebuilt inside the timed region: {rebuilt}",
+                           "parallelism": f"walker-sharded x{world}, no collective"},
+                "clocks": clocks, "e2e": {"value": e2e_value, "unit": "atom-force-evals/s", "h2d_bytes_per_step": h2d,
+                                          "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+                "gpu_launches": int(launches), "roofline": roofline,
+                "extra": {"wall_s_timed_region": t_wall, "value_hot_l2": units / world / (t_hot * 1e-3),
+                          "value_fresh_list_every_step": units / world / (t_fresh * 1e-3),
+                          "fp64_peak_tflops_measured": fp64_peak / 1e12},
+                "search": search}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    pot.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skin", type=float, default=1.0)
+    ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

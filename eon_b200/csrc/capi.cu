@@ -1,0 +1,1052 @@
+// capi.cu -- the C ABI of libeonb200.so (include/eonb200.h): handles, HBM residency, launches.
+//
+// Host logic only; every floating-point result comes from the kernels in kernels.cuh.  There is
+// no CPU evaluation path: without a usable CUDA device eonb200_create fails.
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace eonb200;
+
+namespace {
+
+const EonB200EamRow kBuiltinRows[3] = {
+    // include/eon/potentials/EAM/Parameters.h:15-50 (Z, Dm, alphaM, Rm, beta1, beta2, r_cut, c0..c8)
+    {13, 3.63262, 1.49303, 2.12396, 3.45762, 3.54208, 5.555,
+     {-0.0847305, 17.0887, 60.7909, -75.8412, 39.9948, -6.21563, -3.07993, 1.51365, -0.196034}},
+    {46, 1.6054, 1.55083, 2.35604, 3.35148, 3.34715, 5.4120,
+     {0.0992627, 4.8356, -0.368647, 17.2739, -18.450, 9.5018, -2.69876, 0.405341, -0.0251768}},
+    {79, 0.669134, 1.89707, 2.57021, 3.69785, 3.69674, 5.5155,
+     {-0.198791, -27.7663, 224.068, -594.101, 1316.31, -2070.62, 1973.14, -1012.02, 214.373}}};
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  // grow-only; contents are NOT preserved
+  cudaError_t reserve(size_t count) {
+    if (count <= n) return cudaSuccess;
+    release();
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  ~PinBuf() {
+    if (p) cudaFreeHost(p);
+  }
+  cudaError_t reserve(size_t count) {
+    if (count <= n) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    n = 0;
+    cudaError_t e = cudaMallocHost(reinterpret_cast<void **>(&p), std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+};
+
+struct NlStore {
+  DevBuf<int> nbr, cnt, state;
+  DevBuf<double> rbuild;
+  long S = 0, N = 0;
+  int K = 0, Np = 0;
+};
+
+}  // namespace
+
+struct EonB200Pot {
+  EonB200Config cfg;
+  PotParams hp;
+  std::vector<EonB200EamRow> rows;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  DevBuf<PotParams> dP;
+  DevBuf<int> d_overflow;
+  DevBuf<unsigned long long> d_stats;
+  PinBuf<unsigned long long> h_stats;
+  PinBuf<int> h_overflow;
+  // stateless batch staging
+  DevBuf<double> dR, dF, dU, dbox;
+  DevBuf<int> dZ;
+  PinBuf<double> hR, hF, hU, hbox;
+  PinBuf<int> hZ;
+  std::vector<double> last_boxes;
+  NlStore nl;  // cache of the stateless batch slots
+  unsigned long long force_calls = 0, launches = 0;
+  long long last_stats[5] = {0, 0, 0, 0, 0};
+  double last_ms[2] = {0.0, 0.0};
+  int max_dyn_smem = 0;
+  int split_kernels = 0;
+  std::string err;
+};
+
+struct EonB200Walkers {
+  EonB200Pot *pot = nullptr;
+  long W = 0, N = 0;
+  int D = 0, Dp = 0, nfree = 0, any_fixed = 0;
+  DevBuf<double> pos, frc, mode, energy, ws, mask, box, react, eig, conv;
+  DevBuf<int> dirty, free_atoms, Z, status;
+  DevBuf<long long> iters, fcalls;
+  DevBuf<EonB200SearchParams> prm;
+  NlStore nl;
+  size_t ws_stride = 0;
+  size_t off_lbfgs_s = 0, off_lbfgs_y = 0, off_lanczos_q = 0, off_rot_s = 0, off_rot_y = 0;
+  std::vector<double> h_box;
+  double last_ms = 0.0;
+  bool have_modes = false;
+};
+
+namespace {
+
+int fail(EonB200Pot *pot, int rc, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (pot) pot->err = buf;
+  return rc;
+}
+
+#define CU_TRY(pot, call)                                                                      \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) return fail((pot), 700 + static_cast<int>(e_), "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+void fill_params(EonB200Pot *pot) {
+  const EonB200Config &c = pot->cfg;
+  PotParams &P = pot->hp;
+  memset(&P, 0, sizeof(P));
+  P.kind = c.kind;
+  P.lj_u0 = c.lj_u0;
+  P.lj_psi = c.lj_psi;
+  P.morse_De = c.morse_De;
+  P.morse_a = c.morse_a;
+  P.morse_re = c.morse_re;
+  P.eam_conservative = c.eam_conservative;
+  P.skin = c.skin;
+  P.cutoff = c.cutoff;
+  P.eshift = 0.0;
+  if (c.kind == EONB200_POT_EAM) {
+    P.nl_mode = NL_MIC;
+    P.n_rows = static_cast<int>(pot->rows.size());
+    double rcmax = 0.0;
+    for (int r = 0; r < P.n_rows; r++) {
+      const EonB200EamRow &s = pot->rows[r];
+      EamRowDev &d = P.rows[r];
+      d.Z = s.Z;
+      d.Dm = s.Dm;
+      d.alphaM = s.alphaM;
+      d.Rm = s.Rm;
+      d.beta1 = s.beta1;
+      d.beta2 = s.beta2;
+      d.r_cut = s.r_cut;
+      d.rc2 = s.r_cut * s.r_cut;
+      for (int k = 0; k < 9; k++) {
+        d.c[k] = s.func_coeff[k];
+        d.dc[k] = k * s.func_coeff[k];
+      }
+      rcmax = std::max(rcmax, s.r_cut);
+    }
+    P.cutoff = rcmax;
+  } else {
+    P.nl_mode = NL_VESIN;
+    const double rc = P.cutoff;
+    if (c.kind == EONB200_POT_LJ) {
+      const double s6 = std::pow(P.lj_psi / rc, 6);
+      P.eshift = 4.0 * P.lj_u0 * (s6 * s6 - s6);
+    } else if (c.kind == EONB200_POT_MORSE_PT) {
+      const double d = 1.0 - std::exp(-P.morse_a * (rc - P.morse_re));
+      P.eshift = P.morse_De * d * d - P.morse_De;
+    }
+  }
+  P.cutoff2 = P.cutoff * P.cutoff;
+  P.rc_list = P.cutoff + P.skin;
+  P.rc_list2 = P.rc_list * P.rc_list;
+}
+
+int pick_lpa(const EonB200Pot *pot, long N, int threads_cap) {
+  (void)pot;
+#ifdef EONB200_EMU
+  (void)N;
+  (void)threads_cap;
+  return 1;
+#else
+  int lpa = 1;
+  while (lpa < 8 && N * (lpa * 2) <= threads_cap) lpa *= 2;
+  return lpa;
+#endif
+}
+
+int pick_threads(const EonB200Pot *pot, long N, int lpa) {
+#ifdef EONB200_EMU
+  (void)pot;
+  (void)N;
+  (void)lpa;
+  return 1;
+#else
+  if (pot->cfg.threads_per_walker > 0) {
+    int t = (pot->cfg.threads_per_walker + 31) / 32 * 32;
+    return std::min(std::max(t, 32), 512);
+  }
+  long t = (N * lpa + 31) / 32 * 32;
+  return static_cast<int>(std::min<long>(std::max<long>(t, 32), 512));
+#endif
+}
+
+int pick_max_cells(long N) { return static_cast<int>(std::min<long>(std::max<long>(64, N), 4096)); }
+
+// Row capacity guess from the mean density; truncated builds are detected and regrown.
+int guess_K(double rc, long N, const double *box) {
+  const double *m = box;
+  const double det = std::fabs(m[0] * (m[4] * m[8] - m[7] * m[5]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+                               m[2] * (m[3] * m[7] - m[4] * m[6]));
+  double expect = det > 1e-30 ? static_cast<double>(N) / det * (4.0 / 3.0) * kPi * rc * rc * rc : static_cast<double>(N);
+  long K = static_cast<long>(std::ceil(1.5 * expect)) + 16;
+  K = std::min<long>(K, std::max<long>(N - 1, 16) + 32);
+  K = (K + 3) / 4 * 4;
+  return static_cast<int>(std::max<long>(K, 8));
+}
+
+int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K) {
+  const int Np = static_cast<int>((N + 31) / 32 * 32);
+  CU_TRY(pot, nl.nbr.reserve(static_cast<size_t>(S) * K * Np));
+  CU_TRY(pot, nl.cnt.reserve(static_cast<size_t>(S) * Np));
+  CU_TRY(pot, nl.rbuild.reserve(static_cast<size_t>(S) * 3 * N));
+  CU_TRY(pot, nl.state.reserve(static_cast<size_t>(S)));
+  CU_TRY(pot, cudaMemsetAsync(nl.state.p, 0, sizeof(int) * S, pot->stream));
+  nl.S = S;
+  nl.N = N;
+  nl.K = K;
+  nl.Np = Np;
+  return 0;
+}
+
+NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
+  NlBatch b;
+  b.nbr = nl.nbr.p;
+  b.cnt = nl.cnt.p;
+  b.rbuild = nl.rbuild.p;
+  b.state = nl.state.p;
+  b.K = nl.K;
+  b.Np = nl.Np;
+  b.overflow = pot->d_overflow.p;
+  b.stats = pot->d_stats.p;
+  return b;
+}
+
+int check_smem(EonB200Pot *pot, long N, int maxCells, size_t *bytes) {
+  *bytes = smem_bytes(static_cast<int>(N), maxCells);
+  if (static_cast<long>(*bytes) > pot->max_dyn_smem)
+    return fail(pot, 3, "system of %ld atoms needs %zu bytes of shared memory per walker CTA (limit %d)", N, *bytes,
+                pot->max_dyn_smem);
+  return 0;
+}
+
+// Launch the batched force evaluation on device-resident arrays; handles truncated lists by
+// regrowing the row capacity and re-running.  Synchronises when it has to look at the flags.
+int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double *h_box0, bool sync_and_check) {
+  const long S = a.S, N = a.N;
+  if (nl.S < S || nl.N != N || nl.K == 0) {
+    double unit[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const int K = std::max(nl.N == N ? nl.K : 0, guess_K(pot->hp.rc_list, N, h_box0 ? h_box0 : unit));
+    int rc = nl_alloc(pot, nl, S, N, K);
+    if (rc) return rc;
+  }
+  a.maxCells = pick_max_cells(N);
+  a.lpa = pick_lpa(pot, N, 512);
+  const int threads = pick_threads(pot, N, a.lpa);
+  size_t smem;
+  int rc = check_smem(pot, N, a.maxCells, &smem);
+  if (rc) return rc;
+  for (int attempt = 0; attempt < 6; attempt++) {
+    CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
+    CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
+    NlBatch view = nl_view(pot, nl);
+    CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
+    if (pot->split_kernels) {
+      ForceBatchArgs a1 = a;
+      a1.mode = FM_ENSURE;
+      EONB200_LAUNCH(k_force_batch, static_cast<unsigned>(S), threads, smem, pot->stream, pot->dP.p, view, a1);
+      CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
+      ForceBatchArgs a2 = a;
+      a2.mode = FM_FORCE;
+      a2.force_rebuild = 0;
+      EONB200_LAUNCH(k_force_batch, static_cast<unsigned>(S), threads, smem, pot->stream, pot->dP.p, view, a2);
+      pot->launches += 2;
+    } else {
+      a.mode = FM_BOTH;
+      CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
+      EONB200_LAUNCH(k_force_batch, static_cast<unsigned>(S), threads, smem, pot->stream, pot->dP.p, view, a);
+      pot->launches += 1;
+    }
+    CU_TRY(pot, cudaEventRecord(pot->ev[2], pot->stream));
+    CU_TRY(pot, cudaGetLastError());
+    pot->force_calls += static_cast<unsigned long long>(S);
+    if (!sync_and_check) return 0;
+    CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
+    CU_TRY(pot, cudaMemcpyAsync(pot->h_stats.p, pot->d_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                pot->stream));
+    CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+    float ms0 = 0, ms1 = 0;
+    cudaEventElapsedTime(&ms0, pot->ev[0], pot->ev[1]);
+    cudaEventElapsedTime(&ms1, pot->ev[1], pot->ev[2]);
+    pot->last_ms[0] = ms0;
+    pot->last_ms[1] = ms1;
+    const int need = pot->h_overflow.p[0];
+    pot->last_stats[0] = static_cast<long long>(pot->h_stats.p[0]);
+    pot->last_stats[1] = static_cast<long long>(pot->h_stats.p[1]);
+    pot->last_stats[2] = nl.K;
+    pot->last_stats[3] = need;
+    pot->last_stats[4] = static_cast<long long>(pot->h_stats.p[2]);
+    if (need <= nl.K) return 0;
+    if (need >= (1 << 30))
+      return fail(pot, 100, "neighbour image shift outside the representable range (box much smaller than the cutoff)");
+    pot->force_calls -= static_cast<unsigned long long>(S);
+    const int K = (static_cast<int>(need * 1.2) + 8 + 3) / 4 * 4;
+    nl.K = 0;
+    rc = nl_alloc(pot, nl, S, N, K);
+    if (rc) return rc;
+    a.force_rebuild = 1;
+  }
+  return fail(pot, 100, "neighbour list capacity did not converge");
+}
+
+}  // namespace
+
+extern "C" {
+
+void eonb200_config_default(EonB200Config *cfg, int kind) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->kind = kind;
+  cfg->lj_u0 = 1.0;
+  cfg->lj_psi = 1.0;
+  cfg->morse_De = 0.7102;
+  cfg->morse_a = 1.6047;
+  cfg->morse_re = 2.8970;
+  if (kind == EONB200_POT_LJ || kind == EONB200_POT_LJCLUSTER) cfg->cutoff = 15.0;
+  if (kind == EONB200_POT_MORSE_PT) cfg->cutoff = 9.5;
+  cfg->skin = 1.0;
+}
+
+int eonb200_abi_version(void) { return EONB200_ABI_VERSION; }
+
+EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t errlen) {
+  auto bail = [&](const std::string &msg) -> EonB200Pot * {
+    if (errbuf && errlen > 0) {
+      strncpy(errbuf, msg.c_str(), errlen - 1);
+      errbuf[errlen - 1] = 0;
+    }
+    return nullptr;
+  };
+  if (!cfg_in) return bail("eonb200_create: null config");
+  EonB200Config cfg = *cfg_in;
+  if (cfg.kind < EONB200_POT_LJ || cfg.kind > EONB200_POT_EAM) return bail("eonb200_create: unknown potential kind");
+  EonB200Config def;
+  eonb200_config_default(&def, cfg.kind);
+  if (cfg.cutoff <= 0) cfg.cutoff = def.cutoff;
+  if (cfg.lj_u0 <= 0) cfg.lj_u0 = def.lj_u0;
+  if (cfg.lj_psi <= 0) cfg.lj_psi = def.lj_psi;
+  if (cfg.morse_De == 0 && cfg.morse_a == 0 && cfg.morse_re == 0) {
+    cfg.morse_De = def.morse_De;
+    cfg.morse_a = def.morse_a;
+    cfg.morse_re = def.morse_re;
+  }
+  if (cfg.skin < 0) cfg.skin = 1.0;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0)
+    return bail(std::string("eonb200_create: no CUDA device (") + cudaGetErrorString(e) +
+                "); this backend has no CPU fallback");
+  if (cfg.device < 0 || cfg.device >= ndev) return bail("eonb200_create: device ordinal out of range");
+  if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, cfg.device)) != cudaSuccess)
+    return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+  if (prop.major < 10) return bail("eonb200_create: device is not sm_100 class; libeonb200 is built for sm_100a only");
+
+  EonB200Pot *pot = new EonB200Pot();
+  pot->cfg = cfg;
+  pot->device = cfg.device;
+  if (cfg.kind == EONB200_POT_EAM) {
+    if (cfg.n_eam_rows > 0 && cfg.eam_rows) {
+      if (cfg.n_eam_rows > kMaxEamRows) {
+        delete pot;
+        return bail("eonb200_create: too many EAM rows");
+      }
+      pot->rows.assign(cfg.eam_rows, cfg.eam_rows + cfg.n_eam_rows);
+    } else {
+      pot->rows.assign(kBuiltinRows, kBuiltinRows + 3);
+    }
+  }
+  pot->cfg.eam_rows = nullptr;
+  fill_params(pot);
+  bool ok = cudaStreamCreate(&pot->stream) == cudaSuccess;
+  for (int k = 0; k < 3 && ok; k++) ok = cudaEventCreate(&pot->ev[k]) == cudaSuccess;
+  ok = ok && pot->dP.reserve(1) == cudaSuccess && pot->d_overflow.reserve(1) == cudaSuccess &&
+       pot->d_stats.reserve(4) == cudaSuccess && pot->h_stats.reserve(4) == cudaSuccess &&
+       pot->h_overflow.reserve(1) == cudaSuccess;
+  ok = ok && cudaMemcpy(pot->dP.p, &pot->hp, sizeof(PotParams), cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    // opt in to the full shared memory of the SM for the walker kernels
+    cudaFuncAttributes fa;
+    int limit = static_cast<int>(prop.sharedMemPerBlockOptin);
+    int worst_static = 0;
+    if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(k_walkers)) == cudaSuccess)
+      worst_static = std::max<int>(worst_static, static_cast<int>(fa.sharedSizeBytes));
+    if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(k_force_batch)) == cudaSuccess)
+      worst_static = std::max<int>(worst_static, static_cast<int>(fa.sharedSizeBytes));
+    pot->max_dyn_smem = limit - worst_static - 1024;
+    ok = cudaFuncSetAttribute(reinterpret_cast<const void *>(k_walkers), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_force_batch),
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_neighbors), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess;
+  }
+  if (!ok) {
+    std::string msg = std::string("eonb200_create: CUDA setup failed: ") + cudaGetErrorString(cudaGetLastError());
+    eonb200_destroy(pot);
+    return bail(msg);
+  }
+  return pot;
+}
+
+void eonb200_destroy(EonB200Pot *pot) {
+  if (!pot) return;
+  cudaSetDevice(pot->device);
+  if (pot->stream) cudaStreamSynchronize(pot->stream);
+  for (int k = 0; k < 3; k++)
+    if (pot->ev[k]) cudaEventDestroy(pot->ev[k]);
+  if (pot->stream) cudaStreamDestroy(pot->stream);
+  delete pot;
+}
+
+const char *eonb200_last_error(const EonB200Pot *pot) { return pot ? pot->err.c_str() : "null handle"; }
+unsigned long long eonb200_force_calls(const EonB200Pot *pot) { return pot ? pot->force_calls : 0; }
+unsigned long long eonb200_kernel_launches(const EonB200Pot *pot) { return pot ? pot->launches : 0; }
+
+int eonb200_nl_stats(EonB200Pot *pot, long long out[5]) {
+  if (!pot) return 1;
+  for (int k = 0; k < 5; k++) out[k] = pot->last_stats[k];
+  return 0;
+}
+
+int eonb200_last_force_ms(EonB200Pot *pot, double out[2]) {
+  if (!pot) return 1;
+  out[0] = pot->last_ms[0];
+  out[1] = pot->last_ms[1];
+  return 0;
+}
+
+int eonb200_set_split_kernels(EonB200Pot *pot, int split) {
+  if (!pot) return 1;
+  pot->split_kernels = split;
+  return 0;
+}
+
+int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *positions, const int *const *atomicNrs,
+                        double *const *forces, double *energies, double *variances, const double *const *boxes) {
+  if (!pot) return 1;
+  if (S <= 0 || N <= 0) return fail(pot, 2, "force_batch: nSystems and nAtoms must be positive");
+  if (N > kNbrIndexMask) return fail(pot, 2, "force_batch: more than %d atoms per system", kNbrIndexMask);
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  // unknown element -> 14324 (EAM.cpp:116-123)
+  if (pot->cfg.kind == EONB200_POT_EAM) {
+    for (long s = 0; s < S; s++)
+      for (long i = 0; i < N; i++) {
+        const int z = atomicNrs[s][i];
+        bool found = false;
+        for (const auto &r : pot->rows) found = found || r.Z == z;
+        if (!found) return fail(pot, 14324, "EAM: no parameter row for atomic number %d", z);
+      }
+  }
+  const size_t D = 3 * static_cast<size_t>(N);
+  const size_t strideR = (D + 1) / 2 * 2;  // even: every system starts 16-byte aligned
+  CU_TRY(pot, pot->dR.reserve(S * strideR));
+  CU_TRY(pot, pot->dF.reserve(S * strideR));
+  CU_TRY(pot, pot->dU.reserve(S));
+  CU_TRY(pot, pot->dbox.reserve(S * 9));
+  CU_TRY(pot, pot->dZ.reserve(S * N));
+  CU_TRY(pot, pot->hR.reserve(S * strideR));
+  CU_TRY(pot, pot->hF.reserve(S * strideR));
+  CU_TRY(pot, pot->hU.reserve(S));
+  CU_TRY(pot, pot->hbox.reserve(S * 9));
+  CU_TRY(pot, pot->hZ.reserve(S * N));
+  bool box_changed = pot->last_boxes.size() != static_cast<size_t>(S) * 9;
+  for (long s = 0; s < S; s++) {
+    memcpy(pot->hR.p + s * strideR, positions[s], D * sizeof(double));
+    if (strideR > D) pot->hR.p[s * strideR + D] = 0.0;
+    memcpy(pot->hZ.p + s * N, atomicNrs[s], N * sizeof(int));
+    memcpy(pot->hbox.p + s * 9, boxes[s], 9 * sizeof(double));
+  }
+  if (!box_changed) box_changed = memcmp(pot->last_boxes.data(), pot->hbox.p, S * 9 * sizeof(double)) != 0;
+  if (box_changed) pot->last_boxes.assign(pot->hbox.p, pot->hbox.p + S * 9);
+  CU_TRY(pot, cudaMemcpyAsync(pot->dR.p, pot->hR.p, S * strideR * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->dZ.p, pot->hZ.p, S * N * sizeof(int), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->dbox.p, pot->hbox.p, S * 9 * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  ForceBatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.S = static_cast<int>(S);
+  a.N = static_cast<int>(N);
+  a.R = pot->dR.p;
+  a.strideR = static_cast<int>(strideR);
+  a.Z = pot->dZ.p;
+  a.strideZ = static_cast<int>(N);
+  a.box = pot->dbox.p;
+  a.strideBox = 9;
+  a.F = pot->dF.p;
+  a.U = pot->dU.p;
+  a.force_rebuild = box_changed ? 1 : 0;
+  int rc = run_force_batch(pot, pot->nl, a, pot->hbox.p, true);
+  if (rc) return rc;
+  CU_TRY(pot, cudaMemcpyAsync(pot->hF.p, pot->dF.p, S * strideR * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->hU.p, pot->dU.p, S * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+  CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+  for (long s = 0; s < S; s++) {
+    memcpy(forces[s], pot->hF.p + s * strideR, D * sizeof(double));
+    energies[s] = pot->hU.p[s];
+    if (variances) variances[s] = 0.0;
+  }
+  return 0;
+}
+
+int eonb200_force(EonB200Pot *pot, long N, const double *positions, const int *atomicNrs, double *forces, double *energy,
+                  double *variance, const double *box) {
+  const double *R[1] = {positions};
+  const int *Z[1] = {atomicNrs};
+  double *F[1] = {forces};
+  const double *B[1] = {box};
+  double var = 0.0;
+  int rc = eonb200_force_batch(pot, 1, N, R, Z, F, energy, &var, B);
+  if (variance) *variance = var;
+  return rc;
+}
+
+int eonb200_force_batch_device(EonB200Pot *pot, long S, long N, const double *d_positions, const int *d_atomicNrs,
+                               double *d_forces, double *d_energies, const double *d_boxes, int sync) {
+  if (!pot) return 1;
+  if (S <= 0 || N <= 0) return fail(pot, 2, "force_batch_device: nSystems and nAtoms must be positive");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  ForceBatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.S = static_cast<int>(S);
+  a.N = static_cast<int>(N);
+  a.R = d_positions;
+  a.strideR = static_cast<int>(3 * N);
+  a.Z = d_atomicNrs;
+  a.strideZ = static_cast<int>(N);
+  a.box = d_boxes;
+  a.strideBox = 9;
+  a.F = d_forces;
+  a.U = d_energies;
+  a.force_rebuild = 0;
+  double hb[9];
+  const double *hb0 = nullptr;
+  if (pot->nl.S < S || pot->nl.N != N) {
+    CU_TRY(pot, cudaMemcpy(hb, d_boxes, sizeof(hb), cudaMemcpyDeviceToHost));
+    hb0 = hb;
+  }
+  return run_force_batch(pot, pot->nl, a, hb0, sync != 0);
+}
+
+// ---- neighbour lists ---------------------------------------------------------------------------------------
+int eonb200_neighbors(EonB200Pot *pot, long S, long N, const double *positions, const double *boxes,
+                      const int periodic[3], double cutoff, int full, long cap, long *pair_offsets, int64_t *pairs,
+                      int32_t *shifts, double *distances, double *vectors, long *n_pairs) {
+  if (!pot) return 1;
+  if (S <= 0 || N <= 0 || !(cutoff > 0)) return fail(pot, 2, "neighbors: bad arguments");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  DevBuf<double> dR, dB;
+  CU_TRY(pot, dR.reserve(S * 3 * N));
+  CU_TRY(pot, dB.reserve(S * 9));
+  CU_TRY(pot, cudaMemcpyAsync(dR.p, positions, S * 3 * N * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(dB.p, boxes, S * 9 * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  NlParams np;
+  np.mode = NL_VESIN;
+  np.rc = cutoff;
+  np.rc2 = cutoff * cutoff;
+  np.skin = 0.0;
+  for (int k = 0; k < 3; k++) np.per[k] = periodic ? (periodic[k] != 0) : 1;
+  NlStore nl;
+  int K = guess_K(cutoff, N, boxes);
+  const int maxCells = pick_max_cells(N);
+  const int threads = pick_threads(pot, N, 1);
+  size_t smem;
+  int rc = check_smem(pot, N, maxCells, &smem);
+  if (rc) return rc;
+  for (int attempt = 0;; attempt++) {
+    if (attempt >= 6) return fail(pot, 100, "neighbors: list capacity did not converge");
+    rc = nl_alloc(pot, nl, S, N, K);
+    if (rc) return rc;
+    CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
+    CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
+    NlBatch view = nl_view(pot, nl);
+    EONB200_LAUNCH(k_neighbors, static_cast<unsigned>(S), threads, smem, pot->stream, view, np, static_cast<int>(S),
+                   static_cast<int>(N), dR.p, dB.p, maxCells);
+    pot->launches += 1;
+    CU_TRY(pot, cudaGetLastError());
+    CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
+    CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+    const int need = pot->h_overflow.p[0];
+    if (need >= (1 << 30)) return fail(pot, 100, "neighbors: image shift outside the representable range");
+    if (need <= K) break;
+    K = (need + 3) / 4 * 4;
+    nl.K = 0;
+  }
+  std::vector<int> hn(static_cast<size_t>(S) * nl.K * nl.Np), hc(static_cast<size_t>(S) * nl.Np);
+  CU_TRY(pot, cudaMemcpy(hn.data(), nl.nbr.p, hn.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  CU_TRY(pot, cudaMemcpy(hc.data(), nl.cnt.p, hc.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  long total = 0;
+  for (long s = 0; s < S; s++) {
+    if (pair_offsets) pair_offsets[s] = total;
+    const double *R = positions + s * 3 * N, *H = boxes + s * 9;
+    for (long i = 0; i < N; i++) {
+      const int n = hc[s * nl.Np + i];
+      for (int k = 0; k < n; k++) {
+        int j, sx, sy, sz;
+        unpack_nbr(hn[(static_cast<size_t>(s) * nl.K + k) * nl.Np + i], j, sx, sy, sz);
+        if (!full) {
+          // half-list rule, vesin-single-build.cpp:1165-1196
+          if (i > j) continue;
+          if (i == j) {
+            const int sum = sx + sy + sz;
+            if (sum < 0) continue;
+            if (sum == 0 && (sz < 0 || (sz == 0 && sy < 0))) continue;
+          }
+        }
+        if (total < cap) {
+          if (pairs) {
+            pairs[2 * total] = i;
+            pairs[2 * total + 1] = j;
+          }
+          if (shifts) {
+            shifts[3 * total] = sx;
+            shifts[3 * total + 1] = sy;
+            shifts[3 * total + 2] = sz;
+          }
+          if (distances || vectors) {
+            // same un-fused order as the device predicate (host code is compiled without contraction)
+            const volatile double tx = (sx * H[0] + sy * H[3]) + sz * H[6];
+            const volatile double ty = (sx * H[1] + sy * H[4]) + sz * H[7];
+            const volatile double tz = (sx * H[2] + sy * H[5]) + sz * H[8];
+            const volatile double vx = (R[3 * j] - R[3 * i]) + tx;
+            const volatile double vy = (R[3 * j + 1] - R[3 * i + 1]) + ty;
+            const volatile double vz = (R[3 * j + 2] - R[3 * i + 2]) + tz;
+            if (vectors) {
+              vectors[3 * total] = vx;
+              vectors[3 * total + 1] = vy;
+              vectors[3 * total + 2] = vz;
+            }
+            if (distances) {
+              const volatile double xx = vx * vx, yy = vy * vy, zz = vz * vz;
+              const volatile double s2 = xx + yy;
+              distances[total] = std::sqrt(s2 + zz);
+            }
+          }
+        }
+        total++;
+      }
+    }
+  }
+  if (pair_offsets) pair_offsets[S] = total;
+  if (n_pairs) *n_pairs = total;
+  return 0;
+}
+
+// ---- resident walkers --------------------------------------------------------------------------------------------
+void eonb200_search_params_default(EonB200SearchParams *p) {
+  memset(p, 0, sizeof(*p));
+  p->finite_difference = 0.01;
+  p->remove_net_force = 1;
+  p->opt_method = EONB200_OPT_CG;
+  p->convergence_metric = EONB200_METRIC_NORM;
+  p->opt_max_iterations = 1000;
+  p->max_move = 0.2;
+  p->opt_converged_force = 0.01;
+  p->time_step = 1.0 / 10.1805055;
+  p->max_time_step = 2.5 / 10.1805055;
+  p->lbfgs_memory = 20;
+  p->lbfgs_inverse_curvature = 0.01;
+  p->lbfgs_auto_scale = 1;
+  p->lbfgs_angle_reset = 1;
+  p->lbfgs_distance_reset = 1;
+  p->dimer_opt_method = EONB200_ROT_CG;
+  p->dimer_converged_angle = 5.0;
+  p->dimer_rotations_max = 10;
+  p->lanczos_tolerance = 0.01;
+  p->lanczos_max_iterations = 20;
+  p->lanczos_quit_early = 1;
+  p->minmode_method = EONB200_MINMODE_DIMER;
+  p->saddle_max_iterations = 1000;
+  p->saddle_max_energy = 20.0;
+}
+
+EonB200Walkers *eonb200_walkers_create(EonB200Pot *pot, long W, long N, const int *atomicNrs, const int *fixed,
+                                       const double *box, const double *positions, const double *modes, char *errbuf,
+                                       size_t errlen) {
+  auto bail = [&](const std::string &msg) -> EonB200Walkers * {
+    if (errbuf && errlen > 0) {
+      strncpy(errbuf, msg.c_str(), errlen - 1);
+      errbuf[errlen - 1] = 0;
+    }
+    return nullptr;
+  };
+  if (!pot || W <= 0 || N <= 0 || !atomicNrs || !box || !positions) return bail("walkers_create: bad arguments");
+  if (N > kNbrIndexMask) return bail("walkers_create: too many atoms per walker");
+  if (pot->cfg.kind == EONB200_POT_EAM) {
+    for (long i = 0; i < N; i++) {
+      bool found = false;
+      for (const auto &r : pot->rows) found = found || r.Z == atomicNrs[i];
+      if (!found) return bail("walkers_create: EAM has no parameter row for an element (14324)");
+    }
+  }
+  cudaSetDevice(pot->device);
+  EonB200Walkers *w = new EonB200Walkers();
+  w->pot = pot;
+  w->W = W;
+  w->N = N;
+  w->D = static_cast<int>(3 * N);
+  w->Dp = (w->D + 1) / 2 * 2;
+  std::vector<double> mask(w->Dp, 0.0);
+  std::vector<int> free_atoms;
+  for (long i = 0; i < N; i++) {
+    bool all_fixed = true;
+    for (int k = 0; k < 3; k++) {
+      const bool fx = fixed && fixed[3 * i + k] != 0;
+      mask[3 * i + k] = fx ? 0.0 : 1.0;
+      if (fx) w->any_fixed = 1;
+      all_fixed = all_fixed && fx;
+    }
+    if (!all_fixed) free_atoms.push_back(static_cast<int>(i));
+  }
+  w->nfree = static_cast<int>(free_atoms.size());
+  w->h_box.assign(box, box + 9);
+  const size_t WD = static_cast<size_t>(W) * w->Dp;
+  bool ok = w->pos.reserve(WD) == cudaSuccess && w->frc.reserve(WD) == cudaSuccess && w->mode.reserve(WD) == cudaSuccess &&
+            w->energy.reserve(W) == cudaSuccess && w->dirty.reserve(W) == cudaSuccess &&
+            w->mask.reserve(w->Dp) == cudaSuccess && w->free_atoms.reserve(std::max<size_t>(1, free_atoms.size())) == cudaSuccess &&
+            w->Z.reserve(N) == cudaSuccess && w->box.reserve(9) == cudaSuccess && w->react.reserve(W) == cudaSuccess &&
+            w->eig.reserve(W) == cudaSuccess && w->conv.reserve(W) == cudaSuccess && w->status.reserve(W) == cudaSuccess &&
+            w->iters.reserve(W) == cudaSuccess && w->fcalls.reserve(W) == cudaSuccess && w->prm.reserve(1) == cudaSuccess;
+  if (!ok) {
+    delete w;
+    return bail(std::string("walkers_create: out of device memory: ") + cudaGetErrorString(cudaGetLastError()));
+  }
+  cudaMemcpyAsync(w->mask.p, mask.data(), sizeof(double) * w->Dp, cudaMemcpyHostToDevice, pot->stream);
+  if (!free_atoms.empty())
+    cudaMemcpyAsync(w->free_atoms.p, free_atoms.data(), sizeof(int) * free_atoms.size(), cudaMemcpyHostToDevice, pot->stream);
+  cudaMemcpyAsync(w->Z.p, atomicNrs, sizeof(int) * N, cudaMemcpyHostToDevice, pot->stream);
+  cudaMemcpyAsync(w->box.p, box, sizeof(double) * 9, cudaMemcpyHostToDevice, pot->stream);
+  cudaMemsetAsync(w->status.p, 0, sizeof(int) * W, pot->stream);
+  cudaMemsetAsync(w->iters.p, 0, sizeof(long long) * W, pot->stream);
+  cudaMemsetAsync(w->fcalls.p, 0, sizeof(long long) * W, pot->stream);
+  cudaMemsetAsync(w->eig.p, 0, sizeof(double) * W, pot->stream);
+  cudaMemsetAsync(w->conv.p, 0, sizeof(double) * W, pot->stream);
+  cudaMemsetAsync(w->energy.p, 0, sizeof(double) * W, pot->stream);
+  cudaMemsetAsync(w->frc.p, 0, sizeof(double) * WD, pot->stream);
+  cudaMemsetAsync(w->mode.p, 0, sizeof(double) * WD, pot->stream);
+  cudaStreamSynchronize(pot->stream);
+  if (eonb200_walkers_set(w, positions, modes) != 0) {
+    std::string msg = pot->err;
+    delete w;
+    return bail(msg);
+  }
+  return w;
+}
+
+void eonb200_walkers_destroy(EonB200Walkers *w) {
+  if (!w) return;
+  cudaSetDevice(w->pot->device);
+  cudaStreamSynchronize(w->pot->stream);
+  delete w;
+}
+
+int eonb200_walkers_set(EonB200Walkers *w, const double *positions, const double *modes) {
+  if (!w) return 1;
+  EonB200Pot *pot = w->pot;
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  const size_t D = w->D, Dp = w->Dp;
+  if (positions) {
+    CU_TRY(pot, cudaMemcpy2DAsync(w->pos.p, Dp * sizeof(double), positions, D * sizeof(double), D * sizeof(double), w->W,
+                                  cudaMemcpyHostToDevice, pot->stream));
+    std::vector<int> ones(w->W, 1);
+    CU_TRY(pot, cudaMemcpyAsync(w->dirty.p, ones.data(), sizeof(int) * w->W, cudaMemcpyHostToDevice, pot->stream));
+    CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+  }
+  if (modes) {
+    CU_TRY(pot, cudaMemcpy2DAsync(w->mode.p, Dp * sizeof(double), modes, D * sizeof(double), D * sizeof(double), w->W,
+                                  cudaMemcpyHostToDevice, pot->stream));
+    CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+    w->have_modes = true;
+  }
+  return 0;
+}
+
+namespace {
+
+// workspace: S_COUNT vector slots + optimizer / min-mode histories, per walker
+int walkers_workspace(EonB200Walkers *w, const EonB200SearchParams *prm) {
+  EonB200Pot *pot = w->pot;
+  const size_t Dp = w->Dp;
+  size_t n = static_cast<size_t>(S_COUNT) * Dp;
+  w->off_lbfgs_s = w->off_lbfgs_y = w->off_lanczos_q = w->off_rot_s = w->off_rot_y = 0;
+  if (prm) {
+    if (prm->opt_method == EONB200_OPT_LBFGS) {
+      const long m = std::max<long>(1, std::min<long>(prm->lbfgs_memory, kMaxLbfgsMemory));
+      w->off_lbfgs_s = n;
+      n += m * Dp;
+      w->off_lbfgs_y = n;
+      n += m * Dp;
+    }
+    if (prm->minmode_method == EONB200_MINMODE_LANCZOS) {
+      const long m = std::max<long>(1, std::min<long>(prm->lanczos_max_iterations, kMaxLanczosIters));
+      w->off_lanczos_q = n;
+      n += m * Dp;
+    } else if (prm->dimer_opt_method == EONB200_ROT_LBFGS) {
+      w->off_rot_s = n;
+      n += static_cast<size_t>(kMaxRotHistory) * Dp;
+      w->off_rot_y = n;
+      n += static_cast<size_t>(kMaxRotHistory) * Dp;
+    }
+  }
+  w->ws_stride = n;
+  CU_TRY(pot, w->ws.reserve(static_cast<size_t>(w->W) * n));
+  return 0;
+}
+
+int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, int remove_net_force, double scalar) {
+  EonB200Pot *pot = w->pot;
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  EonB200SearchParams local;
+  if (!prm) {
+    eonb200_search_params_default(&local);
+    prm = &local;
+  }
+  if (prm->lanczos_max_iterations > kMaxLanczosIters && prm->minmode_method == EONB200_MINMODE_LANCZOS && job == 1)
+    return fail(pot, 2, "lanczos_max_iterations above the supported %d", kMaxLanczosIters);
+  if (prm->lbfgs_memory > kMaxLbfgsMemory && prm->opt_method == EONB200_OPT_LBFGS && job != 0)
+    return fail(pot, 2, "lbfgs_memory above the supported %d", kMaxLbfgsMemory);
+  if (prm->dimer_rotations_max >= kMaxRotHistory && prm->dimer_opt_method == EONB200_ROT_LBFGS && job == 1)
+    return fail(pot, 2, "dimer rotations_max above the supported %d for the lbfgs rotation", kMaxRotHistory - 1);
+  int rc = walkers_workspace(w, job == 0 ? nullptr : prm);
+  if (rc) return rc;
+  CU_TRY(pot, cudaMemcpyAsync(w->prm.p, prm, sizeof(*prm), cudaMemcpyHostToDevice, pot->stream));
+  const long W = w->W, N = w->N;
+  if (w->nl.S < W || w->nl.N != N || w->nl.K == 0) {
+    rc = nl_alloc(pot, w->nl, W, N, std::max(w->nl.K, guess_K(pot->hp.rc_list, N, w->h_box.data())));
+    if (rc) return rc;
+  }
+  WalkerLaunch wl;
+  wl.maxCells = pick_max_cells(N);
+  wl.lpa = pick_lpa(pot, N, 512);
+  wl.job = job;
+  wl.remove_net_force = remove_net_force;
+  wl.scalar = scalar;
+  const int threads = pick_threads(pot, N, wl.lpa);
+  size_t smem;
+  rc = check_smem(pot, N, wl.maxCells, &smem);
+  if (rc) return rc;
+  WalkerArrays wa;
+  memset(&wa, 0, sizeof(wa));
+  wa.W = static_cast<int>(W);
+  wa.N = static_cast<int>(N);
+  wa.D = w->D;
+  wa.Dp = w->Dp;
+  wa.nfree = w->nfree;
+  wa.any_fixed = w->any_fixed;
+  wa.pos = w->pos.p;
+  wa.frc = w->frc.p;
+  wa.mode = w->mode.p;
+  wa.energy = w->energy.p;
+  wa.dirty = w->dirty.p;
+  wa.ws = w->ws.p;
+  wa.ws_stride = w->ws_stride;
+  wa.off_lbfgs_s = w->off_lbfgs_s;
+  wa.off_lbfgs_y = w->off_lbfgs_y;
+  wa.off_lanczos_q = w->off_lanczos_q;
+  wa.off_rot_s = w->off_rot_s;
+  wa.off_rot_y = w->off_rot_y;
+  wa.mask = w->mask.p;
+  wa.free_atoms = w->free_atoms.p;
+  wa.Z = w->Z.p;
+  wa.box = w->box.p;
+  wa.reactant_energy = w->react.p;
+  wa.status = w->status.p;
+  wa.iterations = w->iters.p;
+  wa.force_calls = w->fcalls.p;
+  wa.eigenvalue = w->eig.p;
+  wa.convergence = w->conv.p;
+  // a job that may move atoms needs head-room in the rows: probe the fill with a force-only pass first
+  for (int attempt = 0; attempt < 6; attempt++) {
+    CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
+    CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
+    NlBatch view = nl_view(pot, w->nl);
+    CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
+    EONB200_LAUNCH(k_walkers, static_cast<unsigned>(W), threads, smem, pot->stream, pot->dP.p, view, wa, wl, w->prm.p);
+    CU_TRY(pot, cudaEventRecord(pot->ev[2], pot->stream));
+    pot->launches += 1;
+    CU_TRY(pot, cudaGetLastError());
+    CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
+    CU_TRY(pot, cudaMemcpyAsync(pot->h_stats.p, pot->d_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                pot->stream));
+    CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, pot->ev[0], pot->ev[2]);
+    w->last_ms = ms;
+    const int need = pot->h_overflow.p[0];
+    pot->last_stats[0] = static_cast<long long>(pot->h_stats.p[0]);
+    pot->last_stats[1] = static_cast<long long>(pot->h_stats.p[1]);
+    pot->last_stats[2] = w->nl.K;
+    pot->last_stats[3] = need;
+    pot->last_stats[4] = static_cast<long long>(pot->h_stats.p[2]);
+    if (need >= (1 << 30)) return fail(pot, 100, "neighbour image shift outside the representable range");
+    if ((job != 0 && job != 4) || need <= w->nl.K) {
+      // count the force calls the walkers made
+      if (job != 3 && job != 4) {
+        std::vector<long long> fc(W);
+        CU_TRY(pot, cudaMemcpy(fc.data(), w->fcalls.p, sizeof(long long) * W, cudaMemcpyDeviceToHost));
+        for (long long v : fc) pot->force_calls += static_cast<unsigned long long>(v);
+      }
+      return 0;
+    }
+    const int K = (static_cast<int>(need * 1.3) + 8 + 3) / 4 * 4;
+    w->nl.K = 0;
+    rc = nl_alloc(pot, w->nl, W, N, K);
+    if (rc) return rc;
+  }
+  return fail(pot, 100, "walkers: neighbour list capacity did not converge");
+}
+
+// Make sure the rows have head-room before a job that moves atoms: one force-only pass sizes K.
+int walkers_size_rows(EonB200Walkers *w) {
+  if (w->nl.K != 0 && w->nl.S >= w->W) {
+    return 0;
+  }
+  int rc = walkers_launch(w, 4, nullptr, 1, 0.0);  // probe: build the lists, touch nothing else
+  if (rc) return rc;
+  EonB200Pot *pot = w->pot;
+  const int fill = static_cast<int>(pot->last_stats[3]);
+  const int want = (static_cast<int>(fill * 1.3) + 8 + 3) / 4 * 4;
+  if (want > w->nl.K) {
+    w->nl.K = 0;
+    rc = nl_alloc(pot, w->nl, w->W, w->N, want);
+  }
+  return rc;
+}
+
+}  // namespace
+
+int eonb200_walkers_matter_forces(EonB200Walkers *w, int remove_net_force, double *energies, double *forces) {
+  if (!w) return 1;
+  EonB200Pot *pot = w->pot;
+  int rc = walkers_launch(w, 0, nullptr, remove_net_force, 0.0);
+  if (rc) return rc;
+  if (energies) CU_TRY(pot, cudaMemcpy(energies, w->energy.p, sizeof(double) * w->W, cudaMemcpyDeviceToHost));
+  if (forces)
+    CU_TRY(pot, cudaMemcpy2D(forces, w->D * sizeof(double), w->frc.p, w->Dp * sizeof(double), w->D * sizeof(double), w->W,
+                             cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int eonb200_walkers_saddle_search(EonB200Walkers *w, const EonB200SearchParams *prm, const double *reactant_energies) {
+  if (!w || !prm) return 1;
+  EonB200Pot *pot = w->pot;
+  if (!w->have_modes) return fail(pot, 2, "walkers_saddle_search: no initial modes uploaded");
+  int rc = walkers_size_rows(w);
+  if (rc) return rc;
+  if (reactant_energies)
+    CU_TRY(pot, cudaMemcpyAsync(w->react.p, reactant_energies, sizeof(double) * w->W, cudaMemcpyHostToDevice, pot->stream));
+  else
+    CU_TRY(pot, cudaMemsetAsync(w->react.p, 0, sizeof(double) * w->W, pot->stream));
+  CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+  return walkers_launch(w, 1, prm, prm->remove_net_force, 0.0);
+}
+
+int eonb200_walkers_relax(EonB200Walkers *w, const EonB200SearchParams *prm) {
+  if (!w || !prm) return 1;
+  int rc = walkers_size_rows(w);
+  if (rc) return rc;
+  return walkers_launch(w, 2, prm, prm->remove_net_force, 0.0);
+}
+
+int eonb200_walkers_displace_along_mode(EonB200Walkers *w, double signed_offset) {
+  if (!w) return 1;
+  return walkers_launch(w, 3, nullptr, 1, signed_offset);
+}
+
+int eonb200_walkers_harvest(EonB200Walkers *w, int *status, long *iterations, long *force_calls, double *energies,
+                            double *eigenvalues, double *convergence, double *positions, double *modes) {
+  if (!w) return 1;
+  EonB200Pot *pot = w->pot;
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+  const long W = w->W;
+  if (status) CU_TRY(pot, cudaMemcpy(status, w->status.p, sizeof(int) * W, cudaMemcpyDeviceToHost));
+  if (iterations) {
+    std::vector<long long> t(W);
+    CU_TRY(pot, cudaMemcpy(t.data(), w->iters.p, sizeof(long long) * W, cudaMemcpyDeviceToHost));
+    for (long k = 0; k < W; k++) iterations[k] = static_cast<long>(t[k]);
+  }
+  if (force_calls) {
+    std::vector<long long> t(W);
+    CU_TRY(pot, cudaMemcpy(t.data(), w->fcalls.p, sizeof(long long) * W, cudaMemcpyDeviceToHost));
+    for (long k = 0; k < W; k++) force_calls[k] = static_cast<long>(t[k]);
+  }
+  if (energies) CU_TRY(pot, cudaMemcpy(energies, w->energy.p, sizeof(double) * W, cudaMemcpyDeviceToHost));
+  if (eigenvalues) CU_TRY(pot, cudaMemcpy(eigenvalues, w->eig.p, sizeof(double) * W, cudaMemcpyDeviceToHost));
+  if (convergence) CU_TRY(pot, cudaMemcpy(convergence, w->conv.p, sizeof(double) * W, cudaMemcpyDeviceToHost));
+  if (positions)
+    CU_TRY(pot, cudaMemcpy2D(positions, w->D * sizeof(double), w->pos.p, w->Dp * sizeof(double), w->D * sizeof(double), W,
+                             cudaMemcpyDeviceToHost));
+  if (modes)
+    CU_TRY(pot, cudaMemcpy2D(modes, w->D * sizeof(double), w->mode.p, w->Dp * sizeof(double), w->D * sizeof(double), W,
+                             cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+double eonb200_walkers_last_ms(const EonB200Walkers *w) { return w ? w->last_ms : 0.0; }
+
+double eonb200_measure_fp64_peak(EonB200Pot *pot, int repeats) {
+  if (!pot) return 0.0;
+  cudaSetDevice(pot->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, pot->device) != cudaSuccess) return 0.0;
+  DevBuf<double> out;
+  if (out.reserve(1) != cudaSuccess) return 0.0;
+  const int iters = 1 << 14, threads = 256, blocks = prop.multiProcessorCount * 8;
+  double best = 0.0;
+  for (int r = 0; r < std::max(1, repeats) + 1; r++) {
+    cudaEventRecord(pot->ev[0], pot->stream);
+    EONB200_LAUNCH(k_dfma_peak, blocks, threads, 0, pot->stream, out.p, iters);
+    cudaEventRecord(pot->ev[2], pot->stream);
+    cudaStreamSynchronize(pot->stream);
+    pot->launches += 1;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, pot->ev[0], pot->ev[2]);
+    if (r == 0 || ms <= 0) continue;  // warm-up
+    const double flops = 2.0 * 8.0 * static_cast<double>(iters) * threads * blocks;
+    best = std::max(best, flops / (ms * 1e-3));
+  }
+  return best;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// common.cuh -- CTA-level primitives shared by every kernel of libeonb200.
+//
+// One CTA owns one walker (one atomic configuration): all control flow is CTA-uniform, every
+// vector operation is a block-strided loop and every scalar a block reduction whose result is
+// broadcast to all threads.  Reductions use a fixed order (thread-strided partials -> xor
+// butterfly inside the warp -> warp partials summed in warp order), so a walker's trajectory is
+// reproducible from run to run.
+//
+// EONB200_EMU: the same sources are compiled as plain C++ (one "thread" per CTA, see
+// tests/emu/emu_shim.h) by the CPU-only test-suite to exercise the algorithm logic where no
+// GPU exists.  The emulation is test infrastructure; the product library never contains it.
+#pragma once
+
+#ifdef EONB200_EMU
+#include "emu_shim.h"
+#else
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#endif
+
+#include <cmath>
+
+namespace eonb200 {
+
+constexpr int kMaxWarps = 32;
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kSafeEps = 1e-300;  // include/eon/SafeMath.h:19
+
+#ifdef EONB200_EMU
+#define EONB200_NOINLINE __attribute__((noinline))
+#else
+#define EONB200_NOINLINE __noinline__
+#endif
+
+#ifdef EONB200_EMU
+#define EONB200_DYN_SMEM(name) unsigned char *name = emu::dyn_smem()
+#define EONB200_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emu::launch((grid), (smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#define EONB200_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define EONB200_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+// ---- un-fused arithmetic for bit-exact predicates --------------------------------------------
+// The neighbour predicate must round exactly like the x86-64 reference (no FMA contraction):
+// client/thirdparty/vesin/vesin-single-build.cpp:41-43,138-144,1199-1202.
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double norm2_rn(double x, double y, double z) {
+  return add_rn(add_rn(mul_rn(x, x), mul_rn(y, y)), mul_rn(z, z));
+}
+
+// ---- warp / block reductions -------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#ifndef EONB200_EMU
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#ifndef EONB200_EMU
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#ifndef EONB200_EMU
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+#endif
+  return v;
+}
+
+// Sum over `lanes` adjacent lanes (lanes a power of two <= 32); every lane of the group gets the total.
+template <int LANES>
+__device__ __forceinline__ double group_sum(double v) {
+#ifndef EONB200_EMU
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+#endif
+  return v;
+}
+
+enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
+
+// Block reduction of NV values at once; scratch holds NV * kMaxWarps doubles of shared memory.
+// Every thread returns with the identical result in v[].  Two barriers.
+template <int NV>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV], double *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double r = op[k] == RED_SUM ? warp_sum(v[k]) : (op[k] == RED_MAX ? warp_max(v[k]) : warp_min(v[k]));
+    if (lane == 0) scratch[k * kMaxWarps + warp] = r;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double r = scratch[k * kMaxWarps];
+    for (int w = 1; w < nwarps; w++) {
+      const double x = scratch[k * kMaxWarps + w];
+      r = op[k] == RED_SUM ? r + x : (op[k] == RED_MAX ? fmax(r, x) : fmin(r, x));
+    }
+    v[k] = r;
+  }
+  __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch) {
+  int op[NV];
+#pragma unroll
+  for (int k = 0; k < NV; k++) op[k] = RED_SUM;
+  block_reduce<NV>(v, op, scratch);
+}
+
+__device__ __forceinline__ double block_sum1(double x, double *scratch) {
+  double v[1] = {x};
+  block_sum<1>(v, scratch);
+  return v[0];
+}
+__device__ __forceinline__ double block_max1(double x, double *scratch) {
+  double v[1] = {x};
+  const int op[1] = {RED_MAX};
+  block_reduce<1>(v, op, scratch);
+  return v[0];
+}
+
+// ---- SafeMath (include/eon/SafeMath.h:19-80) ----------------------------------------------------
+__device__ __forceinline__ double safe_div(double num, double den, double fb) {
+  return fabs(den) < kSafeEps ? fb : num / den;
+}
+__device__ __forceinline__ double safe_recip(double x, double fb) { return safe_div(1.0, x, fb); }
+__device__ __forceinline__ double safe_acos(double x) { return acos(fmin(1.0, fmax(-1.0, x))); }
+__device__ __forceinline__ double safe_atan_ratio(double num, double den, double fb) {
+  return fabs(den) < kSafeEps ? fb : atan(num / den);
+}
+
+// ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) ------------------------------------------
+// Per-walker arrays (positions, forces) are contiguous and 16-byte aligned in HBM, so one elected
+// thread moves a whole walker with a single bulk-copy instruction completing on an mbarrier.
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+#ifndef EONB200_EMU
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+  *bar = 0;
+#endif
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+#ifndef EONB200_EMU
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+#else
+  memcpy(smem_dst, gsrc, bytes);
+#endif
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+#ifndef EONB200_EMU
+  const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(b),
+      "r"(phase)
+      : "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
+#ifndef EONB200_EMU
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_src));
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#else
+  memcpy(gdst, smem_src, bytes);
+#endif
+}
+
+}  // namespace eonb200

@@ -1,0 +1,173 @@
+// types.cuh -- device-side parameter blocks and the per-CTA view of one walker.
+#pragma once
+#include "common.cuh"
+
+namespace eonb200 {
+
+enum PotKind { POT_LJ = 0, POT_LJCLUSTER = 1, POT_MORSE_PT = 2, POT_EAM = 3 };
+enum NlMode { NL_VESIN = 0, NL_MIC = 1 };
+
+constexpr int kMaxEamRows = 8;
+
+// One element row of include/eon/potentials/EAM/Parameters.h:15-50 plus derived constants.
+struct EamRowDev {
+  int Z;
+  double Dm, alphaM, Rm, beta1, beta2, r_cut, rc2;
+  double c[9];   // embedding polynomial c0..c8 (EAM.cpp:349-356)
+  double dc[9];  // k * c[k], derivative polynomial (EAM.cpp:358-365)
+};
+
+struct PotParams {
+  int kind;
+  int nl_mode;            // NL_VESIN for the rgpot pair potentials, NL_MIC for EAM.cpp's minimum image
+  double cutoff, cutoff2; // potential cutoff (LJ / Morse); for EAM the largest row cutoff
+  double rc_list;         // cutoff + skin: what the cached candidate list is built with
+  double rc_list2;
+  double skin;
+  double eshift;          // U(rc) subtracted per pair (LJ, Morse_Pt)
+  double lj_u0, lj_psi;
+  double morse_De, morse_a, morse_re;
+  int n_rows;
+  int eam_conservative;
+  EamRowDev rows[kMaxEamRows];
+};
+
+// Shift code packed above the neighbour index: j in bits 0..19, (s+8) per axis in 4 bits each.
+constexpr int kNbrIndexBits = 20;
+constexpr int kNbrIndexMask = (1 << kNbrIndexBits) - 1;
+constexpr int kShiftNeutral = (8 << 0) | (8 << 4) | (8 << 8);
+__device__ __host__ __forceinline__ int pack_nbr(int j, int sx, int sy, int sz) {
+  return j | ((sx + 8) << kNbrIndexBits) | ((sy + 8) << (kNbrIndexBits + 4)) | ((sz + 8) << (kNbrIndexBits + 8));
+}
+__device__ __host__ __forceinline__ void unpack_nbr(int code, int &j, int &sx, int &sy, int &sz) {
+  j = code & kNbrIndexMask;
+  const int s = static_cast<unsigned>(code) >> kNbrIndexBits;
+  sx = (s & 15) - 8;
+  sy = ((s >> 4) & 15) - 8;
+  sz = ((s >> 8) & 15) - 8;
+}
+
+// Cached neighbour lists of a batch of systems (one row block per system).
+struct NlBatch {
+  int *nbr;        // [S][K][Np]  packed (j, shift); slot-major so that lanes = atoms read coalesced
+  int *cnt;        // [S][Np]     row fill
+  double *rbuild;  // [S][3N]     positions the list was built from (Verlet displacement check)
+  int *state;      // [S]         0 = no list yet, 1 = list valid for rbuild
+  int K, Np;
+  int *overflow;             // [1] largest row fill any build needed (> K means the list is truncated)
+  unsigned long long *stats; // [0] rebuilt, [1] reused, [2] ordered pairs of the last evaluation
+};
+
+// One system as seen by its CTA.
+struct SysView {
+  int N;
+  int Rcap;          // doubles readable at R (>= 3N; the row stride of the walker arrays)
+  const double *R;   // [3N] positions, global
+  const int *Z;      // [N]
+  const double *box; // [9]
+  int *nbr;          // this system's [K][Np] block
+  int *cnt;          // [Np]
+  double *rbuild;    // [3N]
+  int *state;        // [1]
+  int K, Np;
+  int *overflow;
+  unsigned long long *stats;
+};
+
+__device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, const double *R, const int *Z,
+                                            const double *box) {
+  SysView v;
+  v.N = N;
+  v.Rcap = 3 * N;
+  v.R = R;
+  v.Z = Z;
+  v.box = box;
+  v.nbr = nl.nbr + static_cast<size_t>(s) * nl.K * nl.Np;
+  v.cnt = nl.cnt + static_cast<size_t>(s) * nl.Np;
+  v.rbuild = nl.rbuild + static_cast<size_t>(s) * 3 * N;
+  v.state = nl.state + s;
+  v.K = nl.K;
+  v.Np = nl.Np;
+  v.overflow = nl.overflow;
+  v.stats = nl.stats;
+  return v;
+}
+
+// Cell geometry of one system, computed by thread 0 of the CTA from the box.
+struct Geom {
+  double H[9];
+  double Hinv[9];
+  double lo[3];     // MIC mode: per-axis coordinate shift of EAM.cpp:56-83 (|min(0, lowest coordinate)|)
+  double fmin[3];   // VESIN mode, non-periodic axes: lowest fractional coordinate
+  double fspan[3];  // VESIN mode, non-periodic axes: fractional extent
+  int nc[3];        // cells per axis
+  int ns[3];        // search range in cells per axis
+  int per[3];       // periodic flags
+  int ncells;
+  int ok;           // box invertible
+};
+
+// Carve-up of the dynamic shared memory of a walker CTA.
+struct Smem {
+  double4 *pos;      // [N]   staged positions; .w carries dF/drho in the EAM force pass
+  double *red;       // [8 * kMaxWarps] reduction scratch
+  double *dfd;       // [N]   EAM: dF/drho per atom
+  double *stage;     // [3N + 2] landing zone of the bulk copy / outgoing forces
+  int *cell_of;      // [N]
+  int *wrapc;        // [N]   packed wrap shift of each atom (VESIN mode)
+  int *order;        // [N]   atoms sorted by cell
+  int *cell_start;   // [maxCells + 1]
+  int *cell_fill;    // [maxCells + 1]
+  unsigned char *rowid;  // [N] EAM row of each atom
+  uint64_t *mbar;
+  Geom *geom;
+  int maxCells;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__host__ __device__ inline size_t smem_bytes(int N, int maxCells) {
+  size_t b = 0;
+  b += align_up(sizeof(double4) * N, 128);
+  b += align_up(sizeof(double) * 8 * kMaxWarps, 128);
+  b += align_up(sizeof(double) * N, 128);
+  b += align_up(sizeof(double) * (3 * static_cast<size_t>(N) + 2), 128);
+  b += 3 * align_up(sizeof(int) * N, 128);
+  b += 2 * align_up(sizeof(int) * (maxCells + 1), 128);
+  b += align_up(static_cast<size_t>(N), 128);
+  b += 128;  // mbarrier
+  b += align_up(sizeof(Geom), 128);
+  return b;
+}
+
+__device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells) {
+  Smem s;
+  size_t o = 0;
+  s.pos = reinterpret_cast<double4 *>(base + o);
+  o += align_up(sizeof(double4) * N, 128);
+  s.red = reinterpret_cast<double *>(base + o);
+  o += align_up(sizeof(double) * 8 * kMaxWarps, 128);
+  s.dfd = reinterpret_cast<double *>(base + o);
+  o += align_up(sizeof(double) * N, 128);
+  s.stage = reinterpret_cast<double *>(base + o);
+  o += align_up(sizeof(double) * (3 * static_cast<size_t>(N) + 2), 128);
+  s.cell_of = reinterpret_cast<int *>(base + o);
+  o += align_up(sizeof(int) * N, 128);
+  s.wrapc = reinterpret_cast<int *>(base + o);
+  o += align_up(sizeof(int) * N, 128);
+  s.order = reinterpret_cast<int *>(base + o);
+  o += align_up(sizeof(int) * N, 128);
+  s.cell_start = reinterpret_cast<int *>(base + o);
+  o += align_up(sizeof(int) * (maxCells + 1), 128);
+  s.cell_fill = reinterpret_cast<int *>(base + o);
+  o += align_up(sizeof(int) * (maxCells + 1), 128);
+  s.rowid = base + o;
+  o += align_up(static_cast<size_t>(N), 128);
+  s.mbar = reinterpret_cast<uint64_t *>(base + o);
+  o += 128;
+  s.geom = reinterpret_cast<Geom *>(base + o);
+  s.maxCells = maxCells;
+  return s;
+}
+
+}  // namespace eonb200

@@ -1,0 +1,155 @@
+"""Device-resident batches of walkers: the batched counterpart of eOn's job drivers.
+
+`Walkers` keeps W copies of one topology (atomic numbers, fixed mask, box) in HBM and runs, for
+all of them in one launch with one CTA per walker,
+
+* ``matter_forces``   -- ``Matter::getPotentialEnergy / getForces`` (client/Matter.cpp:324-333,498-538)
+* ``saddle_search``   -- ``MinModeSaddleSearch::run`` as driven by ``SaddleSearchJob::run``
+                         (client/SaddleSearchJob.cpp:27-107, client/MinModeSaddleSearch.cpp:211-475)
+* ``relax``           -- ``helpers::relaxMatter`` (client/HelperFunctions.cpp:314-410)
+* ``process_search``  -- the saddle search followed by the two displaced minimisations of
+                         ``ProcessSearchJob::run`` (client/ProcessSearchJob.cpp:165-289)
+
+and harvests results to the host (the path's only "collective").
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from .potential import B200Potential, PotentialError, _dp, _ip
+
+STATUS_GOOD = 0
+STATUS_BAD_HIGH_ENERGY = 3
+STATUS_BAD_MAX_ITERATIONS = 5
+STATUS_POTENTIAL_FAILED = 11
+STATUS_NONLOCAL_ABORT = 13
+STATUS_BAD_NO_NEGATIVE_MODE_AT_SADDLE = 16
+STATUS_ZEROMODE_ABORT = 18
+STATUS_OPTIMIZER_ERROR = 19
+
+
+def search_params(lib=None, **kw) -> _capi.SearchParams:
+    """Defaults of the reference's Parameters for this path (include/eon/Parameters.h), overridden by kw."""
+    if lib is None:
+        from . import _lib
+        lib = _lib.load()
+    p = _capi.SearchParams()
+    lib.eonb200_search_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(f"unknown search parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+@dataclass
+class Harvest:
+    status: np.ndarray
+    iterations: np.ndarray
+    force_calls: np.ndarray
+    energies: np.ndarray
+    eigenvalues: np.ndarray
+    convergence: np.ndarray
+    positions: Optional[np.ndarray] = None
+    modes: Optional[np.ndarray] = None
+
+
+class Walkers:
+    def __init__(self, pot: B200Potential, atomicNrs, fixed, box, positions, modes=None):
+        self._pot = pot
+        self._lib = pot._lib
+        Z = np.ascontiguousarray(atomicNrs, dtype=np.int32).reshape(-1)
+        N = Z.size
+        R = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3 * N)
+        W = R.shape[0]
+        fx = np.ascontiguousarray(np.asarray(fixed).astype(np.int32).reshape(N, 3))
+        B = np.ascontiguousarray(box, dtype=np.float64).reshape(9)
+        M = None
+        if modes is not None:
+            M = np.ascontiguousarray(modes, dtype=np.float64).reshape(W, 3 * N)
+        err = C.create_string_buffer(512)
+        self._h = self._lib.eonb200_walkers_create(pot._h, W, N, _ip(Z), _ip(fx), _dp(B), _dp(R),
+                                                   _dp(M) if M is not None else None, err, len(err))
+        if not self._h:
+            raise PotentialError(1, err.value.decode() or "eonb200_walkers_create failed")
+        self.W, self.N = W, N
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.eonb200_walkers_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        self._pot._check(rc)
+
+    def set(self, positions=None, modes=None):
+        R = M = None
+        if positions is not None:
+            R = np.ascontiguousarray(positions, dtype=np.float64).reshape(self.W, 3 * self.N)
+        if modes is not None:
+            M = np.ascontiguousarray(modes, dtype=np.float64).reshape(self.W, 3 * self.N)
+        self._check(self._lib.eonb200_walkers_set(self._h, _dp(R) if R is not None else None,
+                                                  _dp(M) if M is not None else None))
+
+    def matter_forces(self, remove_net_force: bool = True):
+        E = np.empty(self.W)
+        F = np.empty((self.W, 3 * self.N))
+        self._check(self._lib.eonb200_walkers_matter_forces(self._h, 1 if remove_net_force else 0, _dp(E), _dp(F)))
+        return E, F.reshape(self.W, self.N, 3)
+
+    def saddle_search(self, prm: _capi.SearchParams, reactant_energies=None):
+        re = None
+        if reactant_energies is not None:
+            re = np.ascontiguousarray(np.broadcast_to(np.asarray(reactant_energies, dtype=np.float64), (self.W,)))
+        self._check(self._lib.eonb200_walkers_saddle_search(self._h, C.byref(prm), _dp(re) if re is not None else None))
+
+    def relax(self, prm: _capi.SearchParams):
+        self._check(self._lib.eonb200_walkers_relax(self._h, C.byref(prm)))
+
+    def displace_along_mode(self, signed_offset: float):
+        self._check(self._lib.eonb200_walkers_displace_along_mode(self._h, float(signed_offset)))
+
+    def harvest(self, geometry: bool = True) -> Harvest:
+        W, N = self.W, self.N
+        st = np.zeros(W, dtype=np.int32)
+        it = np.zeros(W, dtype=np.int64)
+        fc = np.zeros(W, dtype=np.int64)
+        E, ev, cv = np.zeros(W), np.zeros(W), np.zeros(W)
+        R = np.zeros((W, 3 * N)) if geometry else None
+        M = np.zeros((W, 3 * N)) if geometry else None
+        lp = C.POINTER(C.c_long)
+        self._check(self._lib.eonb200_walkers_harvest(
+            self._h, _ip(st), it.ctypes.data_as(lp), fc.ctypes.data_as(lp), _dp(E), _dp(ev), _dp(cv),
+            _dp(R) if geometry else None, _dp(M) if geometry else None))
+        return Harvest(st, it, fc, E, ev, cv, R.reshape(W, N, 3) if geometry else None,
+                       M.reshape(W, N, 3) if geometry else None)
+
+    @property
+    def last_ms(self) -> float:
+        return float(self._lib.eonb200_walkers_last_ms(self._h))
+
+    # ProcessSearchJob::run without file I/O (client/ProcessSearchJob.cpp:165-289): saddle search, then
+    # min1 / min2 = saddle -/+ minimization_offset * mode relaxed on the free coordinates.
+    def process_search(self, prm: _capi.SearchParams, reactant_energies=None, minimization_offset=None):
+        offset = prm.max_move if minimization_offset is None else minimization_offset  # ParametersINI.cpp:1374-1376
+        self.saddle_search(prm, reactant_energies)
+        saddle = self.harvest()
+        out = {"saddle": saddle}
+        for name, sign in (("min1", +1.0), ("min2", -1.0)):
+            self.set(positions=saddle.positions, modes=saddle.modes)
+            self.displace_along_mode(sign * offset)
+            self.relax(prm)
+            out[name] = self.harvest()
+        self.set(positions=saddle.positions, modes=saddle.modes)
+        return out

@@ -1,0 +1,244 @@
+/*
+ * eonb200.h -- C ABI of libeonb200.so, the B200 (sm_100a) backend for eOn's batched
+ * saddle-search hot path.
+ *
+ * Plain C: pointers and sizes only, no C++/torch types.  Every entry point names the
+ * reference interface (paths relative to the eOn checkout) it stands in for.  The pattern
+ * (opaque handle, create/destroy/force/abi_version, int return code + char* errbuf) is the
+ * reference's own dlopen precedent:
+ *     include/eon/potentials/Metatomic/metatomic_c_abi.h:30-79
+ *     client/potentials/Metatomic/MetatomicDynPot.cpp:39-70
+ *
+ * All floating point is FP64.  Positions are row-major [x0,y0,z0,x1,...] in Angstrom, boxes
+ * are row-major 3x3 with the cell vectors as rows (include/eon/Eigen.h:28-37,
+ * client/Matter.cpp:523-524).  The library needs a CUDA device; there is no CPU fallback --
+ * eonb200_create fails with a message when no sm_100 device is usable.
+ */
+#ifndef EONB200_H
+#define EONB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EONB200_ABI_VERSION 1
+
+#if defined(_WIN32)
+#define EONB200_API __declspec(dllexport)
+#else
+#define EONB200_API __attribute__((visibility("default")))
+#endif
+
+/* ---- potential description ------------------------------------------------------------- */
+
+/* PotType arms this backend re-points (include/eon/BaseStructures.h:36-71,
+ * client/Potential.cpp:140-153): LJ, LJCLUSTER, MORSE_PT (rgpot kernels) and the in-tree EAM
+ * class (client/potentials/EAM/EAM.cpp). */
+enum {
+  EONB200_POT_LJ = 0,        /* 4 u0 [(psi/r)^12 - (psi/r)^6] - U(rc), r < rc        */
+  EONB200_POT_LJCLUSTER = 1, /* same, no energy shift                                */
+  EONB200_POT_MORSE_PT = 2,  /* De (1 - exp(-a (r - re)))^2 - De - U(rc), r < rc     */
+  EONB200_POT_EAM = 3        /* EAM.cpp:125-226: r^6 (e^-b1 r + 512 e^-2 b2 r) density,
+                                degree-8 embedding polynomial, Morse pair part        */
+};
+
+/* One element row of include/eon/potentials/EAM/Parameters.h:15-50. */
+typedef struct EonB200EamRow {
+  int Z;
+  double Dm, alphaM, Rm, beta1, beta2, r_cut;
+  double func_coeff[9];
+} EonB200EamRow;
+
+typedef struct EonB200Config {
+  int kind;               /* EONB200_POT_*                                                     */
+  int device;             /* CUDA device ordinal                                               */
+  double cutoff;          /* LJ / Morse cutoff; <= 0 -> 15.0 (LJ) / 9.5 (Morse_Pt)              */
+  double lj_u0, lj_psi;   /* <= 0 -> 1.0                                                       */
+  double morse_De, morse_a, morse_re; /* all 0 -> Pt values 0.7102 / 1.6047 / 2.8970           */
+  int n_eam_rows;         /* 0 -> the reference's built-in Al / Pd / Au rows                   */
+  const EonB200EamRow *eam_rows; /* caller-supplied table (e.g. a Cu row), copied at create    */
+  int eam_conservative;   /* 0: pair-force sign exactly as EAM.cpp:203-215 (bit-faithful to the
+                             reference class, which is NOT -grad U); 1: F = -grad U            */
+  double skin;            /* Verlet skin of the cached neighbour lists, Angstrom; < 0 -> 1.0;
+                             0 -> exact list rebuilt on every evaluation                       */
+  int threads_per_walker; /* CTA size override, 0 -> chosen from nAtoms                        */
+} EonB200Config;
+
+typedef struct EonB200Pot EonB200Pot; /* opaque */
+
+/* Fill cfg with the defaults of the given potential kind. */
+EONB200_API void eonb200_config_default(EonB200Config *cfg, int kind);
+
+/* replaces helpers::makePotential for these PotTypes (client/Potential.cpp:124-303).
+ * NULL on failure with a message in errbuf. */
+EONB200_API EonB200Pot *eonb200_create(const EonB200Config *cfg, char *errbuf, size_t errlen);
+EONB200_API void eonb200_destroy(EonB200Pot *pot);
+EONB200_API int eonb200_abi_version(void);
+/* message of the last failing call on this handle ("" if none) */
+EONB200_API const char *eonb200_last_error(const EonB200Pot *pot);
+
+/* Return codes: 0 ok; 14324 unknown element (EAM.cpp:116-123 `throw 14324`); 100 potential
+ * failed (the reference's legacy `throw 100`, SaddleSearchJob.cpp:116-123); other non-zero =
+ * CUDA / argument error (see eonb200_last_error). */
+
+/* replaces Potential::force (include/eon/Potential.h:55-57).  Host pointers; forces is fully
+ * overwritten; variance may be NULL (written 0 otherwise).  Ignores the fixed mask. */
+EONB200_API int eonb200_force(EonB200Pot *pot, long nAtoms, const double *positions, const int *atomicNrs,
+                              double *forces, double *energy, double *variance, const double *box);
+
+/* replaces Potential::forceBatch (include/eon/Potential.h:98-122) as consumed by
+ * client/ImprovedDimer.cpp:160-193, client/Dimer.cpp:170-210, client/NudgedElasticBand.cpp:475-521.
+ * Arrays of nSystems host pointers; every system has nAtoms atoms.  One H2D copy, one batched
+ * launch sequence, one D2H copy. */
+EONB200_API int eonb200_force_batch(EonB200Pot *pot, long nSystems, long nAtoms, const double *const *positions,
+                                    const int *const *atomicNrs, double *const *forces, double *energies,
+                                    double *variances, const double *const *boxes);
+
+/* Same evaluation with everything already resident in HBM (contiguous device arrays):
+ * d_positions [S][3N], d_atomicNrs [S][N], d_boxes [S][9] in; d_forces [S][3N], d_energies [S] out.
+ * Asynchronous on the handle's stream unless sync != 0.  atomicNrs are NOT validated here. */
+EONB200_API int eonb200_force_batch_device(EonB200Pot *pot, long nSystems, long nAtoms, const double *d_positions,
+                                           const int *d_atomicNrs, double *d_forces, double *d_energies,
+                                           const double *d_boxes, int sync);
+
+/* Force-call counter of the handle (Potential::forceCallCounter, include/eon/Potential.h:32):
+ * one increment per system evaluated through force / force_batch / resident walkers. */
+EONB200_API unsigned long long eonb200_force_calls(const EonB200Pot *pot);
+
+/* ---- neighbour lists -------------------------------------------------------------------- */
+
+/* replaces vesin_neighbors (client/thirdparty/vesin/vesin.h:190-199) as wrapped by
+ * VesinNeighbors::compute (client/VesinNeighbors.cpp:42-89): periodic cell-list build on the
+ * device for nSystems independent systems of nAtoms points.  The set of (i, j, shift) per system
+ * equals vesin's bit for bit (same final predicate |(r_j - r_i) + S.H|^2 < cutoff^2 with
+ * un-fused arithmetic, same half-list rule); order is by i, unspecified within i.
+ *   full != 0: both (i,j,S) and (j,i,-S).
+ * Output (host, caller-allocated): pair_offsets [nSystems+1]; pairs [cap][2] (int64), shifts
+ * [cap][3] (int32); distances [cap] and vectors [cap][3] may be NULL.  Returns the total number
+ * of pairs through *n_pairs; if it exceeds cap nothing is written beyond cap and the call
+ * returns 0 with *n_pairs > cap (call again with a larger buffer). */
+EONB200_API int eonb200_neighbors(EonB200Pot *pot, long nSystems, long nAtoms, const double *positions,
+                                  const double *boxes, const int periodic[3], double cutoff, int full,
+                                  long cap, long *pair_offsets, int64_t *pairs, int32_t *shifts,
+                                  double *distances, double *vectors, long *n_pairs);
+
+/* ---- resident walkers ------------------------------------------------------------------- */
+
+enum { EONB200_OPT_CG = 0, EONB200_OPT_LBFGS = 1, EONB200_OPT_FIRE = 2 };
+enum { EONB200_MINMODE_DIMER = 0, EONB200_MINMODE_LANCZOS = 1 };
+enum { EONB200_ROT_SD = 0, EONB200_ROT_CG = 1, EONB200_ROT_LBFGS = 2 };
+enum { EONB200_METRIC_NORM = 0, EONB200_METRIC_MAX_ATOM = 1, EONB200_METRIC_MAX_COMPONENT = 2 };
+
+/* The subset of eonc::Parameters this path reads (include/eon/Parameters.h:55,58,176-197,
+ * 220-277,418-423; links client/ParametersINI.cpp:1075-1077,1335-1377).  Field-for-field the
+ * same as the oracle's OrcSearchParams. */
+typedef struct EonB200SearchParams {
+  double finite_difference;
+  int remove_net_force;
+  int opt_method;
+  int convergence_metric;
+  long opt_max_iterations;
+  double max_move;
+  double opt_converged_force;
+  double time_step;
+  double max_time_step;
+  long lbfgs_memory;
+  double lbfgs_inverse_curvature;
+  int lbfgs_auto_scale, lbfgs_angle_reset, lbfgs_distance_reset;
+  int cg_no_overshooting, cg_knock_out_max_move;
+  long cg_max_iter_before_reset;
+  int dimer_opt_method;
+  double dimer_converged_angle;
+  long dimer_rotations_max;
+  double lanczos_tolerance;
+  long lanczos_max_iterations;
+  int lanczos_quit_early;
+  int minmode_method;
+  long saddle_max_iterations;
+  double saddle_converged_force;
+  double saddle_max_energy;
+  double saddle_perp_force_ratio;
+  double saddle_zero_mode_abort_curvature;
+  long saddle_nonlocal_count_abort;
+  double saddle_nonlocal_distance_abort;
+} EonB200SearchParams;
+
+EONB200_API void eonb200_search_params_default(EonB200SearchParams *p);
+
+typedef struct EonB200Walkers EonB200Walkers; /* opaque: W walkers of one topology, resident in HBM */
+
+/* Upload W walkers that share nAtoms, atomicNrs, the per-axis fixed mask [N][3] (0 free / 1 fixed,
+ * include/eon/Matter.h:217-227) and the box.  positions [W][3N]: start geometries (the displaced
+ * structures, SaddleSearchJob.cpp:27-61); modes [W][3N]: initial directions (direction.dat), may be
+ * NULL for relaxation-only use.  Everything stays on the device until harvest. */
+EONB200_API EonB200Walkers *eonb200_walkers_create(EonB200Pot *pot, long nWalkers, long nAtoms, const int *atomicNrs,
+                                                   const int *fixed, const double *box, const double *positions,
+                                                   const double *modes, char *errbuf, size_t errlen);
+EONB200_API void eonb200_walkers_destroy(EonB200Walkers *w);
+
+/* Replace the geometries / modes of all walkers (host arrays [W][3N]; either may be NULL). */
+EONB200_API int eonb200_walkers_set(EonB200Walkers *w, const double *positions, const double *modes);
+
+/* Matter::getPotentialEnergy + getForces on every walker (client/Matter.cpp:324-333,498-538):
+ * potential, net-force removal when nothing is fixed, fixed-axis mask.  Host outputs, may be NULL. */
+EONB200_API int eonb200_walkers_matter_forces(EonB200Walkers *w, int remove_net_force, double *energies,
+                                              double *forces);
+
+/* MinModeSaddleSearch::run for every walker, device resident, one CTA per walker, no host
+ * round trips inside a search (client/MinModeSaddleSearch.cpp:211-475 with
+ * client/ImprovedDimer.cpp:63-434 or client/Lanczos.cpp:46-173 and client/{ConjugateGradients,
+ * LBFGS,FIRE}.cpp).  reactant_energies [W] (or NULL -> 0) feed the max_energy abort. */
+EONB200_API int eonb200_walkers_saddle_search(EonB200Walkers *w, const EonB200SearchParams *prm,
+                                              const double *reactant_energies);
+
+/* helpers::relaxMatter on every walker (client/HelperFunctions.cpp:273-410): minimisation over
+ * the free degrees of freedom with the optimizer named in prm. */
+EONB200_API int eonb200_walkers_relax(EonB200Walkers *w, const EonB200SearchParams *prm);
+
+/* ProcessSearchJob's displacement of the two minima from the saddle
+ * (client/ProcessSearchJob.cpp:188-202): positions += sign * offset * mode on the free axes. */
+EONB200_API int eonb200_walkers_displace_along_mode(EonB200Walkers *w, double signed_offset);
+
+/* Host-side harvest (the only "collective" of the path): any output may be NULL.
+ *   status [W]       MinModeSaddleSearch::Status (include/eon/MinModeSaddleSearch.h:29-53) or, after
+ *                    relax, 0 converged / 1 not converged
+ *   iterations [W], force_calls [W]
+ *   energies [W], eigenvalues [W], convergence [W]
+ *   positions [W][3N], modes [W][3N] */
+EONB200_API int eonb200_walkers_harvest(EonB200Walkers *w, int *status, long *iterations, long *force_calls,
+                                        double *energies, double *eigenvalues, double *convergence,
+                                        double *positions, double *modes);
+
+/* Device time in milliseconds of the last walkers_* launch sequence (CUDA events on the
+ * handle's stream), for the measurement harness. */
+EONB200_API double eonb200_walkers_last_ms(const EonB200Walkers *w);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+
+/* Register-resident DFMA microbenchmark: returns the measured non-tensor FP64 rate in FLOP/s
+ * (2 flop per DFMA) on the handle's device; the roofline denominator for the pair kernels. */
+EONB200_API double eonb200_measure_fp64_peak(EonB200Pot *pot, int repeats);
+
+/* Kernel launch counter of the handle (every kernel this library launches bumps it). */
+EONB200_API unsigned long long eonb200_kernel_launches(const EonB200Pot *pot);
+
+/* Neighbour-list statistics of the last force_batch / walkers call on the handle:
+ * out[0] = lists rebuilt, out[1] = lists reused, out[2] = row capacity K, out[3] = max row fill,
+ * out[4] = ordered in-cutoff pairs visited by the last force evaluation (sum over systems). */
+EONB200_API int eonb200_nl_stats(EonB200Pot *pot, long long out[5]);
+
+/* Time the force_batch_device kernels only: CUDA-event milliseconds of the last call, split as
+ * out[0] = neighbour ensure kernel, out[1] = force kernel(s). */
+EONB200_API int eonb200_last_force_ms(EonB200Pot *pot, double out[2]);
+
+/* Launch the neighbour check/rebuild and the force evaluation as two kernels instead of one so
+ * that eonb200_last_force_ms can split their device time (measurement only). */
+EONB200_API int eonb200_set_split_kernels(EonB200Pot *pot, int split);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EONB200_H */
