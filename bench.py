@@ -255,7 +255,7 @@ def run_b200(args):
     first = rank * N_WALKERS
     struct, sets = force_workload(first)
     N, W = struct.n_atoms, N_WALKERS
-    pot = B200Potential("eam", device=local_rank, skin=args.skin)
+    pot = B200Potential("eam", device=local_rank, skin=args.skin, tiles_override=args.tiles, lpa_override=args.lpa)
     d_R = torch.from_numpy(sets.reshape(N_POSITION_SETS, W, 3 * N)).to(dev)
     d_Z = torch.from_numpy(np.broadcast_to(struct.atomic_nrs, (W, N)).copy()).to(dev)
     d_box = torch.from_numpy(np.broadcast_to(struct.cell.reshape(9), (W, 9)).copy()).to(dev)
@@ -301,7 +301,7 @@ def run_b200(args):
     t_hot = 0.0
     for k in range(args.steps):
         t_hot += step(k)
-    pot0 = B200Potential("eam", device=local_rank, skin=0.0)
+    pot0 = B200Potential("eam", device=local_rank, skin=0.0, tiles_override=args.tiles, lpa_override=args.lpa)
     for k in range(3):
         pot0.forceBatchDevice(W, N, d_R[k % N_POSITION_SETS].data_ptr(), d_Z.data_ptr(), d_F.data_ptr(), d_U.data_ptr(),
                               d_box.data_ptr(), sync=True)
@@ -342,7 +342,7 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     hbm_achieved = eam_min_bytes(pairs_per_step, W * N) / (ms_kernel * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "kernel": "k_force_batch", "achieved": achieved, "peak": fp64_peak / 1e12,
+    roofline = {"bound": "fp64", "kernel": "k_eam_pass1 + k_eam_pass2 (+ k_prepare)", "achieved": achieved, "peak": fp64_peak / 1e12,
                 "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": None,
                 "peak_source": "DFMA microbenchmark k_dfma_peak measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
                 "algorithmic_flops_per_launch": flops, "ordered_pairs_per_launch": pairs_per_step,
@@ -421,6 +421,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skin", type=float, default=1.0)
+    ap.add_argument("--tiles", type=int, default=0, help="CTAs per walker in the force passes (0 = automatic)")
+    ap.add_argument("--lpa", type=int, default=0, help="lanes per atom (0 = automatic)")
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -26,7 +26,7 @@ SYMBOLS = [
     "eonb200_walkers_matter_forces", "eonb200_walkers_saddle_search", "eonb200_walkers_relax",
     "eonb200_walkers_displace_along_mode", "eonb200_walkers_harvest", "eonb200_walkers_last_ms",
     "eonb200_measure_fp64_peak", "eonb200_kernel_launches", "eonb200_nl_stats",
-    "eonb200_last_force_ms", "eonb200_set_split_kernels",
+    "eonb200_last_force_ms",
 ]
 
 
@@ -41,7 +41,8 @@ class Config(C.Structure):
                 ("lj_u0", C.c_double), ("lj_psi", C.c_double),
                 ("morse_De", C.c_double), ("morse_a", C.c_double), ("morse_re", C.c_double),
                 ("n_eam_rows", C.c_int), ("eam_rows", C.POINTER(EamRow)),
-                ("eam_conservative", C.c_int), ("skin", C.c_double), ("threads_per_walker", C.c_int)]
+                ("eam_conservative", C.c_int), ("skin", C.c_double), ("threads_per_walker", C.c_int),
+                ("tiles_override", C.c_int), ("lpa_override", C.c_int)]
 
 
 class SearchParams(C.Structure):
@@ -118,6 +119,4 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.eonb200_nl_stats.restype = C.c_int
     lib.eonb200_last_force_ms.argtypes = [_vp, _dp]
     lib.eonb200_last_force_ms.restype = C.c_int
-    lib.eonb200_set_split_kernels.argtypes = [_vp, C.c_int]
-    lib.eonb200_set_split_kernels.restype = C.c_int
     return lib

@@ -62,8 +62,10 @@ struct PinBuf {
 };
 
 struct NlStore {
-  DevBuf<int> nbr, cnt, state;
-  DevBuf<double> rbuild;
+  DevBuf<int> nbr, cnt, state, flags, done;
+  DevBuf<double> rbuild, pairA, pairB, dfd, upart;
+  DevBuf<double4> pos4;
+  DevBuf<unsigned char> rowid;
   long S = 0, N = 0;
   int K = 0, Np = 0;
 };
@@ -78,6 +80,7 @@ struct EonB200Pot {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   DevBuf<PotParams> dP;
+  DevBuf<double> d_exp_tab;
   DevBuf<int> d_overflow;
   DevBuf<unsigned long long> d_stats;
   PinBuf<unsigned long long> h_stats;
@@ -93,7 +96,7 @@ struct EonB200Pot {
   long long last_stats[5] = {0, 0, 0, 0, 0};
   double last_ms[2] = {0.0, 0.0};
   int max_dyn_smem = 0;
-  int split_kernels = 0;
+  int sm_count = 148;
   std::string err;
 };
 
@@ -212,6 +215,40 @@ int pick_threads(const EonB200Pot *pot, long N, int lpa) {
 #endif
 }
 
+// Tiling of the stateless force passes: enough CTAs to give every SM several, at most kMaxTiles per system,
+// tiles of at least 32 atoms; lanes per atom so that a tile fills a CTA of a few hundred threads.
+void pick_tiling(const EonB200Pot *pot, long S, long N, int *tiles, int *lpa) {
+#ifdef EONB200_EMU
+  (void)pot;
+  *tiles = S > 1 ? 2 : 3;  // exercise the multi-tile path
+  if (*tiles > N) *tiles = static_cast<int>(N);
+  *lpa = 1;
+#else
+  const long want_ctas = 4L * pot->sm_count;
+  long t = (want_ctas + S - 1) / S;
+  t = std::max<long>(1, std::min<long>(t, kMaxTiles));
+  t = std::min<long>(t, std::max<long>(1, N / 32));
+  if (pot->cfg.tiles_override > 0) t = std::min<long>(pot->cfg.tiles_override, std::min<long>(kMaxTiles, N));
+  *tiles = static_cast<int>(t);
+  const long tile_atoms = (N + t - 1) / t;
+  int l = 1;
+  while (l < 8 && tile_atoms * (l * 2) <= 256) l *= 2;
+  if (pot->cfg.lpa_override > 0) l = pot->cfg.lpa_override;
+  *lpa = l;
+#endif
+}
+
+int tile_threads_for(int tile_atoms, int lpa) {
+#ifdef EONB200_EMU
+  (void)tile_atoms;
+  (void)lpa;
+  return 1;
+#else
+  long t = (static_cast<long>(tile_atoms) * lpa + 31) / 32 * 32;
+  return static_cast<int>(std::min<long>(std::max<long>(t, 32), kMaxThreadsPerWalker));
+#endif
+}
+
 int pick_max_cells(long N) { return static_cast<int>(std::min<long>(std::max<long>(64, N), 4096)); }
 
 // Row capacity guess from the mean density; truncated builds are detected and regrown.
@@ -232,7 +269,19 @@ int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K) {
   CU_TRY(pot, nl.cnt.reserve(static_cast<size_t>(S) * Np));
   CU_TRY(pot, nl.rbuild.reserve(static_cast<size_t>(S) * 3 * N));
   CU_TRY(pot, nl.state.reserve(static_cast<size_t>(S)));
+  CU_TRY(pot, nl.flags.reserve(static_cast<size_t>(S)));
+  CU_TRY(pot, nl.done.reserve(static_cast<size_t>(S)));
+  CU_TRY(pot, nl.pos4.reserve(static_cast<size_t>(S) * Np));
+  CU_TRY(pot, nl.dfd.reserve(static_cast<size_t>(S) * Np));
+  CU_TRY(pot, nl.rowid.reserve(static_cast<size_t>(S) * Np));
+  CU_TRY(pot, nl.upart.reserve(static_cast<size_t>(S) * kMaxTiles * 4));
+  if (pot->cfg.kind == EONB200_POT_EAM) {
+    CU_TRY(pot, nl.pairA.reserve(static_cast<size_t>(S) * K * Np));
+    CU_TRY(pot, nl.pairB.reserve(static_cast<size_t>(S) * K * Np));
+  }
   CU_TRY(pot, cudaMemsetAsync(nl.state.p, 0, sizeof(int) * S, pot->stream));
+  CU_TRY(pot, cudaMemsetAsync(nl.done.p, 0, sizeof(int) * S, pot->stream));
+  CU_TRY(pot, cudaMemsetAsync(nl.flags.p, 0, sizeof(int) * S, pot->stream));
   nl.S = S;
   nl.N = N;
   nl.K = K;
@@ -250,6 +299,14 @@ NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
   b.Np = nl.Np;
   b.overflow = pot->d_overflow.p;
   b.stats = pot->d_stats.p;
+  b.pairA = nl.pairA.p;
+  b.pairB = nl.pairB.p;
+  b.pos4 = nl.pos4.p;
+  b.dfd = nl.dfd.p;
+  b.rowid = nl.rowid.p;
+  b.flags = nl.flags.p;
+  b.upart = nl.upart.p;
+  b.done = nl.done.p;
   return b;
 }
 
@@ -272,31 +329,35 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     if (rc) return rc;
   }
   a.maxCells = pick_max_cells(N);
-  a.lpa = pick_lpa(pot, N, 512);
-  const int threads = pick_threads(pot, N, a.lpa);
+  const int prep_threads = pick_threads(pot, N, 1);
   size_t smem;
   int rc = check_smem(pot, N, a.maxCells, &smem);
   if (rc) return rc;
+  // force passes: T tiles per system so that S * T CTAs cover the SMs a few times over
+  pick_tiling(pot, S, N, &a.tiles, &a.lpa);
+  const int tile_atoms = static_cast<int>((N + a.tiles - 1) / a.tiles);
+  const int tile_threads = tile_threads_for(tile_atoms, a.lpa);
+  const size_t tile_smem = smem_bytes_tile(static_cast<int>(N));
+  if (static_cast<long>(tile_smem) > pot->max_dyn_smem) return fail(pot, 3, "system too large for the tiled force kernels");
+#ifdef EONB200_EMU
+  const unsigned gy = static_cast<unsigned>(S);
+  (void)gy;
+#endif
   for (int attempt = 0; attempt < 6; attempt++) {
     CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
     CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
     NlBatch view = nl_view(pot, nl);
     CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
-    if (pot->split_kernels) {
-      ForceBatchArgs a1 = a;
-      a1.mode = FM_ENSURE;
-      EONB200_LAUNCH(k_force_batch, static_cast<unsigned>(S), threads, smem, pot->stream, pot->dP.p, view, a1);
-      CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
-      ForceBatchArgs a2 = a;
-      a2.mode = FM_FORCE;
-      a2.force_rebuild = 0;
-      EONB200_LAUNCH(k_force_batch, static_cast<unsigned>(S), threads, smem, pot->stream, pot->dP.p, view, a2);
-      pot->launches += 2;
+    EONB200_LAUNCH(k_prepare, dim3(static_cast<unsigned>(S)), prep_threads, smem, pot->stream, pot->dP.p, view, a);
+    CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
+    const dim3 grid(static_cast<unsigned>(a.tiles), static_cast<unsigned>(S));
+    if (pot->cfg.kind == EONB200_POT_EAM) {
+      EONB200_LAUNCH(k_eam_pass1, grid, tile_threads, tile_smem, pot->stream, pot->dP.p, view, a);
+      EONB200_LAUNCH(k_eam_pass2, grid, tile_threads, tile_smem, pot->stream, pot->dP.p, view, a);
+      pot->launches += 3;
     } else {
-      a.mode = FM_BOTH;
-      CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
-      EONB200_LAUNCH(k_force_batch, static_cast<unsigned>(S), threads, smem, pot->stream, pot->dP.p, view, a);
-      pot->launches += 1;
+      EONB200_LAUNCH(k_pair, grid, tile_threads, tile_smem, pot->stream, pot->dP.p, view, a);
+      pot->launches += 2;
     }
     CU_TRY(pot, cudaEventRecord(pot->ev[2], pot->stream));
     CU_TRY(pot, cudaGetLastError());
@@ -398,7 +459,19 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
     }
   }
   pot->cfg.eam_rows = nullptr;
+  pot->sm_count = prop.multiProcessorCount;
   fill_params(pot);
+  {
+    // 2^(j/128) rounded from long double: the table of exp_tab (potentials.cuh)
+    double tab[128];
+    for (int j = 0; j < 128; j++) tab[j] = static_cast<double>(exp2l(static_cast<long double>(j) / 128.0L));
+    if (pot->d_exp_tab.reserve(128) != cudaSuccess ||
+        cudaMemcpy(pot->d_exp_tab.p, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess) {
+      delete pot;
+      return bail("eonb200_create: cannot allocate device memory");
+    }
+    pot->hp.exp_tab = pot->d_exp_tab.p;
+  }
   bool ok = cudaStreamCreate(&pot->stream) == cudaSuccess;
   for (int k = 0; k < 3 && ok; k++) ok = cudaEventCreate(&pot->ev[k]) == cudaSuccess;
   ok = ok && pot->dP.reserve(1) == cudaSuccess && pot->d_overflow.reserve(1) == cudaSuccess &&
@@ -412,13 +485,19 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
     int worst_static = 0;
     if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(k_walkers)) == cudaSuccess)
       worst_static = std::max<int>(worst_static, static_cast<int>(fa.sharedSizeBytes));
-    if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(k_force_batch)) == cudaSuccess)
+    if (cudaFuncGetAttributes(&fa, reinterpret_cast<const void *>(k_prepare)) == cudaSuccess)
       worst_static = std::max<int>(worst_static, static_cast<int>(fa.sharedSizeBytes));
     pot->max_dyn_smem = limit - worst_static - 1024;
     ok = cudaFuncSetAttribute(reinterpret_cast<const void *>(k_walkers), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
-         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_force_batch),
-                              cudaFuncAttributeMaxDynamicSharedMemorySize, pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_prepare), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_pass1), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_pass2), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_neighbors), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess;
   }
@@ -454,12 +533,6 @@ int eonb200_last_force_ms(EonB200Pot *pot, double out[2]) {
   if (!pot) return 1;
   out[0] = pot->last_ms[0];
   out[1] = pot->last_ms[1];
-  return 0;
-}
-
-int eonb200_set_split_kernels(EonB200Pot *pot, int split) {
-  if (!pot) return 1;
-  pot->split_kernels = split;
   return 0;
 }
 
@@ -601,7 +674,7 @@ int eonb200_neighbors(EonB200Pot *pot, long S, long N, const double *positions, 
     CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
     NlBatch view = nl_view(pot, nl);
     EONB200_LAUNCH(k_neighbors, static_cast<unsigned>(S), threads, smem, pot->stream, view, np, static_cast<int>(S),
-                   static_cast<int>(N), dR.p, dB.p, maxCells);
+                   static_cast<int>(N), dR.p, dB.p, maxCells, pot->d_exp_tab.p);
     pot->launches += 1;
     CU_TRY(pot, cudaGetLastError());
     CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));

@@ -1,13 +1,20 @@
-// kernels.cuh -- __global__ entry points.  One CTA per system / walker everywhere.
+// kernels.cuh -- __global__ entry points.
+//
+// Stateless batched evaluation (Potential::force / forceBatch) runs as a short pipeline over S systems:
+//   k_prepare   grid S          stage positions (bulk copy), EAM shift/wrap, Verlet check, cell-list rebuild
+//                               when needed, prepared positions + element rows to HBM
+//   k_eam_pass1 grid (T, S)     density pass over a tile of atoms, pair cache, dF/drho       (EAM)
+//   k_eam_pass2 grid (T, S)     force gather over a tile of atoms, energy                     (EAM)
+//   k_pair      grid (T, S)     single pass                                                   (LJ / Morse)
+// T tiles per system spread a walker over several CTAs so that a few hundred walkers fill 148 SMs.
+// Resident walkers (k_walkers) keep one CTA per walker for the whole saddle search.
 #pragma once
 #include "search.cuh"
 
 namespace eonb200 {
 
-// CTA size cap: 512 threads leaves 128 registers per thread for the FP64 exp-heavy pair loops.
+// CTA size cap: 512 threads leaves 128 registers per thread for the FP64 pair loops.
 constexpr int kMaxThreadsPerWalker = 512;
-
-enum ForceMode { FM_ENSURE = 1, FM_FORCE = 2, FM_BOTH = 3 };
 
 struct ForceBatchArgs {
   int S, N;
@@ -21,7 +28,7 @@ struct ForceBatchArgs {
   double *U;         // [S]
   int maxCells;
   int lpa;
-  int mode;          // ForceMode
+  int tiles;         // CTAs per system in the force passes
   int force_rebuild;
 };
 
@@ -30,27 +37,20 @@ __device__ inline NlParams make_nl_params(const PotParams &P) {
   np.mode = P.nl_mode;
   np.rc = P.rc_list;
   np.rc2 = P.rc_list2;
+  np.rc_core2 = P.cutoff2;
   np.skin = P.skin;
   np.per[0] = np.per[1] = np.per[2] = 1;
   return np;
 }
 
-// Raw forces from sm.stage to HBM: one bulk store when the destination is 16-byte aligned.
-__device__ inline void store_forces(const Smem &sm, double *F, int N, int cap) {
-  int nd = 3 * N;
-  const bool even_ok = (nd & 1) == 0;
-  const bool aligned = even_ok && ((reinterpret_cast<uintptr_t>(F) & 15u) == 0);
-  (void)cap;
-  if (aligned) {
-    if (threadIdx.x == 0) bulk_s2g(F, sm.stage, static_cast<uint32_t>(nd) * 8u);
-  } else {
-    for (int k = threadIdx.x; k < nd; k += blockDim.x) F[k] = sm.stage[k];
-  }
-  __syncthreads();
+__device__ inline SysView batch_sys(const NlBatch &nl, const ForceBatchArgs &a, int s) {
+  SysView sys = make_sys(nl, s, a.N, a.R + static_cast<size_t>(s) * a.strideR, a.Z + static_cast<size_t>(s) * a.strideZ,
+                         a.box + static_cast<size_t>(s) * a.strideBox);
+  sys.Rcap = a.strideR;
+  return sys;
 }
 
-// Potential::force / forceBatch on S independent systems (include/eon/Potential.h:55-57,98-122).
-__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_force_batch(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
+__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_prepare(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
   EONB200_DYN_SMEM(smem_raw);
   const int s = blockIdx.x;
   if (s >= a.S) return;
@@ -59,26 +59,154 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_force_batch(const PotP
   if (threadIdx.x == 0) mbar_init(sm.mbar, 1);
   __syncthreads();
   uint32_t phase = 0;
-  SysView sys = make_sys(nl, s, a.N, a.R + static_cast<size_t>(s) * a.strideR, a.Z + static_cast<size_t>(s) * a.strideZ,
-                         a.box + static_cast<size_t>(s) * a.strideBox);
-  sys.Rcap = a.strideR;
+  const SysView sys = batch_sys(nl, a, s);
   const NlParams np = make_nl_params(P);
-  if (a.mode & FM_ENSURE) {
-    nl_ensure(np, sys, sm, phase, a.force_rebuild != 0);
+  nl_ensure(np, sys, sm, phase, a.force_rebuild != 0, P.exp_tab);
+  int flags = 0;
+  if (P.kind == POT_EAM) flags = eam_assign_rows(P, sys, sm.rowid, sm.red);
+  for (int i = threadIdx.x; i < a.N; i += blockDim.x) {
+    sys.pos4[i] = sm.pos[i];
+    if (P.kind == POT_EAM) sys.rowid[i] = sm.rowid[i];
+  }
+  if (threadIdx.x == 0) {
+    *sys.flags = flags;
+    *sys.done = 0;
+  }
+}
+
+// Common prologue of the tiled force kernels: positions of the whole system (one bulk copy), tables,
+// geometry.  Returns the atom range of this tile.
+__device__ inline void tile_prologue(const PotParams &P, const SysView &sys, Smem &sm, int tiles, int &i0, int &i1, bool want_dfd) {
+  const int N = sys.N;
+  if (threadIdx.x == 0) {
+    mbar_init(sm.mbar, 1);
+    bulk_g2s(sm.pos, sys.pos4, static_cast<uint32_t>(N) * 32u, sm.mbar);
+    Geom &g = *sm.geom;
+    for (int k = 0; k < 9; k++) g.H[k] = sys.box[k];
+    if (P.nl_mode == NL_MIC) {
+      const double need = 2.0 * P.rc_list + P.skin;
+      g.tab_ok = (g.H[0] >= need && g.H[4] >= need && g.H[8] >= need) ? 1 : 0;
+    } else {
+      g.tab_ok = (g.H[1] == 0.0 && g.H[2] == 0.0 && g.H[3] == 0.0 && g.H[5] == 0.0 && g.H[6] == 0.0 && g.H[7] == 0.0) ? 1 : 0;
+    }
+  }
+  for (int k = threadIdx.x; k < 128; k += blockDim.x) sm.exp_tab[k] = P.exp_tab[k];
+  for (int k = threadIdx.x; k < 48; k += blockDim.x) {
+    const int axis = k >> 4;
+    const double sft = static_cast<double>((k & 15) - 8);
+    const double len = sys.box[4 * axis];
+    const double val = P.nl_mode == NL_MIC ? -mul_rn(sft, len) : mul_rn(sft, len);
+    (axis == 0 ? sm.shx : (axis == 1 ? sm.shy : sm.shz))[k & 15] = val;
+  }
+  if (P.kind == POT_EAM)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sm.rowid[i] = sys.rowid[i];
+  __syncthreads();  // mbarrier initialised before anyone waits on it
+  mbar_wait(sm.mbar, 0);
+  if (want_dfd) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sm.pos[i].w = sys.dfd[i];
+  }
+  __syncthreads();
+  const int per = (N + tiles - 1) / tiles;
+  i0 = blockIdx.x * per;
+  i1 = i0 + per < N ? i0 + per : N;
+  if (i0 > N) i0 = N;
+}
+
+// Per-tile partial sums -> per-system energy; the last tile to finish adds them in tile order.
+__device__ inline void tile_epilogue(const SysView &sys, Smem &sm, int tiles, double (&acc)[2], int pass, double *U, bool final_pass) {
+  block_sum<2>(acc, sm.red);
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    sys.upart[blockIdx.x * 4 + 2 * pass] = acc[0];
+    sys.upart[blockIdx.x * 4 + 2 * pass + 1] = acc[1];
+    s_last = 0;
+    if (final_pass) {
+#ifndef EONB200_EMU
+      __threadfence();
+#endif
+      const int prev = atomicAdd(sys.done, 1);
+      s_last = (prev == tiles - 1) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (final_pass && s_last && threadIdx.x == 0) {
+#ifndef EONB200_EMU
+    __threadfence();
+#endif
+    double e = 0.0, n = 0.0;
+    for (int t = 0; t < tiles; t++) {
+      for (int p = 0; p <= pass; p++) {
+        e += sys.upart[t * 4 + 2 * p];
+        n += sys.upart[t * 4 + 2 * p + 1];
+      }
+    }
+    *U = (*sys.flags & 2) ? nan("") : e;
+    *sys.done = 0;
+    atomicAdd(&sys.stats[2], static_cast<unsigned long long>(n));
+  }
+}
+
+__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_eam_pass1(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
+  EONB200_DYN_SMEM(smem_raw);
+  const int s = blockIdx.y;
+  Smem sm = carve_smem_tile(smem_raw, a.N);
+  const PotParams &P = *Pp;
+  const SysView sys = batch_sys(nl, a, s);
+  int i0, i1;
+  tile_prologue(P, sys, sm, a.tiles, i0, i1, false);
+  double acc[2] = {0.0, 0.0};
+  const int flags = *sys.flags;
+  if (!(flags & 2)) {
+    if (flags & 1)
+      eam_pass1<true>(P, sys, sm, a.lpa, i0, i1, sys.dfd, acc);
+    else
+      eam_pass1<false>(P, sys, sm, a.lpa, i0, i1, sys.dfd, acc);
+  }
+  tile_epilogue(sys, sm, a.tiles, acc, 0, nullptr, false);
+}
+
+__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_eam_pass2(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
+  EONB200_DYN_SMEM(smem_raw);
+  const int s = blockIdx.y;
+  Smem sm = carve_smem_tile(smem_raw, a.N);
+  const PotParams &P = *Pp;
+  const SysView sys = batch_sys(nl, a, s);
+  int i0, i1;
+  tile_prologue(P, sys, sm, a.tiles, i0, i1, true);
+  double acc[2] = {0.0, 0.0};
+  const int flags = *sys.flags;
+  double *F = a.F + static_cast<size_t>(s) * a.strideR;
+  if (flags & 2) {
+    for (int k = 3 * i0 + threadIdx.x; k < 3 * i1; k += blockDim.x) F[k] = 0.0;
+  } else if (flags & 1) {
+    eam_pass2<true>(P, sys, sm, a.lpa, i0, i1, F, acc);
   } else {
-    stage_raw_positions(sys, sm, phase);
-    prepare_positions(np, sys, sm);
+    eam_pass2<false>(P, sys, sm, a.lpa, i0, i1, F, acc);
   }
-  if (a.mode & FM_FORCE) {
-    const double U = walker_forces(P, sys, sm, a.lpa);
-    store_forces(sm, a.F + static_cast<size_t>(s) * a.strideR, a.N, a.strideR);
-    if (threadIdx.x == 0) a.U[s] = U;
-  }
+  tile_epilogue(sys, sm, a.tiles, acc, 1, a.U + s, true);
+}
+
+__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_pair(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
+  EONB200_DYN_SMEM(smem_raw);
+  const int s = blockIdx.y;
+  Smem sm = carve_smem_tile(smem_raw, a.N);
+  const PotParams &P = *Pp;
+  const SysView sys = batch_sys(nl, a, s);
+  int i0, i1;
+  tile_prologue(P, sys, sm, a.tiles, i0, i1, false);
+  double acc[2] = {0.0, 0.0};
+  double *F = a.F + static_cast<size_t>(s) * a.strideR;
+  if (P.kind == POT_MORSE_PT)
+    pair_pass<POT_MORSE_PT>(P, sys, sm, a.lpa, i0, i1, F, acc);
+  else
+    pair_pass<POT_LJ>(P, sys, sm, a.lpa, i0, i1, F, acc);
+  tile_epilogue(sys, sm, a.tiles, acc, 0, a.U + s, true);
 }
 
 // Neighbour lists only (eonb200_neighbors): build with the caller's cutoff, skin 0.
 __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_neighbors(NlBatch nl, NlParams np, int S, int N, const double *R,
-                                                    const double *box, int maxCells) {
+                                                                    const double *box, int maxCells, const double *exp_tab) {
   EONB200_DYN_SMEM(smem_raw);
   const int s = blockIdx.x;
   if (s >= S) return;
@@ -88,7 +216,7 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_neighbors(NlBatch nl, 
   uint32_t phase = 0;
   SysView sys = make_sys(nl, s, N, R + static_cast<size_t>(s) * 3 * N, nullptr, box + static_cast<size_t>(s) * 9);
   sys.Rcap = 3 * N;
-  nl_ensure(np, sys, sm, phase, true);
+  nl_ensure(np, sys, sm, phase, true, exp_tab);
 }
 
 struct WalkerLaunch {
@@ -129,7 +257,7 @@ __device__ inline void setup_ctx(Ctx &c, const PotParams *Pp, const NlBatch &nl,
 
 // Resident walkers: the whole job of a walker runs inside one CTA, start to finish.
 __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_walkers(const PotParams *__restrict__ Pp, NlBatch nl, WalkerArrays wa,
-                                                  WalkerLaunch wl, const EonB200SearchParams *__restrict__ prm_g) {
+                                                                  WalkerLaunch wl, const EonB200SearchParams *__restrict__ prm_g) {
   EONB200_DYN_SMEM(smem_raw);
   __shared__ EonB200SearchParams prm_sh;
   __shared__ double cell_sh[19];
@@ -154,7 +282,7 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_walkers(const PotParam
   double eigenvalue = 0.0, conv = 0.0;
   if (wl.job == 4) {  // size the neighbour rows for the current geometry; no walker state changes
     c.sys.R = matter.pos;
-    nl_ensure(c.np, c.sys, c.sm, c.phase, true);
+    nl_ensure(c.np, c.sys, c.sm, c.phase, true, Pp->exp_tab);
     return;
   }
   // a job starts from a freshly loaded Matter: setPositions wraps and invalidates the force cache

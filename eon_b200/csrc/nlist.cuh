@@ -26,6 +26,7 @@ struct NlParams {
   int mode;       // NL_VESIN / NL_MIC
   double rc;      // list cutoff (potential cutoff + skin)
   double rc2;     // rc * rc, rounded once on the host exactly like `cutoff * cutoff`
+  double rc_core2;  // the potential's own cutoff^2: rows list these pairs first, the skin shell after them
   double skin;    // 0 -> rebuild on every evaluation
   int per[3];
 };
@@ -73,54 +74,70 @@ __device__ inline void stage_raw_positions(const SysView &sys, Smem &sm, uint32_
 
 // Geometry of the box + positions in the layout the predicate wants (sm.pos):
 //   NL_VESIN: raw coordinates.   NL_MIC: EAM.cpp:56-90 shifted / wrapped coordinates.
-// Also returns (to every thread) the largest squared displacement from the list's build positions.
-__device__ inline double prepare_positions(const NlParams &np, const SysView &sys, Smem &sm) {
+// Also fills the shift tables and the exp table, and returns (to every thread) the largest squared
+// displacement of the prepared positions from the ones the cached list was built with.
+__device__ inline double prepare_positions(const NlParams &np, const SysView &sys, Smem &sm, const double *exp_tab_g) {
   const int N = sys.N;
   const bool have_list = *sys.state != 0;
-  double v[4] = {1e300, 1e300, 1e300, 0.0};
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    const double x = sm.stage[3 * i], y = sm.stage[3 * i + 1], z = sm.stage[3 * i + 2];
-    v[0] = fmin(v[0], x);
-    v[1] = fmin(v[1], y);
-    v[2] = fmin(v[2], z);
-    if (have_list) {
-      const double dx = x - sys.rbuild[3 * i], dy = y - sys.rbuild[3 * i + 1], dz = z - sys.rbuild[3 * i + 2];
-      v[3] = fmax(v[3], dx * dx + dy * dy + dz * dz);
+  double v[3] = {1e300, 1e300, 1e300};
+  if (np.mode == NL_MIC) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      v[0] = fmin(v[0], sm.stage[3 * i]);
+      v[1] = fmin(v[1], sm.stage[3 * i + 1]);
+      v[2] = fmin(v[2], sm.stage[3 * i + 2]);
     }
+    const int op[3] = {RED_MIN, RED_MIN, RED_MIN};
+    block_reduce<3>(v, op, sm.red);
   }
-  const int op[4] = {RED_MIN, RED_MIN, RED_MIN, RED_MAX};
-  block_reduce<4>(v, op, sm.red);
   if (threadIdx.x == 0) {
     Geom &g = *sm.geom;
     for (int k = 0; k < 9; k++) g.H[k] = sys.box[k];
     g.ok = invert3(g.H, g.Hinv) ? 1 : 0;
     for (int k = 0; k < 3; k++) {
       const double lo = v[k] > 0.0 ? 0.0 : v[k];  // EAM.cpp:56-76: only negative minima shift
-      g.lo[k] = fabs(lo);
-      g.per[k] = np.per[k];
+      g.lo[k] = np.mode == NL_MIC ? fabs(lo) : 0.0;
+      g.per[k] = g.ok ? np.per[k] : 0;
+    }
+    if (np.mode == NL_MIC) {
+      // stored folds stay the reference's minimum image while every box length >= 2 rc_list + skin
+      const double need = 2.0 * np.rc + np.skin;
+      g.tab_ok = (g.H[0] >= need && g.H[4] >= need && g.H[8] >= need) ? 1 : 0;
+    } else {
+      g.tab_ok = (g.H[1] == 0.0 && g.H[2] == 0.0 && g.H[3] == 0.0 && g.H[5] == 0.0 && g.H[6] == 0.0 && g.H[7] == 0.0) ? 1 : 0;
     }
   }
+  for (int k = threadIdx.x; k < 128; k += blockDim.x) sm.exp_tab[k] = exp_tab_g[k];
   __syncthreads();
-  if (np.mode == NL_MIC) {
-    const Geom &g = *sm.geom;
-    const double L[3] = {g.H[0], g.H[4], g.H[8]};  // EAM.cpp:31 reads the diagonal only
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-      double p[3];
-      for (int k = 0; k < 3; k++) {
-        p[k] = sm.stage[3 * i + k] + g.lo[k];  // EAM.cpp:78-83
+  const Geom &g = *sm.geom;
+  for (int k = threadIdx.x; k < 48; k += blockDim.x) {
+    const int axis = k >> 4;
+    const double sft = static_cast<double>((k & 15) - 8);
+    const double len = g.H[4 * axis];
+    // NL_MIC: d = r_i - r_j, fold +1 means "dx > L/2 -> dx -= L" (EAM.cpp:157-168); NL_VESIN: + s * H_kk
+    const double val = np.mode == NL_MIC ? -mul_rn(sft, len) : mul_rn(sft, len);
+    (axis == 0 ? sm.shx : (axis == 1 ? sm.shy : sm.shz))[k & 15] = val;
+  }
+  double disp2 = 0.0;
+  const double L[3] = {g.H[0], g.H[4], g.H[8]};  // EAM.cpp:31 reads the diagonal only
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double p[3];
+    for (int k = 0; k < 3; k++) {
+      p[k] = sm.stage[3 * i + k];
+      if (np.mode == NL_MIC) {
+        p[k] += g.lo[k];  // EAM.cpp:78-83
         if (L[k] > 0.0) {
           int guard = 0;
           while (p[k] > L[k] && guard++ < 1000000) p[k] -= L[k];  // EAM.cpp:86-90
         }
       }
-      sm.pos[i] = make_double4(p[0], p[1], p[2], 0.0);
     }
-  } else {
-    for (int i = threadIdx.x; i < N; i += blockDim.x)
-      sm.pos[i] = make_double4(sm.stage[3 * i], sm.stage[3 * i + 1], sm.stage[3 * i + 2], 0.0);
+    sm.pos[i] = make_double4(p[0], p[1], p[2], 0.0);
+    if (have_list) {
+      const double dx = p[0] - sys.rbuild[3 * i], dy = p[1] - sys.rbuild[3 * i + 1], dz = p[2] - sys.rbuild[3 * i + 2];
+      disp2 = fmax(disp2, dx * dx + dy * dy + dz * dz);
+    }
   }
-  __syncthreads();
-  return v[3];
+  return block_max1(disp2, sm.red);
 }
 
 // Choose the cell grid (thread 0), given the list cutoff.  Cells are at least rc_eff wide so that
@@ -320,7 +337,21 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
     const int cz = ci % g.nc[2], cy = (ci / g.nc[2]) % g.nc[1], cx = ci / (g.nc[2] * g.nc[1]);
     const int wi = sm.wrapc[i];
     const int wix = (wi & 1023) - 512, wiy = ((wi >> 10) & 1023) - 512, wiz = ((wi >> 20) & 1023) - 512;
-    int count = 0;
+    // core pairs (inside the potential's cutoff) fill the row from the front, the skin shell from the back;
+    // the shell is moved down behind the core afterwards, so that the lanes of a warp accept / reject together
+    int ncore = 0, nshell = 0;
+    auto emit = [&](int code, bool core) {
+      if (ncore + nshell < K) {
+        if (core)
+          sys.nbr[static_cast<size_t>(ncore) * Np + i] = code;
+        else
+          sys.nbr[static_cast<size_t>(K - 1 - nshell) * Np + i] = code;
+      }
+      if (core)
+        ncore++;
+      else
+        nshell++;
+    };
     for (int ox = -g.ns[0]; ox <= g.ns[0]; ox++) {
       int qx = cx + ox, sx = 0;
       if (np.mode == NL_MIC || g.per[0]) {
@@ -365,8 +396,7 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
               if (fz > 0) dz -= g.H[8]; else if (fz < 0) dz += g.H[8];
               const double r2 = norm2_rn(dx, dy, dz);
               if (!(r2 <= np.rc2)) continue;
-              if (count < K) sys.nbr[static_cast<size_t>(count) * Np + i] = pack_nbr(j, 0, 0, 0);
-              count++;
+              emit(pack_nbr(j, fx, fy, fz), r2 <= np.rc_core2);
             } else {
               const int wj = sm.wrapc[j];
               const int Sx = sx + wix - ((wj & 1023) - 512);
@@ -387,14 +417,21 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
                 bad_shift = true;
                 continue;
               }
-              if (count < K) sys.nbr[static_cast<size_t>(count) * Np + i] = pack_nbr(j, Sx, Sy, Sz);
-              count++;
+              emit(pack_nbr(j, Sx, Sy, Sz), d2 < np.rc_core2);
             }
           }
         }
       }
     }
-    sys.cnt[i] = count < K ? count : K;
+    const int count = ncore + nshell;
+    if (count <= K) {
+      // fill the hole between core and shell from the top of the shell
+      const int holes = K - nshell - ncore;
+      const int moves = nshell < holes ? nshell : holes;
+      for (int t = 0; t < moves; t++)
+        sys.nbr[static_cast<size_t>(ncore + t) * Np + i] = sys.nbr[static_cast<size_t>(K - 1 - t) * Np + i];
+    }
+    sys.cnt[i] = count <= K ? count : 0;
     my_max = max(my_max, count);
   }
   if (bad_shift) my_max = 1 << 30;  // unrepresentable image shift: reported as an overflow that never fits
@@ -408,9 +445,9 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
 // On return sm.pos holds the positions in the predicate's layout and sm.stage the raw ones.
 // Returns (to all threads) the largest row fill of a rebuild (> sys.K: the list is truncated), 0 if reused.
 __device__ inline int nl_ensure(const NlParams &np, const SysView &sys, Smem &sm, uint32_t &phase,
-                                bool force_rebuild) {
+                                bool force_rebuild, const double *exp_tab_g) {
   stage_raw_positions(sys, sm, phase);
-  const double disp2 = prepare_positions(np, sys, sm);
+  const double disp2 = prepare_positions(np, sys, sm, exp_tab_g);
   const bool have = *sys.state != 0;
   const double lim = 0.5 * np.skin;
   const bool rebuild = force_rebuild || !have || np.skin <= 0.0 || !(disp2 <= lim * lim);
@@ -418,7 +455,12 @@ __device__ inline int nl_ensure(const NlParams &np, const SysView &sys, Smem &sm
   int row_max = 0;
   if (rebuild) {
     row_max = nl_build(np, sys, sm);
-    for (int k = threadIdx.x; k < 3 * sys.N; k += blockDim.x) sys.rbuild[k] = sm.stage[k];
+    for (int i = threadIdx.x; i < sys.N; i += blockDim.x) {
+      const double4 p = sm.pos[i];
+      sys.rbuild[3 * i] = p.x;
+      sys.rbuild[3 * i + 1] = p.y;
+      sys.rbuild[3 * i + 2] = p.z;
+    }
     if (threadIdx.x == 0) {
       *sys.state = 1;
       atomicAdd(&sys.stats[0], 1ULL);

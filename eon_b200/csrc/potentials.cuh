@@ -1,17 +1,23 @@
-// potentials.cuh -- FP64 energy/force evaluation of one walker by its CTA.
+// potentials.cuh -- FP64 energy/force evaluation of (a tile of) one walker by a CTA.
 //
 // Thread mapping: `lpa` adjacent lanes share one atom and split its neighbour row; the atom's
-// force and density are combined with an xor butterfly inside the lane group (fixed order), and
-// per-walker scalars (energy, pair count) with one block reduction.  Neighbour rows come from the
-// cached candidate list (nlist.cuh); every candidate is re-tested with the potential's own exact
-// predicate, so the result does not depend on the skin.
+// force / density are combined with an xor butterfly inside the lane group (fixed order) and the
+// per-walker scalars (energy, pair count) with a block reduction.  Rows come from the cached
+// candidate list (nlist.cuh): pairs inside the potential's cutoff first, the Verlet skin shell
+// after them, so the lanes of a warp accept and reject together.  Every candidate is re-tested
+// with the potential's own exact (un-fused) predicate, so results do not depend on the skin.
 //
 //   LJ / LJCluster / Morse_Pt: arithmetic of the un-vendored rgpot kernels the reference reaches
 //     through RgpotAdapter (include/eon/potentials/RgpotAdapter/RgpotAdapter.h:41-50,68-94,
 //     factory arms client/Potential.cpp:140-153); forms pinned by the reference's goldens
 //     (client/unit_tests/PotTest.cpp:38-43,130-132; data/reference/point_morse_pt.dat).
-//   EAM: client/potentials/EAM/EAM.cpp:125-226,349-365 as a density pass, the embedding
-//     polynomial, and a force pass that gathers F'_i g'_i(r) + F'_j g'_j(r) + pair'(r).
+//   EAM: client/potentials/EAM/EAM.cpp:125-226,349-365 as a pipeline:
+//     pass 1 (density)  per ordered pair: r, the three exponentials, rho_i += g(r); the pair's
+//                       g'(r)/r and +-phi'(r)/r are kept in HBM/L2 scratch (pairA / pairB);
+//     embedding         F(rho_i), F'(rho_i) by Horner (EAM.cpp:349-365);
+//     pass 2 (force)    F_i = -sum_j [(F'_i + F'_j) g'(r)/r +- phi'(r)/r] d, a pure gather with no
+//                       transcendental, sqrt or division.
+//   Systems with several elements take a slower variant of pass 2 that re-derives the per-row terms.
 #pragma once
 #include "nlist.cuh"
 
@@ -24,47 +30,130 @@ __device__ __forceinline__ double group_sum_rt(double v, int lpa) {
   return v;
 }
 
-// ---- LJ / Morse --------------------------------------------------------------------------------
-// Forces land in sm.stage ([3N], raw, unmasked).  Returns the energy to every thread.
-template <int KIND>
-__device__ EONB200_NOINLINE double pair_forces(const PotParams &P, const SysView &sys, Smem &sm, int lpa) {
-  const int N = sys.N;
-  const int group = threadIdx.x / lpa, gl = threadIdx.x % lpa, ngroups = blockDim.x / lpa;
+// ---- exp ---------------------------------------------------------------------------------------------
+// Table-driven exp in the style of glibc's: x = (128 k + j) ln2/128 + r, |r| <= ln2/256,
+// e^x = 2^k * T[j] * (1 + r + ... + r^5/120).  T = 2^(j/128) lives in shared memory.  About a third of
+// the FP64 instructions of the library exp; error below 1 ulp over the range the potentials use
+// (arguments in [-700, 700]; smaller arguments return 0).
+__device__ __forceinline__ double exp_tab(double x, const double *T) {
+  const double kInv = 184.6649652337873;            // 128 / ln 2
+  const double kShift = 6755399441055744.0;         // 1.5 * 2^52
+  const double kLn2Hi = 6.93147180369123816490e-01 / 128.0;  // high part of ln2 (trailing zeros), exact / 128
+  const double kLn2Lo = 1.90821492927058770002e-10 / 128.0;
+  double kd = fma(x, kInv, kShift);
+#ifdef EONB200_EMU
+  long long ki;
+  memcpy(&ki, &kd, 8);
+#else
+  const long long ki = __double_as_longlong(kd);
+#endif
+  kd -= kShift;
+  double r = fma(kd, -kLn2Hi, x);
+  r = fma(kd, -kLn2Lo, r);
+  const int k = static_cast<int>(ki);
+  const double t = T[k & 127];
+  double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  const double res = fma(t, q * r, t);
+  const long long e = static_cast<long long>(k >> 7) << 52;
+#ifdef EONB200_EMU
+  long long bits;
+  memcpy(&bits, &res, 8);
+  bits += e;
+  double out;
+  memcpy(&out, &bits, 8);
+#else
+  const double out = __longlong_as_double(__double_as_longlong(res) + e);
+#endif
+  return x < -700.0 ? 0.0 : out;
+}
+
+__device__ __forceinline__ double rsqrt_f64(double x) {
+#ifdef EONB200_EMU
+  return 1.0 / sqrt(x);
+#else
+  return rsqrt(x);
+#endif
+}
+
+// ---- pair vectors --------------------------------------------------------------------------------------
+// NL_VESIN: v = (r_j - r_i) + S.H, un-fused (vesin-single-build.cpp:1199-1202).
+__device__ __forceinline__ void vesin_vec(const Smem &sm, int code, const double4 &pi, const double4 &pj, double &vx,
+                                          double &vy, double &vz) {
   const Geom &g = *sm.geom;
-  double H[9];
-#pragma unroll
-  for (int k = 0; k < 9; k++) H[k] = g.H[k];
+  vx = sub_rn(pj.x, pi.x);
+  vy = sub_rn(pj.y, pi.y);
+  vz = sub_rn(pj.z, pi.z);
+  const unsigned s = static_cast<unsigned>(code) >> kNbrIndexBits;
+  if (s == static_cast<unsigned>(kShiftNeutral)) return;
+  if (g.tab_ok) {  // orthorhombic cell: S.H is one product per axis
+    vx = add_rn(vx, sm.shx[s & 15]);
+    vy = add_rn(vy, sm.shy[(s >> 4) & 15]);
+    vz = add_rn(vz, sm.shz[(s >> 8) & 15]);
+  } else {
+    const double ax = static_cast<double>(static_cast<int>(s & 15) - 8), ay = static_cast<double>(static_cast<int>((s >> 4) & 15) - 8),
+                 az = static_cast<double>(static_cast<int>((s >> 8) & 15) - 8);
+    vx = add_rn(vx, add_rn(add_rn(mul_rn(ax, g.H[0]), mul_rn(ay, g.H[3])), mul_rn(az, g.H[6])));
+    vy = add_rn(vy, add_rn(add_rn(mul_rn(ax, g.H[1]), mul_rn(ay, g.H[4])), mul_rn(az, g.H[7])));
+    vz = add_rn(vz, add_rn(add_rn(mul_rn(ax, g.H[2]), mul_rn(ay, g.H[5])), mul_rn(az, g.H[8])));
+  }
+}
+
+// NL_MIC: d = r_i - r_j folded once by +-L (EAM.cpp:152-168).  The fold recorded at build time is the
+// reference's fold while the box is at least 2 rc_list + skin wide; otherwise it is re-derived.
+__device__ __forceinline__ void mic_vec(const Smem &sm, int code, const double4 &pi, const double4 &pj, double &dx, double &dy,
+                                        double &dz) {
+  const Geom &g = *sm.geom;
+  dx = pi.x - pj.x;
+  dy = pi.y - pj.y;
+  dz = pi.z - pj.z;
+  if (g.tab_ok) {
+    const unsigned s = static_cast<unsigned>(code) >> kNbrIndexBits;
+    dx += sm.shx[s & 15];
+    dy += sm.shy[(s >> 4) & 15];
+    dz += sm.shz[(s >> 8) & 15];
+  } else {
+    const double Lx = g.H[0], Ly = g.H[4], Lz = g.H[8];
+    if (dx > 0.5 * Lx) dx -= Lx; else if (dx < -0.5 * Lx) dx += Lx;
+    if (dy > 0.5 * Ly) dy -= Ly; else if (dy < -0.5 * Ly) dy += Ly;
+    if (dz > 0.5 * Lz) dz -= Lz; else if (dz < -0.5 * Lz) dz += Lz;
+  }
+}
+
+// ---- LJ / Morse ------------------------------------------------------------------------------------------
+// Atoms [i0, i1) of the walker staged in sm.pos; forces to F[3 (i - fbase)...] (shared or global).
+// acc[0] += energy share, acc[1] += ordered pairs (per-lane partials, reduced by the caller).
+template <int KIND>
+__device__ EONB200_NOINLINE void pair_pass(const PotParams &P, const SysView &sys, const Smem &sm, int lpa, int i0, int i1,
+                                          double *F, double (&acc)[2]) {
+  const int group = threadIdx.x / lpa, gl = threadIdx.x % lpa, ngroups = blockDim.x / lpa;
   const double rc2 = P.cutoff2, eshift = P.eshift;
   const double De = P.morse_De, ma = P.morse_a, re = P.morse_re;
   const double u0 = P.lj_u0, psi2 = P.lj_psi * P.lj_psi;
   double e_acc = 0.0, n_acc = 0.0;
-  for (int i0 = 0; i0 < N; i0 += ngroups) {
-    const int i = i0 + group;
+  for (int ib = i0; ib < i1; ib += ngroups) {
+    const int i = ib + group;
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    if (i < N) {
+    if (i < i1) {
       const double4 pi = sm.pos[i];
       const int n = sys.cnt[i];
       for (int k = gl; k < n; k += lpa) {
         const int code = sys.nbr[static_cast<size_t>(k) * sys.Np + i];
-        int j, sx, sy, sz;
-        unpack_nbr(code, j, sx, sy, sz);
-        const double4 pj = sm.pos[j];
-        double vx = sub_rn(pj.x, pi.x), vy = sub_rn(pj.y, pi.y), vz = sub_rn(pj.z, pi.z);
-        if ((sx | sy | sz) != 0) {
-          const double ax = static_cast<double>(sx), ay = static_cast<double>(sy), az = static_cast<double>(sz);
-          vx = add_rn(vx, add_rn(add_rn(mul_rn(ax, H[0]), mul_rn(ay, H[3])), mul_rn(az, H[6])));
-          vy = add_rn(vy, add_rn(add_rn(mul_rn(ax, H[1]), mul_rn(ay, H[4])), mul_rn(az, H[7])));
-          vz = add_rn(vz, add_rn(add_rn(mul_rn(ax, H[2]), mul_rn(ay, H[5])), mul_rn(az, H[8])));
-        }
+        const double4 pj = sm.pos[code & kNbrIndexMask];
+        double vx, vy, vz;
+        vesin_vec(sm, code, pi, pj, vx, vy, vz);
         const double d2 = norm2_rn(vx, vy, vz);
         if (!(d2 < rc2)) continue;
         double e, s;  // pair energy and (dU/dr)/r
         if (KIND == POT_MORSE_PT) {
-          const double r = sqrt(d2);
-          const double ex = exp(-ma * (r - re));
+          const double invr = rsqrt_f64(d2);
+          const double r = d2 * invr;
+          const double ex = exp_tab(-ma * (r - re), sm.exp_tab);
           const double d = 1.0 - ex;
           e = De * d * d - De;
-          s = (2.0 * De * ma * d * ex) / r;
+          s = (2.0 * De * ma * d * ex) * invr;
         } else {
           const double sr2 = psi2 / d2;
           const double sr6 = sr2 * sr2 * sr2;
@@ -82,19 +171,17 @@ __device__ EONB200_NOINLINE double pair_forces(const PotParams &P, const SysView
     fx = group_sum_rt(fx, lpa);
     fy = group_sum_rt(fy, lpa);
     fz = group_sum_rt(fz, lpa);
-    if (i < N && gl == 0) {
-      sm.stage[3 * i] = fx;
-      sm.stage[3 * i + 1] = fy;
-      sm.stage[3 * i + 2] = fz;
+    if (i < i1 && gl == 0) {
+      F[3 * i] = fx;
+      F[3 * i + 1] = fy;
+      F[3 * i + 2] = fz;
     }
   }
-  double v[2] = {e_acc, n_acc};
-  block_sum<2>(v, sm.red);
-  if (threadIdx.x == 0) atomicAdd(&sys.stats[2], static_cast<unsigned long long>(v[1]));
-  return v[0];
+  acc[0] += e_acc;
+  acc[1] += n_acc;
 }
 
-// ---- EAM ------------------------------------------------------------------------------------------
+// ---- EAM ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double eam_embed(const double *c, double rho) {  // EAM.cpp:349-356
   double acc = c[8];
 #pragma unroll
@@ -107,15 +194,9 @@ __device__ __forceinline__ double eam_dembed(const double *dc, double rho) {  //
   for (int k = 7; k >= 1; k--) acc = acc * rho + dc[k];
   return acc;
 }
-__device__ __forceinline__ void eam_fold(double &d, double L, double h) {  // EAM.cpp:157-168
-  if (d > h)
-    d -= L;
-  else if (d < -h)
-    d += L;
-}
 
-// Element rows of the atoms (sm.rowid); returns false to every thread if an element is unknown.
-__device__ inline bool eam_assign_rows(const PotParams &P, const SysView &sys, Smem &sm, bool &multi) {
+// Element rows of the atoms -> rowid[] (shared or global); flags: bit 0 mixed elements, bit 1 unknown element.
+__device__ inline int eam_assign_rows(const PotParams &P, const SysView &sys, unsigned char *rowid, double *red) {
   double bad = 0.0, mixed = 0.0;
   const int z0 = sys.Z[0];
   for (int i = threadIdx.x; i < sys.N; i += blockDim.x) {
@@ -126,129 +207,133 @@ __device__ inline bool eam_assign_rows(const PotParams &P, const SysView &sys, S
         r = q;
         break;
       }
-    sm.rowid[i] = static_cast<unsigned char>(r);
+    rowid[i] = static_cast<unsigned char>(r);
     if (r == 255) bad = 1.0;
     if (z != z0) mixed = 1.0;
   }
   double v[2] = {bad, mixed};
   const int op[2] = {RED_MAX, RED_MAX};
-  block_reduce<2>(v, op, sm.red);
-  multi = v[1] != 0.0;
-  return v[0] == 0.0;
+  block_reduce<2>(v, op, red);
+  return (v[1] != 0.0 ? 1 : 0) | (v[0] != 0.0 ? 2 : 0);
 }
 
-// g(r) = r^6 (e^{-b1 r} + 512 e^{-2 b2 r}) and g'(r), EAM.cpp:174-190
-__device__ __forceinline__ void eam_density_terms(const EamRowDev &p, double r, double r2, double &gval, double &gder) {
+// g'(r) of one row: d/dr [r^6 (e^{-b1 r} + 512 e^{-2 b2 r})], EAM.cpp:174-190
+__device__ __forceinline__ double eam_gder(const EamRowDev &p, double r, double r2, const double *T) {
   const double r6 = r2 * r2 * r2;
-  const double e1 = exp(-p.beta1 * r);
-  const double e2 = exp(-2.0 * p.beta2 * r);
+  const double e1 = exp_tab(-p.beta1 * r, T);
+  const double e2 = exp_tab(-2.0 * p.beta2 * r, T);
   const double rho_pair = e1 + 512.0 * e2;
-  gval = r6 * rho_pair;
   const double r5 = r2 * r2 * r;
-  gder = 6.0 * r5 * rho_pair + r6 * (-p.beta1 * e1 - 1024.0 * p.beta2 * e2);
+  return 6.0 * r5 * rho_pair + r6 * (-p.beta1 * e1 - 1024.0 * p.beta2 * e2);
 }
 
+// Pass 1 over atoms [i0, i1): densities with the row of atom i (EAM.cpp:140,172-183) -> dF/drho into
+// dfd[i], embedding energy; single-element systems also do the whole pair arithmetic here.
 template <bool MULTI>
-__device__ EONB200_NOINLINE double eam_forces(const PotParams &P, const SysView &sys, Smem &sm, int lpa) {
-  const int N = sys.N;
+__device__ EONB200_NOINLINE void eam_pass1(const PotParams &P, const SysView &sys, const Smem &sm, int lpa, int i0, int i1,
+                                          double *dfd, double (&acc)[2]) {
   const int group = threadIdx.x / lpa, gl = threadIdx.x % lpa, ngroups = blockDim.x / lpa;
-  const Geom &g = *sm.geom;
-  const double Lx = g.H[0], Ly = g.H[4], Lz = g.H[8];
-  const double hx = Lx * 0.5, hy = Ly * 0.5, hz = Lz * 0.5;
-  const EamRowDev row0 = P.rows[sm.rowid[0]];
+  const double *T = sm.exp_tab;
+  const EamRowDev *row0 = &P.rows[sm.rowid[0]];
+  const double pair_sign = P.eam_conservative ? 1.0 : -1.0;
   double e_acc = 0.0, n_acc = 0.0;
-
-  // pass 1: densities with the row of atom i (EAM.cpp:140,172-183) -> embedding energy, dF/drho
-  for (int i0 = 0; i0 < N; i0 += ngroups) {
-    const int i = i0 + group;
+  for (int ib = i0; ib < i1; ib += ngroups) {
+    const int i = ib + group;
     double dens = 0.0;
-    if (i < N) {
+    if (i < i1) {
       const double4 pi = sm.pos[i];
       const int n = sys.cnt[i];
-      const EamRowDev *pr = MULTI ? &P.rows[sm.rowid[i]] : &row0;
-      const double b1 = pr->beta1, b2x2 = 2.0 * pr->beta2, rc2 = pr->rc2;
+      const EamRowDev *pr = MULTI ? &P.rows[sm.rowid[i]] : row0;
+      const double b1 = pr->beta1, b2 = pr->beta2, rc2 = pr->rc2;
+      const double aM = pr->alphaM, Rm = pr->Rm, Dm = pr->Dm;
       for (int k = gl; k < n; k += lpa) {
-        const int j = sys.nbr[static_cast<size_t>(k) * sys.Np + i] & kNbrIndexMask;
-        const double4 pj = sm.pos[j];
-        double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-        eam_fold(dx, Lx, hx);
-        eam_fold(dy, Ly, hy);
-        eam_fold(dz, Lz, hz);
+        const size_t slot = static_cast<size_t>(k) * sys.Np + i;
+        const int code = sys.nbr[slot];
+        const double4 pj = sm.pos[code & kNbrIndexMask];
+        double dx, dy, dz;
+        mic_vec(sm, code, pi, pj, dx, dy, dz);
         const double r2 = norm2_rn(dx, dy, dz);
         if (r2 > rc2) continue;  // EAM.cpp:172 (inclusive cutoff)
-        const double r = sqrt(r2);
+        const double invr = rsqrt_f64(r2);
+        const double r = r2 * invr;
         const double r6 = r2 * r2 * r2;
-        dens += r6 * (exp(-b1 * r) + 512.0 * exp(-b2x2 * r));
+        const double e1 = exp_tab(-b1 * r, T);
+        const double e2 = exp_tab(-2.0 * b2 * r, T);
+        const double rho_pair = e1 + 512.0 * e2;
+        dens += r6 * rho_pair;
         n_acc += 1.0;
+        if (!MULTI) {
+          const double r5 = r2 * r2 * r;
+          const double gder = 6.0 * r5 * rho_pair + r6 * (-b1 * e1 - 1024.0 * b2 * e2);
+          sys.pairA[slot] = gder * invr;
+          const double ex = exp_tab(-aM * (r - Rm), T);
+          const double d = 1.0 - ex;
+          sys.pairB[slot] = pair_sign * (2.0 * aM * Dm * d * ex) * invr;
+          e_acc += 0.5 * (Dm * d * d - Dm);  // the pair energy is counted from both ends
+        }
       }
     }
     dens = group_sum_rt(dens, lpa);
-    if (i < N && gl == 0) {
-      const EamRowDev *pr = MULTI ? &P.rows[sm.rowid[i]] : &row0;
+    if (i < i1 && gl == 0) {
+      const EamRowDev *pr = MULTI ? &P.rows[sm.rowid[i]] : row0;
       e_acc += eam_embed(pr->c, dens);
-      sm.dfd[i] = eam_dembed(pr->dc, dens);
+      dfd[i] = eam_dembed(pr->dc, dens);
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < N; i += blockDim.x) sm.pos[i].w = sm.dfd[i];
-  __syncthreads();
+  acc[0] += e_acc;
+  acc[1] += n_acc;
+}
 
-  // pass 2: F_i = -sum_j [F'_i g'_i(r) + F'_j g'_j(r) + s phi'_m(r)] d / r, d = r_i - r_j,
-  // m = min(i, j) (EAM.cpp:200: the pair part uses the row of the lower index), s = +1 for
-  // F = -grad U and -1 for the reference's own sign (EAM.cpp:203-215).
+// Pass 2 over atoms [i0, i1): sm.pos[j].w must hold dF/drho of atom j.
+//   F_i = -sum_j [F'_i g'_i(r) + F'_j g'_j(r) + s phi'_m(r)] d / r,  d = r_i - r_j, m = min(i, j)
+// (EAM.cpp:200: the pair part uses the row of the lower index), s = +1 for F = -grad U and -1 for the
+// reference's own sign (EAM.cpp:203-215).
+template <bool MULTI>
+__device__ EONB200_NOINLINE void eam_pass2(const PotParams &P, const SysView &sys, const Smem &sm, int lpa, int i0, int i1,
+                                          double *F, double (&acc)[2]) {
+  const int group = threadIdx.x / lpa, gl = threadIdx.x % lpa, ngroups = blockDim.x / lpa;
+  const double *T = sm.exp_tab;
+  const EamRowDev *row0 = &P.rows[sm.rowid[0]];
   const double pair_sign = P.eam_conservative ? 1.0 : -1.0;
-  for (int i0 = 0; i0 < N; i0 += ngroups) {
-    const int i = i0 + group;
+  double e_acc = 0.0;
+  for (int ib = i0; ib < i1; ib += ngroups) {
+    const int i = ib + group;
     double fx = 0.0, fy = 0.0, fz = 0.0;
-    if (i < N) {
+    if (i < i1) {
       const double4 pi = sm.pos[i];
       const int n = sys.cnt[i];
-      const EamRowDev *pri = MULTI ? &P.rows[sm.rowid[i]] : &row0;
+      const EamRowDev *pri = MULTI ? &P.rows[sm.rowid[i]] : row0;
+      const double rc2 = pri->rc2;
       for (int k = gl; k < n; k += lpa) {
-        const int j = sys.nbr[static_cast<size_t>(k) * sys.Np + i] & kNbrIndexMask;
+        const size_t slot = static_cast<size_t>(k) * sys.Np + i;
+        const int code = sys.nbr[slot];
+        const int j = code & kNbrIndexMask;
         const double4 pj = sm.pos[j];
-        double dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-        eam_fold(dx, Lx, hx);
-        eam_fold(dy, Ly, hy);
-        eam_fold(dz, Lz, hz);
+        double dx, dy, dz;
+        mic_vec(sm, code, pi, pj, dx, dy, dz);
         const double r2 = norm2_rn(dx, dy, dz);
-        double coef = 0.0;
-        double r, invr;
+        double s3;
         if (!MULTI) {
-          if (r2 > pri->rc2) continue;
-          r = sqrt(r2);
-          invr = 1.0 / r;
-          double gv, gd;
-          eam_density_terms(*pri, r, r2, gv, gd);
-          coef = (pi.w + pj.w) * gd;
-          const double ex = exp(-pri->alphaM * (r - pri->Rm));
-          const double d = 1.0 - ex;
-          coef += pair_sign * 2.0 * pri->alphaM * pri->Dm * d * ex;
-          e_acc += 0.5 * (pri->Dm * d * d - pri->Dm);
+          if (r2 > rc2) continue;
+          s3 = -((pi.w + pj.w) * sys.pairA[slot] + sys.pairB[slot]);
         } else {
           const EamRowDev *prj = &P.rows[sm.rowid[j]];
           const EamRowDev *prm = (i < j) ? pri : prj;
           const bool in_i = !(r2 > pri->rc2), in_j = !(r2 > prj->rc2), in_m = !(r2 > prm->rc2);
-          if (!(in_i || in_j)) continue;
-          r = sqrt(r2);
-          invr = 1.0 / r;
-          double gv, gd;
-          if (in_i) {
-            eam_density_terms(*pri, r, r2, gv, gd);
-            coef += pi.w * gd;
-          }
-          if (in_j) {
-            eam_density_terms(*prj, r, r2, gv, gd);
-            coef += pj.w * gd;
-          }
+          if (!(in_i || in_j || in_m)) continue;
+          const double invr = rsqrt_f64(r2);
+          const double r = r2 * invr;
+          double coef = 0.0;
+          if (in_i) coef += pi.w * eam_gder(*pri, r, r2, T);
+          if (in_j) coef += pj.w * eam_gder(*prj, r, r2, T);
           if (in_m) {
-            const double ex = exp(-prm->alphaM * (r - prm->Rm));
+            const double ex = exp_tab(-prm->alphaM * (r - prm->Rm), T);
             const double d = 1.0 - ex;
             coef += pair_sign * 2.0 * prm->alphaM * prm->Dm * d * ex;
             e_acc += 0.5 * (prm->Dm * d * d - prm->Dm);
           }
+          s3 = -coef * invr;
         }
-        const double s3 = -coef * invr;
         fx += s3 * dx;
         fy += s3 * dy;
         fz += s3 * dz;
@@ -257,36 +342,47 @@ __device__ EONB200_NOINLINE double eam_forces(const PotParams &P, const SysView 
     fx = group_sum_rt(fx, lpa);
     fy = group_sum_rt(fy, lpa);
     fz = group_sum_rt(fz, lpa);
-    if (i < N && gl == 0) {
-      sm.stage[3 * i] = fx;
-      sm.stage[3 * i + 1] = fy;
-      sm.stage[3 * i + 2] = fz;
+    if (i < i1 && gl == 0) {
+      F[3 * i] = fx;
+      F[3 * i + 1] = fy;
+      F[3 * i + 2] = fz;
     }
   }
-  double v[2] = {e_acc, n_acc};
-  block_sum<2>(v, sm.red);
-  if (threadIdx.x == 0) atomicAdd(&sys.stats[2], static_cast<unsigned long long>(v[1]));
-  return v[0];
+  acc[0] += e_acc;
 }
 
-// Energy + raw forces (into sm.stage) of the walker whose positions are staged in sm.pos.
+// Energy + raw forces (into sm.stage) of the whole walker staged in sm.pos -- the resident kernels' path.
 // Returns NaN if an element has no EAM row (the reference throws 14324, EAM.cpp:116-123).
 __device__ inline double walker_forces(const PotParams &P, const SysView &sys, Smem &sm, int lpa) {
-  switch (P.kind) {
-    case POT_MORSE_PT:
-      return pair_forces<POT_MORSE_PT>(P, sys, sm, lpa);
-    case POT_EAM: {
-      bool multi = false;
-      if (!eam_assign_rows(P, sys, sm, multi)) {
-        for (int k = threadIdx.x; k < 3 * sys.N; k += blockDim.x) sm.stage[k] = 0.0;
-        __syncthreads();
-        return nan("");
-      }
-      return multi ? eam_forces<true>(P, sys, sm, lpa) : eam_forces<false>(P, sys, sm, lpa);
+  double acc[2] = {0.0, 0.0};
+  const int N = sys.N;
+  if (P.kind == POT_EAM) {
+    const int flags = eam_assign_rows(P, sys, sm.rowid, sm.red);
+    if (flags & 2) {
+      for (int k = threadIdx.x; k < 3 * N; k += blockDim.x) sm.stage[k] = 0.0;
+      __syncthreads();
+      return nan("");
     }
-    default:
-      return pair_forces<POT_LJ>(P, sys, sm, lpa);
+    const bool multi = (flags & 1) != 0;
+    if (multi)
+      eam_pass1<true>(P, sys, sm, lpa, 0, N, sm.dfd, acc);
+    else
+      eam_pass1<false>(P, sys, sm, lpa, 0, N, sm.dfd, acc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) sm.pos[i].w = sm.dfd[i];
+    __syncthreads();
+    if (multi)
+      eam_pass2<true>(P, sys, sm, lpa, 0, N, sm.stage, acc);
+    else
+      eam_pass2<false>(P, sys, sm, lpa, 0, N, sm.stage, acc);
+  } else if (P.kind == POT_MORSE_PT) {
+    pair_pass<POT_MORSE_PT>(P, sys, sm, lpa, 0, N, sm.stage, acc);
+  } else {
+    pair_pass<POT_LJ>(P, sys, sm, lpa, 0, N, sm.stage, acc);
   }
+  block_sum<2>(acc, sm.red);
+  if (threadIdx.x == 0) atomicAdd(&sys.stats[2], static_cast<unsigned long long>(acc[1]));
+  return acc[0];
 }
 
 }  // namespace eonb200

@@ -143,7 +143,7 @@ __device__ inline void matter_set_positions_free(const Ctx &c, MatterS &m, const
 __device__ EONB200_NOINLINE void matter_compute(Ctx &c, MatterS &m) {
   if (!m.dirty) return;
   c.sys.R = m.pos;
-  if (nl_ensure(c.np, c.sys, c.sm, c.phase, false) > c.sys.K) c.failed = 1;  // truncated list
+  if (nl_ensure(c.np, c.sys, c.sm, c.phase, false, c.P->exp_tab) > c.sys.K) c.failed = 1;  // truncated list
   double U = walker_forces(*c.P, c.sys, c.sm, c.lpa);
   if (U != U) c.failed = 1;
   c.force_calls++;

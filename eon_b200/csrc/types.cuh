@@ -8,6 +8,7 @@ enum PotKind { POT_LJ = 0, POT_LJCLUSTER = 1, POT_MORSE_PT = 2, POT_EAM = 3 };
 enum NlMode { NL_VESIN = 0, NL_MIC = 1 };
 
 constexpr int kMaxEamRows = 8;
+constexpr int kMaxTiles = 16;
 
 // One element row of include/eon/potentials/EAM/Parameters.h:15-50 plus derived constants.
 struct EamRowDev {
@@ -29,6 +30,7 @@ struct PotParams {
   double morse_De, morse_a, morse_re;
   int n_rows;
   int eam_conservative;
+  const double *exp_tab;  // [128] 2^(j/128), device memory (table of the exp used by the pair loops)
   EamRowDev rows[kMaxEamRows];
 };
 
@@ -56,6 +58,15 @@ struct NlBatch {
   int K, Np;
   int *overflow;             // [1] largest row fill any build needed (> K means the list is truncated)
   unsigned long long *stats; // [0] rebuilt, [1] reused, [2] ordered pairs of the last evaluation
+  // scratch of the tiled / two-pass force pipeline
+  double *pairA;    // [S][K][Np] EAM: g'(r)/r of the ordered pair in slot (k, i), written by the density pass
+  double *pairB;    // [S][K][Np] EAM: +-phi'(r)/r
+  double4 *pos4;    // [S][Np]    prepared positions (stateless tiled kernels)
+  double *dfd;      // [S][Np]    EAM dF/drho
+  unsigned char *rowid;  // [S][Np]
+  int *flags;       // [S] bit 0: more than one element, bit 1: element without a row
+  double *upart;    // [S][kMaxTiles][4] energy / pair-count partials per tile and pass
+  int *done;        // [S] tiles finished (last one sums the partials in tile order)
 };
 
 // One system as seen by its CTA.
@@ -72,6 +83,13 @@ struct SysView {
   int K, Np;
   int *overflow;
   unsigned long long *stats;
+  double *pairA, *pairB;  // this system's [K][Np] blocks (null for the pair potentials)
+  double4 *pos4;
+  double *dfd;
+  unsigned char *rowid;
+  int *flags;
+  double *upart;
+  int *done;
 };
 
 __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, const double *R, const int *Z,
@@ -90,6 +108,14 @@ __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, con
   v.Np = nl.Np;
   v.overflow = nl.overflow;
   v.stats = nl.stats;
+  v.pairA = nl.pairA ? nl.pairA + static_cast<size_t>(s) * nl.K * nl.Np : nullptr;
+  v.pairB = nl.pairB ? nl.pairB + static_cast<size_t>(s) * nl.K * nl.Np : nullptr;
+  v.pos4 = nl.pos4 ? nl.pos4 + static_cast<size_t>(s) * nl.Np : nullptr;
+  v.dfd = nl.dfd ? nl.dfd + static_cast<size_t>(s) * nl.Np : nullptr;
+  v.rowid = nl.rowid ? nl.rowid + static_cast<size_t>(s) * nl.Np : nullptr;
+  v.flags = nl.flags ? nl.flags + s : nullptr;
+  v.upart = nl.upart ? nl.upart + static_cast<size_t>(s) * kMaxTiles * 4 : nullptr;
+  v.done = nl.done ? nl.done + s : nullptr;
   return v;
 }
 
@@ -105,6 +131,7 @@ struct Geom {
   int per[3];       // periodic flags
   int ncells;
   int ok;           // box invertible
+  int tab_ok;       // the per-axis shift tables (Smem::shx/shy/shz) are valid for this box
 };
 
 // Carve-up of the dynamic shared memory of a walker CTA.
@@ -121,6 +148,8 @@ struct Smem {
   unsigned char *rowid;  // [N] EAM row of each atom
   uint64_t *mbar;
   Geom *geom;
+  double *exp_tab;   // [128] 2^(j/128)
+  double *shx, *shy, *shz;  // [16] each: image shift s in [-8, 7] -> Cartesian offset along the axis
   int maxCells;
 };
 
@@ -137,7 +166,44 @@ __host__ __device__ inline size_t smem_bytes(int N, int maxCells) {
   b += align_up(static_cast<size_t>(N), 128);
   b += 128;  // mbarrier
   b += align_up(sizeof(Geom), 128);
+  b += sizeof(double) * (128 + 48);
   return b;
+}
+
+// Tiled force kernels need only the positions, reduction scratch, row ids and tables.
+__host__ __device__ inline size_t smem_bytes_tile(int N) {
+  size_t b = 0;
+  b += align_up(sizeof(double4) * N, 128);
+  b += align_up(sizeof(double) * 8 * kMaxWarps, 128);
+  b += align_up(static_cast<size_t>(N), 128);
+  b += 128;
+  b += align_up(sizeof(Geom), 128);
+  b += sizeof(double) * (128 + 48);
+  return b;
+}
+
+__device__ inline Smem carve_smem_tile(unsigned char *base, int N) {
+  Smem s;
+  size_t o = 0;
+  s.pos = reinterpret_cast<double4 *>(base + o);
+  o += align_up(sizeof(double4) * N, 128);
+  s.red = reinterpret_cast<double *>(base + o);
+  o += align_up(sizeof(double) * 8 * kMaxWarps, 128);
+  s.rowid = base + o;
+  o += align_up(static_cast<size_t>(N), 128);
+  s.mbar = reinterpret_cast<uint64_t *>(base + o);
+  o += 128;
+  s.geom = reinterpret_cast<Geom *>(base + o);
+  o += align_up(sizeof(Geom), 128);
+  s.exp_tab = reinterpret_cast<double *>(base + o);
+  s.shx = s.exp_tab + 128;
+  s.shy = s.shx + 16;
+  s.shz = s.shy + 16;
+  s.dfd = nullptr;
+  s.stage = nullptr;
+  s.cell_of = s.wrapc = s.order = s.cell_start = s.cell_fill = nullptr;
+  s.maxCells = 0;
+  return s;
 }
 
 __device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells) {
@@ -166,6 +232,11 @@ __device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells) {
   s.mbar = reinterpret_cast<uint64_t *>(base + o);
   o += 128;
   s.geom = reinterpret_cast<Geom *>(base + o);
+  o += align_up(sizeof(Geom), 128);
+  s.exp_tab = reinterpret_cast<double *>(base + o);
+  s.shx = s.exp_tab + 128;
+  s.shy = s.shx + 16;
+  s.shz = s.shy + 16;
   s.maxCells = maxCells;
   return s;
 }

@@ -237,8 +237,5 @@ class B200Potential:
         self._lib.eonb200_last_force_ms(self._h, out)
         return out[0], out[1]
 
-    def set_split_kernels(self, split: bool):
-        self._lib.eonb200_set_split_kernels(self._h, 1 if split else 0)
-
     def measure_fp64_peak(self, repeats: int = 5) -> float:
         return float(self._lib.eonb200_measure_fp64_peak(self._h, repeats))

@@ -64,7 +64,10 @@ typedef struct EonB200Config {
                              reference class, which is NOT -grad U); 1: F = -grad U            */
   double skin;            /* Verlet skin of the cached neighbour lists, Angstrom; < 0 -> 1.0;
                              0 -> exact list rebuilt on every evaluation                       */
-  int threads_per_walker; /* CTA size override, 0 -> chosen from nAtoms                        */
+  int threads_per_walker; /* CTA size override of the resident walker kernel, 0 -> from nAtoms  */
+  int tiles_override;     /* CTAs per system in the stateless force passes, 0 -> chosen so that
+                             nSystems x tiles covers the SMs a few times                       */
+  int lpa_override;       /* lanes sharing one atom's neighbour row (1, 2, 4, 8), 0 -> automatic */
 } EonB200Config;
 
 typedef struct EonB200Pot EonB200Pot; /* opaque */
@@ -230,13 +233,9 @@ EONB200_API unsigned long long eonb200_kernel_launches(const EonB200Pot *pot);
  * out[4] = ordered in-cutoff pairs visited by the last force evaluation (sum over systems). */
 EONB200_API int eonb200_nl_stats(EonB200Pot *pot, long long out[5]);
 
-/* Time the force_batch_device kernels only: CUDA-event milliseconds of the last call, split as
- * out[0] = neighbour ensure kernel, out[1] = force kernel(s). */
+/* CUDA-event milliseconds of the last (synchronous) force_batch / force_batch_device call, split as
+ * out[0] = k_prepare (staging, Verlet check, cell-list rebuilds), out[1] = the force pass kernel(s). */
 EONB200_API int eonb200_last_force_ms(EonB200Pot *pot, double out[2]);
-
-/* Launch the neighbour check/rebuild and the force evaluation as two kernels instead of one so
- * that eonb200_last_force_ms can split their device time (measurement only). */
-EONB200_API int eonb200_set_split_kernels(EonB200Pot *pot, int split);
 
 #ifdef __cplusplus
 }

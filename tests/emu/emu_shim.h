@@ -57,16 +57,25 @@ inline unsigned char *dyn_smem() {
   uintptr_t p = reinterpret_cast<uintptr_t>(v.data());
   return reinterpret_cast<unsigned char *>((p + 127) / 128 * 128);
 }
+}  // namespace emu
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+namespace emu {
 template <typename F>
-inline void launch(unsigned grid, size_t smem, F &&body) {
+inline void launch(dim3 grid, size_t smem, F &&body) {
   smem_store().assign(smem + 256, 0);
   tidx().x = 0;
   bdim().x = 1;
-  gdim().x = grid;
-  for (unsigned b = 0; b < grid; b++) {
-    bidx().x = b;
-    body();
-  }
+  gdim().x = grid.x;
+  gdim().y = grid.y;
+  for (unsigned by = 0; by < grid.y; by++)
+    for (unsigned b = 0; b < grid.x; b++) {
+      bidx().x = b;
+      bidx().y = by;
+      body();
+    }
 }
 }  // namespace emu
 #define threadIdx (emu::tidx())

@@ -227,10 +227,56 @@ def ref_eam_force(R, Z, box):
 
 
 class _VesinOptions(C.Structure):
-    # client/thirdparty/vesin/vesin.h: VesinOptions
+    # client/thirdparty/vesin/vesin.h: struct VesinOptions
     _fields_ = [("cutoff", C.c_double), ("full", C.c_bool), ("sorted", C.c_bool), ("algorithm", C.c_int),
-                ("return_shifts", C.c_bool), ("return_distances", C.c_bool), ("return_vectors", C.c_bool),
-                ("skin", C.c_double), ("n_threads", C.c_int32)]
+                ("skin", C.c_double), ("n_threads", C.c_int32), ("return_shifts", C.c_bool),
+                ("return_distances", C.c_bool), ("return_vectors", C.c_bool)]
+
+
+class _VesinDevice(C.Structure):
+    _fields_ = [("type", C.c_int), ("device_id", C.c_int)]
+
+
+class _VesinNeighborList(C.Structure):
+    _fields_ = [("length", C.c_size_t), ("device", _VesinDevice), ("pairs", C.POINTER(C.c_size_t)),
+                ("shifts", C.POINTER(C.c_int32)), ("distances", C.POINTER(C.c_double)),
+                ("vectors", C.POINTER(C.c_double)), ("opaque", C.c_void_p)]
+
+
+_ref_vesin = None
+
+
+def ref_vesin_neighbors(R, box, cutoff, full=True, periodic=(1, 1, 1), algorithm=0, vectors=False):
+    """The reference's own vendored vesin (compiled from /root/reference by oracle/Makefile):
+    -> (pairs[P,2] int64, shifts[P,3] int32[, distances, vectors])."""
+    global _ref_vesin
+    if _ref_vesin is None:
+        _ref_vesin = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libvesin_ref.so"))
+        _ref_vesin.vesin_neighbors.restype = C.c_int
+        _ref_vesin.vesin_neighbors.argtypes = [C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double),
+                                               C.POINTER(C.c_bool), _VesinDevice, _VesinOptions,
+                                               C.POINTER(_VesinNeighborList), C.POINTER(C.c_char_p)]
+        _ref_vesin.vesin_free.argtypes = [C.POINTER(_VesinNeighborList)]
+        _ref_vesin.vesin_free.restype = None
+    R = np.ascontiguousarray(R, dtype=np.float64).reshape(-1, 3)
+    box = np.ascontiguousarray(box, dtype=np.float64).reshape(9)
+    per = (C.c_bool * 3)(*[bool(x) for x in periodic])
+    opt = _VesinOptions(float(cutoff), bool(full), False, int(algorithm), 0.0, 1, True, bool(vectors), bool(vectors))
+    nl = _VesinNeighborList()
+    nl.device = _VesinDevice(0, 0)
+    err = C.c_char_p()
+    rc = _ref_vesin.vesin_neighbors(_dp(R), len(R), _dp(box), per, _VesinDevice(1, 0), opt, C.byref(nl), C.byref(err))
+    if rc != 0:
+        raise RuntimeError(f"vesin_neighbors failed: {err.value}")
+    n = nl.length
+    pairs = np.ctypeslib.as_array(nl.pairs, shape=(n, 2)).astype(np.int64) if n else np.zeros((0, 2), np.int64)
+    shifts = np.ctypeslib.as_array(nl.shifts, shape=(n, 3)).copy() if n else np.zeros((0, 3), np.int32)
+    out = [pairs, shifts]
+    if vectors:
+        out.append(np.ctypeslib.as_array(nl.distances, shape=(n,)).copy() if n else np.zeros(0))
+        out.append(np.ctypeslib.as_array(nl.vectors, shape=(n, 3)).copy() if n else np.zeros((0, 3)))
+    _ref_vesin.vesin_free(C.byref(nl))
+    return tuple(out)
 
 
 def load_fixture(name):
