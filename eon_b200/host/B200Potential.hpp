@@ -1,0 +1,147 @@
+// B200Potential.hpp -- the eonclient-side shim: an eonc::Potential subclass over libeonb200.so.
+//
+// This is the file a maintainer drops into client/potentials/B200/ of the reference tree (see
+// INTEGRATION.md).  It follows the reference's own dlopen C-ABI precedent
+//     include/eon/potentials/Metatomic/metatomic_c_abi.h:30-79
+//     client/potentials/Metatomic/MetatomicDynPot.cpp:39-70   (create -> handle, rc != 0 -> runtime_error)
+//     include/eon/potentials/Metatomic/MetatomicLoader.h:18-52 (function-pointer table + ABI version check)
+// and overrides exactly the virtuals of include/eon/Potential.h:55-57,62-122 that route callers
+// (client/Matter.cpp:523, client/ImprovedDimer.cpp:160-193, client/Dimer.cpp:170-210,
+// client/NudgedElasticBand.cpp:475-521) through one batched device evaluation.
+//
+// It compiles against the real <eon/Potential.h> inside an eOn build, and against the small stand-in
+// tests/host/stub/eon/Potential.h in this repository's host harness (the real header needs Eigen,
+// quill and the Parameters tree, none of which exist in this image).
+#pragma once
+
+#include "eon/Potential.h"
+
+#include "eonb200.h"
+
+#include <dlfcn.h>
+
+#include <array>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+namespace eonc {
+
+// Function-pointer table over libeonb200.so (the analogue of MetatomicLoader).
+class B200Loader {
+public:
+  static B200Loader &instance() {
+    static B200Loader l;
+    return l;
+  }
+  // Search order: explicit path, $EONB200_LIBRARY, then the dynamic linker's default path
+  // (the reference adds `[Potential] potentials_path` / $EON_POTENTIALS_PATH in PluginLoader.cpp).
+  void require_loaded(const std::string &path = std::string()) {
+    std::lock_guard<std::mutex> g(m_mu);
+    if (m_handle) return;
+    std::string p = path;
+    if (p.empty()) {
+      if (const char *env = std::getenv("EONB200_LIBRARY")) p = env;
+    }
+    if (p.empty()) p = "libeonb200.so";
+    m_handle = dlopen(p.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!m_handle) throw std::runtime_error(std::string("B200Loader: cannot load ") + p + ": " + dlerror());
+    bind(abi_version, "eonb200_abi_version");
+    if (abi_version() != EONB200_ABI_VERSION) {
+      dlclose(m_handle);
+      m_handle = nullptr;
+      throw std::runtime_error("B200Loader: libeonb200.so ABI version mismatch");
+    }
+    bind(config_default, "eonb200_config_default");
+    bind(create, "eonb200_create");
+    bind(destroy, "eonb200_destroy");
+    bind(last_error, "eonb200_last_error");
+    bind(force, "eonb200_force");
+    bind(force_batch, "eonb200_force_batch");
+    bind(force_calls, "eonb200_force_calls");
+  }
+
+  decltype(&eonb200_abi_version) abi_version{nullptr};
+  decltype(&eonb200_config_default) config_default{nullptr};
+  decltype(&eonb200_create) create{nullptr};
+  decltype(&eonb200_destroy) destroy{nullptr};
+  decltype(&eonb200_last_error) last_error{nullptr};
+  decltype(&eonb200_force) force{nullptr};
+  decltype(&eonb200_force_batch) force_batch{nullptr};
+  decltype(&eonb200_force_calls) force_calls{nullptr};
+
+private:
+  template <typename F>
+  void bind(F &fn, const char *name) {
+    void *s = dlsym(m_handle, name);
+    if (!s) throw std::runtime_error(std::string("B200Loader: missing symbol ") + name);
+    fn = reinterpret_cast<F>(s);
+  }
+  void *m_handle{nullptr};
+  std::mutex m_mu;
+};
+
+// eonc::Potential for PotType::{LJ, LJCLUSTER, MORSE_PT, EAM_AL}, evaluated on a B200.
+class B200Potential : public Potential {
+public:
+  // `kind` is an EONB200_POT_* value; `ptype` the reference tag the instance reports through
+  // getType() / PotRegistry (include/eon/BaseStructures.h:36-71).
+  B200Potential(PotType ptype, int kind, int device = 0, const std::string &library = std::string())
+      : Potential(ptype) {
+    auto &l = B200Loader::instance();
+    l.require_loaded(library);
+    EonB200Config cfg;
+    l.config_default(&cfg, kind);
+    cfg.device = device;
+    std::array<char, 1024> err{};
+    m_handle = l.create(&cfg, err.data(), err.size());
+    if (!m_handle) throw std::runtime_error(std::string("B200Potential: create failed: ") + err.data());
+  }
+  ~B200Potential() override {
+    if (m_handle) B200Loader::instance().destroy(m_handle);
+  }
+  B200Potential(const B200Potential &) = delete;
+  B200Potential &operator=(const B200Potential &) = delete;
+
+  // Potential::force (include/eon/Potential.h:55-57).  Counters are the caller's job here
+  // (client/Matter.cpp:525-526).
+  void force(long nAtoms, const double *positions, const int *atomicNrs, double *forces, double *energy,
+             double *variance, const double *box) override {
+    check(B200Loader::instance().force(m_handle, nAtoms, positions, atomicNrs, forces, energy, variance, box));
+  }
+
+  // Potential::forceBatch (include/eon/Potential.h:108-122): one H2D, one launch sequence, one D2H.
+  // Counters are the callee's job in the batch path (Potential.h:119-120, RgpotAdapter.h:91-92).
+  void forceBatch(long nSystems, long nAtoms, const double *const *positions, const int *const *atomicNrs,
+                  double *const *forces, double *energies, double *variances, const double *const *boxes) override {
+    check(B200Loader::instance().force_batch(m_handle, nSystems, nAtoms, positions, atomicNrs, forces, energies,
+                                             variances, boxes));
+    for (long i = 0; i < nSystems; i++) {
+      forceCallCounter++;
+#ifndef EONB200_HOST_STUB
+      PotRegistry::get().on_force_call(ptype);
+#endif
+    }
+  }
+
+  // Callers test supportsBatchEvaluation() first (ImprovedDimer.cpp:160, NudgedElasticBand.cpp:475) and
+  // must never thread one device handle (isSharedInstanceThreadSafe gates std::thread use).
+  [[nodiscard]] bool supportsBatchEvaluation() const noexcept override { return true; }
+  [[nodiscard]] bool isThreadSafe() const noexcept override { return false; }
+  [[nodiscard]] bool isSharedInstanceThreadSafe() const noexcept override { return false; }
+  [[nodiscard]] bool needsPerImageInstance() const noexcept override { return false; }
+
+  [[nodiscard]] EonB200Pot *handle() const noexcept { return m_handle; }
+
+private:
+  void check(int rc) {
+    if (rc == 0) return;
+    if (rc == 14324) throw 14324;  // client/potentials/EAM/EAM.cpp:116-123
+    if (rc == 100) throw 100;      // legacy "potential failed" -> status 11 (client/SaddleSearchJob.cpp:116-123)
+    throw std::runtime_error(std::string("B200Potential: rc=") + std::to_string(rc) + ": " +
+                             B200Loader::instance().last_error(m_handle));
+  }
+  EonB200Pot *m_handle{nullptr};
+};
+
+}  // namespace eonc

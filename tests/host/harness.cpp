@@ -1,0 +1,65 @@
+// tests/host/harness.cpp -- TEST INFRASTRUCTURE: drives eon_b200/host/B200Potential.hpp the way eonclient does.
+//
+//   harness <lib> <kind> <nSystems> <nAtoms> < input > output
+// input (text): for every system 3N positions, then N atomic numbers, then 9 box values.
+// It calls forceBatch with arrays of per-system pointers exactly like client/ImprovedDimer.cpp:176 /
+// client/NudgedElasticBand.cpp:515, then force() on system 0 like client/Matter.cpp:523, and prints
+// energies and forces with %.17g.  Exit code 3 = potential could not be created (no GPU).
+#include "B200Potential.hpp"
+
+#include <cstdio>
+#include <memory>
+#include <vector>
+
+int main(int argc, char **argv) {
+  if (argc < 5) return 2;
+  const std::string lib = argv[1];
+  const int kind = std::atoi(argv[2]);
+  const long S = std::atol(argv[3]), N = std::atol(argv[4]);
+  std::vector<std::vector<double>> R(S, std::vector<double>(3 * N)), F(S, std::vector<double>(3 * N, -777.0)),
+      B(S, std::vector<double>(9));
+  std::vector<std::vector<int>> Z(S, std::vector<int>(N));
+  for (long s = 0; s < S; s++) {
+    for (auto &x : R[s]) if (scanf("%lf", &x) != 1) return 2;
+    for (auto &z : Z[s]) if (scanf("%d", &z) != 1) return 2;
+    for (auto &b : B[s]) if (scanf("%lf", &b) != 1) return 2;
+  }
+  std::shared_ptr<Potential> pot;
+  try {
+    const eonc::PotType tag = kind == EONB200_POT_EAM ? eonc::PotType::EAM_AL
+                              : kind == EONB200_POT_MORSE_PT ? eonc::PotType::MORSE_PT : eonc::PotType::LJ;
+    pot = std::make_shared<eonc::B200Potential>(tag, kind, 0, lib);
+  } catch (const std::exception &e) {
+    fprintf(stderr, "%s\n", e.what());
+    return 3;
+  }
+  if (!pot->supportsBatchEvaluation() || pot->isSharedInstanceThreadSafe()) return 4;
+  std::vector<const double *> pR(S), pB(S);
+  std::vector<const int *> pZ(S);
+  std::vector<double *> pF(S);
+  for (long s = 0; s < S; s++) {
+    pR[s] = R[s].data();
+    pZ[s] = Z[s].data();
+    pF[s] = F[s].data();
+    pB[s] = B[s].data();
+  }
+  std::vector<double> E(S), V(S, -1.0);
+  try {
+    pot->forceBatch(S, N, pR.data(), pZ.data(), pF.data(), E.data(), V.data(), pB.data());
+  } catch (int code) {
+    printf("thrown %d\n", code);
+    return 0;
+  }
+  std::vector<double> F0(3 * N);
+  double E0 = 0, var0 = -1;
+  pot->force(N, R[0].data(), Z[0].data(), F0.data(), &E0, &var0, B[0].data());
+  pot->forceCallCounter++;  // the caller's increment, client/Matter.cpp:525
+  printf("calls %zu\n", pot->forceCallCounter.load());
+  for (long s = 0; s < S; s++) {
+    printf("%.17g %.17g\n", E[s], V[s]);
+    for (double f : F[s]) printf("%.17g\n", f);
+  }
+  printf("%.17g %.17g\n", E0, var0);
+  for (double f : F0) printf("%.17g\n", f);
+  return 0;
+}
