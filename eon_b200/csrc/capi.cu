@@ -62,7 +62,8 @@ struct PinBuf {
 };
 
 struct NlStore {
-  DevBuf<int> nbr, cnt, state, flags, done;
+  DevBuf<int> nbr, cnt, state, flags, done, nbr2, cnt2, cellscratch;
+  int scratch_stride = 0;
   DevBuf<double> rbuild, pairA, pairB, dfd, upart;
   DevBuf<double4> pos4;
   DevBuf<unsigned char> rowid;
@@ -170,6 +171,15 @@ void fill_params(EonB200Pot *pot) {
       rcmax = std::max(rcmax, s.r_cut);
     }
     P.cutoff = rcmax;
+    // exp_tab_fast has no underflow guard: every exponent argument a row can produce inside its cutoff must stay
+    // well inside the double range
+    P.eam_fast_ok = 1;
+    for (int r = 0; r < P.n_rows; r++) {
+      const EonB200EamRow &s = pot->rows[r];
+      const double worst = std::max(std::max(std::fabs(s.beta1), 2.0 * std::fabs(s.beta2)), std::fabs(s.alphaM)) *
+                           (s.r_cut + std::fabs(s.Rm));
+      if (!(worst < 600.0)) P.eam_fast_ok = 0;
+    }
   } else {
     P.nl_mode = NL_VESIN;
     const double rc = P.cutoff;
@@ -249,6 +259,40 @@ int tile_threads_for(int tile_atoms, int lpa) {
 #endif
 }
 
+// Fused EAM kernel: CTAs per walker (= cluster size, at most 8) and threads per CTA.  Atoms are dealt out in whole
+// warps; CTAs of three to four warps keep the load per SM even when a few hundred walkers meet 148 SMs, a
+// handful of systems (the dimer's two images) is spread as wide as the cluster allows.
+void pick_fused(const EonB200Pot *pot, long S, long N, int *T_out, int *threads_out) {
+#ifdef EONB200_EMU
+  (void)pot;
+  (void)S;
+  (void)N;
+  *T_out = 1;
+  *threads_out = 1;
+#else
+  const long Wn = (N + 31) / 32;
+  const long Tmin = (Wn + 15) / 16;  // at most 512 threads per CTA
+  long T;
+  if (smem_bytes_fused(static_cast<int>(N)) > 100 * 1024) {
+    T = Tmin;  // one large CTA per SM: the walker's positions are replicated in every CTA of its cluster
+  } else if (S * Wn < 4L * pot->sm_count) {
+    T = Wn;
+  } else {
+    T = (2 * Wn + 3) / 7;  // about 3.5 warps per CTA
+  }
+  if (pot->cfg.tiles_override > 0) T = pot->cfg.tiles_override;
+  T = std::max<long>(std::max<long>(T, Tmin), 1);
+  T = std::min<long>(std::min<long>(T, 8), Wn);
+  long wpc = (Wn + T - 1) / T;
+  // the largest slice of the warp-granular split w0 = rank * Wn / T
+  for (long r = 0; r < T; r++) wpc = std::max(wpc, (r + 1) * Wn / T - r * Wn / T);
+  long threads = 32 * wpc;
+  if (pot->cfg.threads_per_walker > 0) threads = std::max<long>(32, (pot->cfg.threads_per_walker + 31) / 32 * 32);
+  *T_out = static_cast<int>(T);
+  *threads_out = static_cast<int>(std::min<long>(threads, kMaxThreadsPerWalker));
+#endif
+}
+
 int pick_max_cells(long N) { return static_cast<int>(std::min<long>(std::max<long>(64, N), 4096)); }
 
 // Row capacity guess from the mean density; truncated builds are detected and regrown.
@@ -278,6 +322,10 @@ int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K) {
   if (pot->cfg.kind == EONB200_POT_EAM) {
     CU_TRY(pot, nl.pairA.reserve(static_cast<size_t>(S) * K * Np));
     CU_TRY(pot, nl.pairB.reserve(static_cast<size_t>(S) * K * Np));
+    CU_TRY(pot, nl.nbr2.reserve(static_cast<size_t>(S) * K * Np));
+    CU_TRY(pot, nl.cnt2.reserve(static_cast<size_t>(S) * Np));
+    nl.scratch_stride = static_cast<int>(fused_scratch_ints(static_cast<int>(N), pick_max_cells(N)));
+    CU_TRY(pot, nl.cellscratch.reserve(static_cast<size_t>(S) * nl.scratch_stride));
   }
   CU_TRY(pot, cudaMemsetAsync(nl.state.p, 0, sizeof(int) * S, pot->stream));
   CU_TRY(pot, cudaMemsetAsync(nl.done.p, 0, sizeof(int) * S, pot->stream));
@@ -301,6 +349,10 @@ NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
   b.stats = pot->d_stats.p;
   b.pairA = nl.pairA.p;
   b.pairB = nl.pairB.p;
+  b.nbr2 = nl.nbr2.p;
+  b.cnt2 = nl.cnt2.p;
+  b.cellscratch = nl.cellscratch.p;
+  b.scratch_stride = nl.scratch_stride;
   b.pos4 = nl.pos4.p;
   b.dfd = nl.dfd.p;
   b.rowid = nl.rowid.p;
@@ -329,33 +381,56 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     if (rc) return rc;
   }
   a.maxCells = pick_max_cells(N);
+  const bool eam = pot->cfg.kind == EONB200_POT_EAM;
   const int prep_threads = pick_threads(pot, N, 1);
-  size_t smem;
-  int rc = check_smem(pot, N, a.maxCells, &smem);
-  if (rc) return rc;
-  // force passes: T tiles per system so that S * T CTAs cover the SMs a few times over
-  pick_tiling(pot, S, N, &a.tiles, &a.lpa);
-  const int tile_atoms = static_cast<int>((N + a.tiles - 1) / a.tiles);
-  const int tile_threads = tile_threads_for(tile_atoms, a.lpa);
-  const size_t tile_smem = smem_bytes_tile(static_cast<int>(N));
-  if (static_cast<long>(tile_smem) > pot->max_dyn_smem) return fail(pot, 3, "system too large for the tiled force kernels");
-#ifdef EONB200_EMU
-  const unsigned gy = static_cast<unsigned>(S);
-  (void)gy;
-#endif
+  size_t smem = 0;
+  int rc = 0;
+  // LJ / Morse force pass: T tiles per system so that S * T CTAs cover the SMs a few times over
+  int tile_threads = 0;
+  size_t tile_smem = 0;
+  // EAM: one cluster of T CTAs per walker
+  int fused_T = 1, fused_threads = 1;
+  size_t fused_smem = 0;
+  if (eam) {
+    pick_fused(pot, S, N, &fused_T, &fused_threads);
+    fused_smem = smem_bytes_fused(static_cast<int>(N));
+    if (static_cast<long>(fused_smem) > pot->max_dyn_smem)
+      return fail(pot, 3, "system of %ld atoms needs %zu bytes of shared memory per CTA (limit %d)", N, fused_smem,
+                  pot->max_dyn_smem);
+    a.tiles = fused_T;
+    a.lpa = 1;
+  } else {
+    rc = check_smem(pot, N, a.maxCells, &smem);
+    if (rc) return rc;
+    pick_tiling(pot, S, N, &a.tiles, &a.lpa);
+    const int tile_atoms = static_cast<int>((N + a.tiles - 1) / a.tiles);
+    tile_threads = tile_threads_for(tile_atoms, a.lpa);
+    tile_smem = smem_bytes_tile(static_cast<int>(N));
+    if (static_cast<long>(tile_smem) > pot->max_dyn_smem) return fail(pot, 3, "system too large for the tiled force kernels");
+  }
   for (int attempt = 0; attempt < 6; attempt++) {
     CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
     CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
     NlBatch view = nl_view(pot, nl);
     CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
-    EONB200_LAUNCH(k_prepare, dim3(static_cast<unsigned>(S)), prep_threads, smem, pot->stream, pot->dP.p, view, a);
-    CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
-    const dim3 grid(static_cast<unsigned>(a.tiles), static_cast<unsigned>(S));
-    if (pot->cfg.kind == EONB200_POT_EAM) {
-      EONB200_LAUNCH(k_eam_pass1, grid, tile_threads, tile_smem, pot->stream, pot->dP.p, view, a);
-      EONB200_LAUNCH(k_eam_pass2, grid, tile_threads, tile_smem, pot->stream, pot->dP.p, view, a);
-      pot->launches += 3;
+    if (eam) {
+      CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
+      const dim3 grid(static_cast<unsigned>(fused_T), static_cast<unsigned>(S));
+#ifdef EONB200_EMU
+      EONB200_LAUNCH_CLUSTER(k_eam_fused, grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+#else
+      if (fused_threads <= 128)
+        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<128, 7>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+      else if (fused_threads <= 256)
+        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<256, 3>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+      else
+        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<512, 1>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+#endif
+      pot->launches += 1;
     } else {
+      EONB200_LAUNCH(k_prepare, dim3(static_cast<unsigned>(S)), prep_threads, smem, pot->stream, pot->dP.p, view, a);
+      CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
+      const dim3 grid(static_cast<unsigned>(a.tiles), static_cast<unsigned>(S));
       EONB200_LAUNCH(k_pair, grid, tile_threads, tile_smem, pot->stream, pot->dP.p, view, a);
       pot->launches += 2;
     }
@@ -492,10 +567,14 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_prepare), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
-         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_pass1), cudaFuncAttributeMaxDynamicSharedMemorySize,
+#ifndef EONB200_EMU
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<128, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
-         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_pass2), cudaFuncAttributeMaxDynamicSharedMemorySize,
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<256, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+#endif
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_neighbors), cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -43,6 +43,30 @@ constexpr double kSafeEps = 1e-300;  // include/eon/SafeMath.h:19
   kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
 
+// Launch with `cx` CTAs (along grid x) per thread-block cluster.  The emulation runs every CTA on its own
+// (callers pass cx == 1 there).
+#ifdef EONB200_EMU
+#define EONB200_LAUNCH_CLUSTER(kernel, grid, block, smem, stream, cx, ...) \
+  emu::launch((grid), (smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#define EONB200_LAUNCH_CLUSTER(kernel, grid_, block_, smem_, stream_, cx_, ...)                  \
+  do {                                                                                         \
+    cudaLaunchConfig_t cfg_ = {};                                                              \
+    cfg_.gridDim = (grid_);                                                                    \
+    cfg_.blockDim = dim3(block_);                                                              \
+    cfg_.dynamicSmemBytes = (smem_);                                                           \
+    cfg_.stream = (stream_);                                                                   \
+    cudaLaunchAttribute attr_[1];                                                              \
+    attr_[0].id = cudaLaunchAttributeClusterDimension;                                         \
+    attr_[0].val.clusterDim.x = (cx_);                                                         \
+    attr_[0].val.clusterDim.y = 1;                                                             \
+    attr_[0].val.clusterDim.z = 1;                                                             \
+    cfg_.attrs = attr_;                                                                        \
+    cfg_.numAttrs = 1;                                                                         \
+    cudaLaunchKernelEx(&cfg_, kernel, __VA_ARGS__);                                            \
+  } while (0)
+#endif
+
 // ---- un-fused arithmetic for bit-exact predicates --------------------------------------------
 // The neighbour predicate must round exactly like the x86-64 reference (no FMA contraction):
 // client/thirdparty/vesin/vesin-single-build.cpp:41-43,138-144,1199-1202.
@@ -130,6 +154,48 @@ __device__ __forceinline__ double block_max1(double x, double *scratch) {
   const int op[1] = {RED_MAX};
   block_reduce<1>(v, op, scratch);
   return v[0];
+}
+
+// ---- thread-block clusters (one cluster per walker in the fused EAM kernel) ---------------------
+// A walker whose atoms are split over T CTAs keeps those CTAs on neighbouring SMs as one cluster:
+// per-atom dF/drho and the energy partials cross CTAs through distributed shared memory
+// (mapa + st.shared::cluster) and one cluster barrier separates the density pass from the force pass.
+__device__ __forceinline__ unsigned cluster_rank() {
+#ifndef EONB200_EMU
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+#else
+  return 0;
+#endif
+}
+__device__ __forceinline__ unsigned cluster_size() {
+#ifndef EONB200_EMU
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+#else
+  return 1;
+#endif
+}
+// Full cluster barrier with release / acquire semantics (covers shared::cluster and global writes).
+__device__ __forceinline__ void cluster_sync_all() {
+#ifndef EONB200_EMU
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#endif
+}
+// Store a double into the same shared-memory location of CTA `rank` of this cluster.
+__device__ __forceinline__ void dsmem_store(double *local_smem_ptr, unsigned rank, double v) {
+#ifndef EONB200_EMU
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local_smem_ptr));
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(ra), "d"(v) : "memory");
+#else
+  (void)rank;
+  *local_smem_ptr = v;
+#endif
 }
 
 // ---- SafeMath (include/eon/SafeMath.h:19-80) ----------------------------------------------------

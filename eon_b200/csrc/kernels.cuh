@@ -1,12 +1,11 @@
 // kernels.cuh -- __global__ entry points.
 //
 // Stateless batched evaluation (Potential::force / forceBatch) runs as a short pipeline over S systems:
-//   k_prepare   grid S          stage positions (bulk copy), EAM shift/wrap, Verlet check, cell-list rebuild
-//                               when needed, prepared positions + element rows to HBM
-//   k_eam_pass1 grid (T, S)     density pass over a tile of atoms, pair cache, dF/drho       (EAM)
-//   k_eam_pass2 grid (T, S)     force gather over a tile of atoms, energy                     (EAM)
-//   k_pair      grid (T, S)     single pass                                                   (LJ / Morse)
-// T tiles per system spread a walker over several CTAs so that a few hundred walkers fill 148 SMs.
+//   EAM:        k_eam_fused grid (T, S), one thread-block cluster of T CTAs per walker: bulk copy of the
+//               positions, Verlet check (in-place rebuild when stale), filter, density, force -- one launch
+//   LJ / Morse: k_prepare   grid S       stage positions, Verlet check, cell-list rebuild when needed
+//               k_pair      grid (T, S)  single pass over a tile of atoms
+// T CTAs per system spread a walker over several SMs so that a few hundred walkers fill 148 SMs.
 // Resident walkers (k_walkers) keep one CTA per walker for the whole saddle search.
 #pragma once
 #include "search.cuh"
@@ -147,46 +146,6 @@ __device__ inline void tile_epilogue(const SysView &sys, Smem &sm, int tiles, do
   }
 }
 
-__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_eam_pass1(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
-  EONB200_DYN_SMEM(smem_raw);
-  const int s = blockIdx.y;
-  Smem sm = carve_smem_tile(smem_raw, a.N);
-  const PotParams &P = *Pp;
-  const SysView sys = batch_sys(nl, a, s);
-  int i0, i1;
-  tile_prologue(P, sys, sm, a.tiles, i0, i1, false);
-  double acc[2] = {0.0, 0.0};
-  const int flags = *sys.flags;
-  if (!(flags & 2)) {
-    if (flags & 1)
-      eam_pass1<true>(P, sys, sm, a.lpa, i0, i1, sys.dfd, acc);
-    else
-      eam_pass1<false>(P, sys, sm, a.lpa, i0, i1, sys.dfd, acc);
-  }
-  tile_epilogue(sys, sm, a.tiles, acc, 0, nullptr, false);
-}
-
-__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_eam_pass2(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
-  EONB200_DYN_SMEM(smem_raw);
-  const int s = blockIdx.y;
-  Smem sm = carve_smem_tile(smem_raw, a.N);
-  const PotParams &P = *Pp;
-  const SysView sys = batch_sys(nl, a, s);
-  int i0, i1;
-  tile_prologue(P, sys, sm, a.tiles, i0, i1, true);
-  double acc[2] = {0.0, 0.0};
-  const int flags = *sys.flags;
-  double *F = a.F + static_cast<size_t>(s) * a.strideR;
-  if (flags & 2) {
-    for (int k = 3 * i0 + threadIdx.x; k < 3 * i1; k += blockDim.x) F[k] = 0.0;
-  } else if (flags & 1) {
-    eam_pass2<true>(P, sys, sm, a.lpa, i0, i1, F, acc);
-  } else {
-    eam_pass2<false>(P, sys, sm, a.lpa, i0, i1, F, acc);
-  }
-  tile_epilogue(sys, sm, a.tiles, acc, 1, a.U + s, true);
-}
-
 __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_pair(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
   EONB200_DYN_SMEM(smem_raw);
   const int s = blockIdx.y;
@@ -203,6 +162,161 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_pair(const PotParams *
     pair_pass<POT_LJ>(P, sys, sm, a.lpa, i0, i1, F, acc);
   tile_epilogue(sys, sm, a.tiles, acc, 0, a.U + s, true);
 }
+
+// ---- fused EAM evaluation: one thread-block cluster per walker -------------------------------------------------
+// grid (T, S), cluster (T, 1, 1): the T CTAs of walker s each stage the walker's positions with one bulk copy,
+// repeat the (cheap) Verlet check, own a warp-granular slice of the atoms and run
+//   filter -> density -> [dF/drho and energy partials through distributed shared memory, one cluster barrier]
+//   -> force
+// with one lane per atom.  A stale list is rebuilt in place by CTA 0 of the cluster (cell-list scratch in HBM).
+// Mixed-element systems and boxes too small for the stored image shifts take the general row functions
+// (eam_pass1 / eam_pass2) inside the same kernel.
+template <bool SINGLE>
+__device__ __forceinline__ void eam_fused_fast(const PotParams &P, const SysView &sys, Smem &sm, int i0, int i1, unsigned T,
+                                               unsigned rank, double *F, double *U) {
+  double acc[2] = {0.0, 0.0};
+  EamLane L = {0.0, 0.0, 0.0, 0.0, 0};
+  const int ifirst = i0 + static_cast<int>(threadIdx.x);
+  for (int i = ifirst; i < i1; i += blockDim.x) {
+    eam_fast_density(P, sys, sm, i, L, acc);
+    if (T > 1) {
+      for (unsigned r = 0; r < T; r++) dsmem_store(&sm.pos[i].w, r, L.dfd);
+    } else {
+      sm.pos[i].w = L.dfd;
+    }
+    if (!SINGLE) {  // more atoms than threads: the lane state goes through HBM
+      F[3 * i] = L.fx;
+      F[3 * i + 1] = L.fy;
+      F[3 * i + 2] = L.fz;
+      sys.dfd[i] = L.dfd;
+      sys.cnt2[i] = L.nin;
+    }
+    if (SINGLE) break;
+  }
+  block_sum<2>(acc, sm.red);
+  if (threadIdx.x == 0) {
+    if (T > 1) {
+      dsmem_store(&sm.clu[rank], 0, acc[0]);
+      dsmem_store(&sm.clu[8 + rank], 0, acc[1]);
+    } else {
+      sm.clu[0] = acc[0];
+      sm.clu[8] = acc[1];
+    }
+  }
+  if (T > 1)
+    cluster_sync_all();
+  else
+    __syncthreads();
+  for (int i = ifirst; i < i1; i += blockDim.x) {
+    if (!SINGLE) {
+      L.fx = F[3 * i];
+      L.fy = F[3 * i + 1];
+      L.fz = F[3 * i + 2];
+      L.dfd = sys.dfd[i];
+      L.nin = sys.cnt2[i];
+    }
+    eam_fast_force(sys, sm, i, L, F);
+    if (SINGLE) break;
+  }
+  if (rank == 0 && threadIdx.x == 0) {
+    double e = 0.0, n = 0.0;
+    for (unsigned r = 0; r < T; r++) {  // fixed order: reproducible energies
+      e += sm.clu[r];
+      n += sm.clu[8 + r];
+    }
+    *U = e;
+    atomicAdd(&sys.stats[2], static_cast<unsigned long long>(n));
+  }
+}
+
+// Mixed elements / small boxes: the general row functions, dF/drho exchanged through HBM.
+__device__ EONB200_NOINLINE void eam_fused_general(const PotParams &P, const SysView &sys, Smem &sm, int flags, int i0, int i1,
+                                                  unsigned T, unsigned rank, double *F, double *U, int N) {
+  double acc[2] = {0.0, 0.0};
+  if (flags & 1)
+    eam_pass1<true>(P, sys, sm, 1, i0, i1, sys.dfd, acc);
+  else
+    eam_pass1<false>(P, sys, sm, 1, i0, i1, sys.dfd, acc);
+  if (T > 1)
+    cluster_sync_all();
+  else
+    __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sm.pos[i].w = sys.dfd[i];
+  __syncthreads();
+  if (flags & 1)
+    eam_pass2<true>(P, sys, sm, 1, i0, i1, F, acc);
+  else
+    eam_pass2<false>(P, sys, sm, 1, i0, i1, F, acc);
+  block_sum<2>(acc, sm.red);
+  if (threadIdx.x == 0) {
+    sys.upart[2 * rank] = acc[0];
+    sys.upart[2 * rank + 1] = acc[1];
+  }
+  if (T > 1)
+    cluster_sync_all();
+  else
+    __syncthreads();
+  if (rank == 0 && threadIdx.x == 0) {
+    double e = 0.0, n = 0.0;
+    for (unsigned r = 0; r < T; r++) {
+      e += sys.upart[2 * r];
+      n += sys.upart[2 * r + 1];
+    }
+    *U = e;
+    atomicAdd(&sys.stats[2], static_cast<unsigned long long>(n));
+  }
+}
+
+__device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp, const NlBatch &nl, const ForceBatchArgs &a) {
+  EONB200_DYN_SMEM(smem_raw);
+  const int s = blockIdx.y;
+  const unsigned T = gridDim.x;      // CTAs per walker == cluster size (cluster dims (T, 1, 1))
+  const unsigned rank = blockIdx.x;  // == %cluster_ctarank
+  const PotParams &P = *Pp;
+  const SysView sys = batch_sys(nl, a, s);
+  Smem sm = carve_smem_fused(smem_raw, a.N, a.maxCells, sys.cellscratch);
+  if (threadIdx.x == 0) mbar_init(sm.mbar, 1);
+  __syncthreads();
+  uint32_t phase = 0;
+  const NlParams np = make_nl_params(P);
+  const bool rebuild = nl_stage_check(np, sys, sm, phase, a.force_rebuild != 0, P.exp_tab);
+  if (rebuild) {  // the same decision in every CTA of the cluster
+    if (T > 1) cluster_sync_all();  // nobody still reads the old list state
+    if (rank == 0) nl_rebuild(np, sys, sm);
+    if (T > 1) cluster_sync_all();
+  } else if (rank == 0 && threadIdx.x == 0) {
+    atomicAdd(&sys.stats[1], 1ULL);
+  }
+  const int flags = eam_assign_rows(P, sys, sm.rowid, sm.red);
+  // warp-granular split of the walker's atoms over the cluster
+  const int Wn = (a.N + 31) >> 5;
+  const int w0 = static_cast<int>(rank) * Wn / static_cast<int>(T), w1 = (static_cast<int>(rank) + 1) * Wn / static_cast<int>(T);
+  const int i0 = w0 * 32, i1 = min(a.N, w1 * 32);
+  double *F = a.F + static_cast<size_t>(s) * a.strideR;
+  if (flags & 2) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
+    for (int k = 3 * i0 + threadIdx.x; k < 3 * i1; k += blockDim.x) F[k] = 0.0;
+    if (rank == 0 && threadIdx.x == 0) a.U[s] = nan("");
+    return;
+  }
+  if (!(flags & 1) && sm.geom->tab_ok && P.eam_fast_ok) {
+    if (i1 - i0 <= static_cast<int>(blockDim.x))
+      eam_fused_fast<true>(P, sys, sm, i0, i1, T, rank, F, a.U + s);
+    else
+      eam_fused_fast<false>(P, sys, sm, i0, i1, T, rank, F, a.U + s);
+    return;
+  }
+  eam_fused_general(P, sys, sm, flags, i0, i1, T, rank, F, a.U + s, a.N);
+}
+
+// Register budgets per CTA size: small CTAs must fit seven to an SM (all walkers resident in one wave).
+#ifdef EONB200_EMU
+inline void k_eam_fused(const PotParams *Pp, NlBatch nl, ForceBatchArgs a) { eam_fused_body(Pp, nl, a); }
+#else
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_eam_fused_t(const PotParams *__restrict__ Pp, NlBatch nl, ForceBatchArgs a) {
+  eam_fused_body(Pp, nl, a);
+}
+#endif
 
 // Neighbour lists only (eonb200_neighbors): build with the caller's cutoff, skin 0.
 __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_neighbors(NlBatch nl, NlParams np, int S, int N, const double *R,

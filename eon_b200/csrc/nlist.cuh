@@ -441,31 +441,45 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
   return row_max;
 }
 
-// Stage positions and make sure a valid candidate list exists for them (Verlet check + rebuild).
-// On return sm.pos holds the positions in the predicate's layout and sm.stage the raw ones.
-// Returns (to all threads) the largest row fill of a rebuild (> sys.K: the list is truncated), 0 if reused.
-__device__ inline int nl_ensure(const NlParams &np, const SysView &sys, Smem &sm, uint32_t &phase,
-                                bool force_rebuild, const double *exp_tab_g) {
+// Stage positions (sm.stage raw, sm.pos in the predicate's layout) and decide whether the cached candidate
+// list still covers them (Verlet check).  CTA-uniform result; every thread has read *sys.state on return.
+__device__ inline bool nl_stage_check(const NlParams &np, const SysView &sys, Smem &sm, uint32_t &phase,
+                                      bool force_rebuild, const double *exp_tab_g) {
   stage_raw_positions(sys, sm, phase);
   const double disp2 = prepare_positions(np, sys, sm, exp_tab_g);
   const bool have = *sys.state != 0;
   const double lim = 0.5 * np.skin;
   const bool rebuild = force_rebuild || !have || np.skin <= 0.0 || !(disp2 <= lim * lim);
   __syncthreads();  // every thread has read *sys.state before it can change
+  return rebuild;
+}
+
+// Rebuild this walker's list from sm.pos and record the build positions.  Returns the largest row fill.
+__device__ EONB200_NOINLINE int nl_rebuild(const NlParams &np, const SysView &sys, Smem &sm) {
+  const int row_max = nl_build(np, sys, sm);
+  for (int i = threadIdx.x; i < sys.N; i += blockDim.x) {
+    const double4 p = sm.pos[i];
+    sys.rbuild[3 * i] = p.x;
+    sys.rbuild[3 * i + 1] = p.y;
+    sys.rbuild[3 * i + 2] = p.z;
+  }
+  if (threadIdx.x == 0) {
+    *sys.state = 1;
+    atomicAdd(&sys.stats[0], 1ULL);
+  }
+  __syncthreads();
+  return row_max;
+}
+
+// Stage positions and make sure a valid candidate list exists for them (Verlet check + rebuild).
+// On return sm.pos holds the positions in the predicate's layout and sm.stage the raw ones.
+// Returns (to all threads) the largest row fill of a rebuild (> sys.K: the list is truncated), 0 if reused.
+__device__ inline int nl_ensure(const NlParams &np, const SysView &sys, Smem &sm, uint32_t &phase,
+                                bool force_rebuild, const double *exp_tab_g) {
+  const bool rebuild = nl_stage_check(np, sys, sm, phase, force_rebuild, exp_tab_g);
   int row_max = 0;
   if (rebuild) {
-    row_max = nl_build(np, sys, sm);
-    for (int i = threadIdx.x; i < sys.N; i += blockDim.x) {
-      const double4 p = sm.pos[i];
-      sys.rbuild[3 * i] = p.x;
-      sys.rbuild[3 * i + 1] = p.y;
-      sys.rbuild[3 * i + 2] = p.z;
-    }
-    if (threadIdx.x == 0) {
-      *sys.state = 1;
-      atomicAdd(&sys.stats[0], 1ULL);
-    }
-    __syncthreads();
+    row_max = nl_rebuild(np, sys, sm);
   } else if (threadIdx.x == 0) {
     atomicAdd(&sys.stats[1], 1ULL);
   }

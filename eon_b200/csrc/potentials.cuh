@@ -351,6 +351,177 @@ __device__ EONB200_NOINLINE void eam_pass2(const PotParams &P, const SysView &sy
   acc[0] += e_acc;
 }
 
+// ---- EAM, single element, one lane per atom: filter -> density -> (barrier) -> force ----------------------------
+// The fast path of the fused kernel.  Per atom i (one thread):
+//   filter   every cached candidate is re-tested with the reference's own predicate (EAM.cpp:152-172, un-fused,
+//            inclusive cutoff); survivors are compacted to the front of the atom's column of sys.nbr2, so the
+//            lanes of a warp run the expensive body with (nearly) all lanes busy instead of stalling on the skin shell;
+//   density  per surviving ordered pair: r, the three exponentials (EAM.cpp:174-215); rho_i += g(r); the pair's
+//            g'(r)/r goes to sys.pairA (L2 resident, 8 B per pair); the Morse pair force is applied right away;
+//            then F(rho_i), F'(rho_i) by Horner (EAM.cpp:349-365);
+//   force    F_i -= sum_j (F'_i + F'_j) g'(r)/r d  -- no transcendental, square root or division.
+// Exp arguments stay far above the underflow guard of exp_tab for any physical row (the host checks
+// PotParams::eam_fast_ok), so the guard is dropped here.
+__device__ __forceinline__ double exp_tab_fast(double x, const double *T) {
+  const double kInv = 184.6649652337873;
+  const double kShift = 6755399441055744.0;
+  const double kLn2Hi = 6.93147180369123816490e-01 / 128.0;
+  const double kLn2Lo = 1.90821492927058770002e-10 / 128.0;
+  double kd = fma(x, kInv, kShift);
+#ifdef EONB200_EMU
+  long long ki;
+  memcpy(&ki, &kd, 8);
+#else
+  const long long ki = __double_as_longlong(kd);
+#endif
+  kd -= kShift;
+  double r = fma(kd, -kLn2Hi, x);
+  r = fma(kd, -kLn2Lo, r);
+  const int k = static_cast<int>(ki);
+  const double t = T[k & 127];
+  double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  const double res = fma(t, q * r, t);
+  const long long e = static_cast<long long>(k >> 7) << 52;
+#ifdef EONB200_EMU
+  long long bits;
+  memcpy(&bits, &res, 8);
+  bits += e;
+  double out;
+  memcpy(&out, &bits, 8);
+  return out;
+#else
+  return __longlong_as_double(__double_as_longlong(res) + e);
+#endif
+}
+
+// d = r_i - r_j folded by the image recorded at build time (shift tables valid: Geom::tab_ok).
+__device__ __forceinline__ void mic_vec_tab(const Smem &sm, int code, const double4 &pi, const double4 &pj, double &dx,
+                                            double &dy, double &dz) {
+  const unsigned s = static_cast<unsigned>(code) >> kNbrIndexBits;
+  dx = (pi.x - pj.x) + sm.shx[s & 15];
+  dy = (pi.y - pj.y) + sm.shy[(s >> 4) & 15];
+  dz = (pi.z - pj.z) + sm.shz[(s >> 8) & 15];
+}
+
+struct EamLane {   // what one atom's thread carries from the density pass into the force pass
+  double fx, fy, fz;  // Morse pair part of the force, accumulated in the density pass
+  double dfd;         // F'(rho_i)
+  int nin;            // surviving (in-cutoff) ordered pairs of this atom
+};
+
+__device__ __forceinline__ void eam_fast_density(const PotParams &P, const SysView &sys, const Smem &sm, int i, EamLane &L,
+                                                 double (&acc)[2]) {
+  const double *T = sm.exp_tab;
+  const EamRowDev *pr = &P.rows[sm.rowid[0]];
+  const double rc2 = pr->rc2;
+  const int Np = sys.Np;
+  const double4 pi = sm.pos[i];
+  const int n = sys.cnt[i];
+  const int *row = sys.nbr + i;
+  int *row2 = sys.nbr2 + i;
+  double *rowA = sys.pairA + i;
+  // -- filter: batches of four candidate codes in flight
+  int nin = 0;
+  for (int k0 = 0; k0 < n; k0 += 4) {
+    int c[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) c[u] = (k0 + u < n) ? row[static_cast<size_t>(k0 + u) * Np] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (c[u] != -1) {
+        const double4 pj = sm.pos[c[u] & kNbrIndexMask];
+        double dx, dy, dz;
+        mic_vec_tab(sm, c[u], pi, pj, dx, dy, dz);
+        const double r2 = norm2_rn(dx, dy, dz);
+        if (!(r2 > rc2)) {  // EAM.cpp:172 (inclusive cutoff)
+          row2[static_cast<size_t>(nin) * Np] = c[u];
+          nin++;
+        }
+      }
+    }
+  }
+  // -- density / pair cache over the survivors
+  const double nb1 = -pr->beta1, nb2x2 = -2.0 * pr->beta2, nb2x1024 = -1024.0 * pr->beta2;
+  const double naM = -pr->alphaM, aMRm = pr->alphaM * pr->Rm, hDm = 0.5 * pr->Dm;
+  // sign of the reference's own pair force (EAM.cpp:203-215) or of -grad U
+  const double nK2 = -(P.eam_conservative ? 1.0 : -1.0) * 2.0 * pr->alphaM * pr->Dm;
+  double dens = 0.0, e_acc = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
+  int cnext = nin > 0 ? row2[0] : 0;
+  for (int kk = 0; kk < nin; kk++) {
+    const int code = cnext;
+    if (kk + 1 < nin) cnext = row2[static_cast<size_t>(kk + 1) * Np];
+    const double4 pj = sm.pos[code & kNbrIndexMask];
+    double dx, dy, dz;
+    mic_vec_tab(sm, code, pi, pj, dx, dy, dz);
+    const double r2 = norm2_rn(dx, dy, dz);
+    const double invr = rsqrt_f64(r2);
+    const double r = r2 * invr;
+    const double r4 = r2 * r2;
+    const double e1 = exp_tab_fast(nb1 * r, T);
+    const double e2 = exp_tab_fast(nb2x2 * r, T);
+    const double ex = exp_tab_fast(fma(naM, r, aMRm), T);
+    const double rho_pair = fma(512.0, e2, e1);
+    const double r6 = r4 * r2;
+    dens = fma(r6, rho_pair, dens);
+    const double u = fma(nb2x1024, e2, nb1 * e1);
+    const double gder = fma(6.0 * (r4 * r), rho_pair, r6 * u);
+    rowA[static_cast<size_t>(kk) * Np] = gder * invr;
+    const double dm = 1.0 - ex;
+    const double nB = (nK2 * dm) * (ex * invr);  // -(+-phi'(r)/r)
+    fx = fma(nB, dx, fx);
+    fy = fma(nB, dy, fy);
+    fz = fma(nB, dz, fz);
+    e_acc = fma(hDm, fma(dm, dm, -1.0), e_acc);  // half of Dm (d^2 - 1): the pair is seen from both ends
+  }
+  e_acc += eam_embed(pr->c, dens);
+  L.dfd = eam_dembed(pr->dc, dens);
+  L.fx = fx;
+  L.fy = fy;
+  L.fz = fz;
+  L.nin = nin;
+  acc[0] += e_acc;
+  acc[1] += static_cast<double>(nin);
+}
+
+// sm.pos[j].w must hold F'(rho_j) of every atom of the walker.
+__device__ __forceinline__ void eam_fast_force(const SysView &sys, const Smem &sm, int i, const EamLane &L, double *F) {
+  const int Np = sys.Np;
+  const double4 pi = sm.pos[i];
+  const int *row2 = sys.nbr2 + i;
+  const double *rowA = sys.pairA + i;
+  double fx = L.fx, fy = L.fy, fz = L.fz;
+  const double dfi = L.dfd;
+  const int nin = L.nin;
+  for (int k0 = 0; k0 < nin; k0 += 4) {
+    int c[4];
+    double A[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const bool ok = k0 + u < nin;
+      c[u] = ok ? row2[static_cast<size_t>(k0 + u) * Np] : -1;
+      A[u] = ok ? rowA[static_cast<size_t>(k0 + u) * Np] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (c[u] != -1) {
+        const double4 pj = sm.pos[c[u] & kNbrIndexMask];
+        double dx, dy, dz;
+        mic_vec_tab(sm, c[u], pi, pj, dx, dy, dz);
+        const double ns = -(dfi + pj.w) * A[u];
+        fx = fma(ns, dx, fx);
+        fy = fma(ns, dy, fy);
+        fz = fma(ns, dz, fz);
+      }
+    }
+  }
+  F[3 * i] = fx;
+  F[3 * i + 1] = fy;
+  F[3 * i + 2] = fz;
+}
+
 // Energy + raw forces (into sm.stage) of the whole walker staged in sm.pos -- the resident kernels' path.
 // Returns NaN if an element has no EAM row (the reference throws 14324, EAM.cpp:116-123).
 __device__ inline double walker_forces(const PotParams &P, const SysView &sys, Smem &sm, int lpa) {

@@ -30,6 +30,7 @@ struct PotParams {
   double morse_De, morse_a, morse_re;
   int n_rows;
   int eam_conservative;
+  int eam_fast_ok;        // every row keeps its exp arguments inside exp_tab_fast's range (set by the host)
   const double *exp_tab;  // [128] 2^(j/128), device memory (table of the exp used by the pair loops)
   EamRowDev rows[kMaxEamRows];
 };
@@ -61,6 +62,10 @@ struct NlBatch {
   // scratch of the tiled / two-pass force pipeline
   double *pairA;    // [S][K][Np] EAM: g'(r)/r of the ordered pair in slot (k, i), written by the density pass
   double *pairB;    // [S][K][Np] EAM: +-phi'(r)/r
+  int *nbr2;        // [S][K][Np] fused EAM kernel: this evaluation's in-cutoff pairs, compacted per atom
+  int *cnt2;        // [S][Np]    their count (only used when a thread owns more than one atom)
+  int *cellscratch; // [S][scratch_stride] cell-list scratch of an in-kernel rebuild (fused kernel)
+  int scratch_stride;
   double4 *pos4;    // [S][Np]    prepared positions (stateless tiled kernels)
   double *dfd;      // [S][Np]    EAM dF/drho
   unsigned char *rowid;  // [S][Np]
@@ -84,6 +89,9 @@ struct SysView {
   int *overflow;
   unsigned long long *stats;
   double *pairA, *pairB;  // this system's [K][Np] blocks (null for the pair potentials)
+  int *nbr2;
+  int *cnt2;
+  int *cellscratch;
   double4 *pos4;
   double *dfd;
   unsigned char *rowid;
@@ -110,6 +118,9 @@ __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, con
   v.stats = nl.stats;
   v.pairA = nl.pairA ? nl.pairA + static_cast<size_t>(s) * nl.K * nl.Np : nullptr;
   v.pairB = nl.pairB ? nl.pairB + static_cast<size_t>(s) * nl.K * nl.Np : nullptr;
+  v.nbr2 = nl.nbr2 ? nl.nbr2 + static_cast<size_t>(s) * nl.K * nl.Np : nullptr;
+  v.cnt2 = nl.cnt2 ? nl.cnt2 + static_cast<size_t>(s) * nl.Np : nullptr;
+  v.cellscratch = nl.cellscratch ? nl.cellscratch + static_cast<size_t>(s) * nl.scratch_stride : nullptr;
   v.pos4 = nl.pos4 ? nl.pos4 + static_cast<size_t>(s) * nl.Np : nullptr;
   v.dfd = nl.dfd ? nl.dfd + static_cast<size_t>(s) * nl.Np : nullptr;
   v.rowid = nl.rowid ? nl.rowid + static_cast<size_t>(s) * nl.Np : nullptr;
@@ -150,6 +161,7 @@ struct Smem {
   Geom *geom;
   double *exp_tab;   // [128] 2^(j/128)
   double *shx, *shy, *shz;  // [16] each: image shift s in [-8, 7] -> Cartesian offset along the axis
+  double *clu;       // [2 * 8] fused kernel: energy / pair-count partials of the CTAs of a cluster (rank 0 sums them)
   int maxCells;
 };
 
@@ -201,8 +213,62 @@ __device__ inline Smem carve_smem_tile(unsigned char *base, int N) {
   s.shz = s.shy + 16;
   s.dfd = nullptr;
   s.stage = nullptr;
+  s.clu = nullptr;
   s.cell_of = s.wrapc = s.order = s.cell_start = s.cell_fill = nullptr;
   s.maxCells = 0;
+  return s;
+}
+
+// Fused EAM kernel: positions, raw staging, reductions, rows, tables.  The cell-list scratch of the (rare)
+// in-kernel rebuild lives in HBM (SysView::cellscratch) so that it does not cost shared memory on every launch.
+__host__ __device__ inline size_t smem_bytes_fused(int N) {
+  size_t b = 0;
+  b += align_up(sizeof(double4) * N, 128);
+  b += align_up(sizeof(double) * 8 * kMaxWarps, 128);
+  b += align_up(sizeof(double) * (3 * static_cast<size_t>(N) + 2), 128);
+  b += align_up(static_cast<size_t>(N), 128);
+  b += 128;  // mbarrier
+  b += 128;  // cluster partials
+  b += align_up(sizeof(Geom), 128);
+  b += sizeof(double) * (128 + 48);
+  return b;
+}
+
+__host__ __device__ inline size_t fused_scratch_ints(int N, int maxCells) {
+  const size_t Np = (static_cast<size_t>(N) + 31) / 32 * 32;
+  return 3 * Np + 2 * ((static_cast<size_t>(maxCells) + 1 + 31) / 32 * 32);
+}
+
+__device__ inline Smem carve_smem_fused(unsigned char *base, int N, int maxCells, int *scratch) {
+  Smem s;
+  size_t o = 0;
+  s.pos = reinterpret_cast<double4 *>(base + o);
+  o += align_up(sizeof(double4) * N, 128);
+  s.red = reinterpret_cast<double *>(base + o);
+  o += align_up(sizeof(double) * 8 * kMaxWarps, 128);
+  s.stage = reinterpret_cast<double *>(base + o);
+  o += align_up(sizeof(double) * (3 * static_cast<size_t>(N) + 2), 128);
+  s.rowid = base + o;
+  o += align_up(static_cast<size_t>(N), 128);
+  s.mbar = reinterpret_cast<uint64_t *>(base + o);
+  o += 128;
+  s.clu = reinterpret_cast<double *>(base + o);
+  o += 128;
+  s.geom = reinterpret_cast<Geom *>(base + o);
+  o += align_up(sizeof(Geom), 128);
+  s.exp_tab = reinterpret_cast<double *>(base + o);
+  s.shx = s.exp_tab + 128;
+  s.shy = s.shx + 16;
+  s.shz = s.shy + 16;
+  s.dfd = nullptr;
+  const size_t Np = (static_cast<size_t>(N) + 31) / 32 * 32;
+  const size_t Cp = (static_cast<size_t>(maxCells) + 1 + 31) / 32 * 32;
+  s.cell_of = scratch;
+  s.wrapc = scratch ? scratch + Np : nullptr;
+  s.order = scratch ? scratch + 2 * Np : nullptr;
+  s.cell_start = scratch ? scratch + 3 * Np : nullptr;
+  s.cell_fill = scratch ? scratch + 3 * Np + Cp : nullptr;
+  s.maxCells = maxCells;
   return s;
 }
 
@@ -237,6 +303,7 @@ __device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells) {
   s.shx = s.exp_tab + 128;
   s.shy = s.shx + 16;
   s.shz = s.shy + 16;
+  s.clu = nullptr;
   s.maxCells = maxCells;
   return s;
 }

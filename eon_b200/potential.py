@@ -36,6 +36,15 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
+def _row_ptrs(a: np.ndarray, ctype):
+    """`ctype **` over the rows of a C-contiguous 2-D array, without a Python loop over the rows."""
+    addr = a.ctypes.data + np.arange(a.shape[0], dtype=np.uint64) * np.uint64(a.strides[0])
+    addr = np.ascontiguousarray(addr, dtype=np.uint64)
+    p = addr.ctypes.data_as(C.POINTER(C.POINTER(ctype)))
+    p._keepalive = addr
+    return p
+
+
 def eam_row(Z, Dm, alphaM, Rm, beta1, beta2, r_cut, func_coeff) -> _capi.EamRow:
     """One element row in the layout of include/eon/potentials/EAM/Parameters.h:15-50."""
     r = _capi.EamRow()
@@ -169,10 +178,9 @@ class B200Potential:
         F = np.empty((S, 3 * N), dtype=np.float64)
         U = np.empty(S, dtype=np.float64)
         V = np.empty(S, dtype=np.float64)
-        pR = (C.POINTER(C.c_double) * S)(*[_dp(R[s]) for s in range(S)])
-        pZ = (C.POINTER(C.c_int) * S)(*[_ip(Z[s]) for s in range(S)])
-        pF = (C.POINTER(C.c_double) * S)(*[_dp(F[s]) for s in range(S)])
-        pB = (C.POINTER(C.c_double) * S)(*[_dp(B[s]) for s in range(S)])
+        # arrays of per-system pointers (the reference's `const double *const *`), built from base address + row stride
+        pR, pZ, pF, pB = (_row_ptrs(R, C.c_double), _row_ptrs(Z, C.c_int), _row_ptrs(F, C.c_double),
+                          _row_ptrs(B, C.c_double))
         self._check(self._lib.eonb200_force_batch(self._h, S, N, pR, pZ, pF, _dp(U), _dp(V), pB))
         return F.reshape(S, N, 3), U, V
 
