@@ -26,7 +26,7 @@ SYMBOLS = [
     "eonb200_walkers_matter_forces", "eonb200_walkers_saddle_search", "eonb200_walkers_relax",
     "eonb200_walkers_displace_along_mode", "eonb200_walkers_harvest", "eonb200_walkers_last_ms",
     "eonb200_measure_fp64_peak", "eonb200_kernel_launches", "eonb200_nl_stats",
-    "eonb200_last_force_ms",
+    "eonb200_last_force_ms", "eonb200_phase_clocks", "eonb200_l2_flush",
 ]
 
 
@@ -119,4 +119,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.eonb200_nl_stats.restype = C.c_int
     lib.eonb200_last_force_ms.argtypes = [_vp, _dp]
     lib.eonb200_last_force_ms.restype = C.c_int
+    lib.eonb200_phase_clocks.argtypes = [_vp, C.c_int, C.POINTER(C.c_longlong), C.c_long, C.POINTER(C.c_long)]
+    lib.eonb200_phase_clocks.restype = C.c_int
+    lib.eonb200_l2_flush.argtypes = [_vp, C.c_size_t]
+    lib.eonb200_l2_flush.restype = C.c_int
     return lib

@@ -64,6 +64,7 @@ struct PinBuf {
 struct NlStore {
   DevBuf<int> nbr, cnt, state, flags, done, nbr2, cnt2, cellscratch;
   int scratch_stride = 0;
+  int rowmax_seen = 0;  // largest row fill any build of this store reported (rows worth prefetching)
   DevBuf<double> rbuild, pairA, pairB, dfd, upart;
   DevBuf<double4> pos4;
   DevBuf<unsigned char> rowid;
@@ -82,6 +83,10 @@ struct EonB200Pot {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   DevBuf<PotParams> dP;
   DevBuf<double> d_exp_tab;
+  DevBuf<unsigned char> d_flush;  // eonb200_l2_flush scratch
+  DevBuf<long long> d_clocks;  // per-CTA phase clocks of the last fused EAM launch (profiling aid)
+  int clocks_on = 0;
+  long clocks_ctas = 0;
   DevBuf<int> d_overflow;
   DevBuf<unsigned long long> d_stats;
   PinBuf<unsigned long long> h_stats;
@@ -278,7 +283,9 @@ void pick_fused(const EonB200Pot *pot, long S, long N, int *T_out, int *threads_
   } else if (S * Wn < 4L * pot->sm_count) {
     T = Wn;
   } else {
-    T = (2 * Wn + 3) / 7;  // about 3.5 warps per CTA
+    // two CTAs per walker: with the 72-register budget four 224-thread CTAs (or two 448-thread ones) share an SM, so a
+    // few hundred walkers are all resident in one round; clusters of four no longer pack into the GPCs that way
+    T = Wn >= 8 ? 2 : 1;
   }
   if (pot->cfg.tiles_override > 0) T = pot->cfg.tiles_override;
   T = std::max<long>(std::max<long>(T, Tmin), 1);
@@ -303,7 +310,7 @@ int guess_K(double rc, long N, const double *box) {
   double expect = det > 1e-30 ? static_cast<double>(N) / det * (4.0 / 3.0) * kPi * rc * rc * rc : static_cast<double>(N);
   long K = static_cast<long>(std::ceil(1.5 * expect)) + 16;
   K = std::min<long>(K, std::max<long>(N - 1, 16) + 32);
-  K = (K + 3) / 4 * 4;
+  K = (K + 7) / 8 * 8;
   return static_cast<int>(std::max<long>(K, 8));
 }
 
@@ -334,6 +341,7 @@ int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K) {
   nl.N = N;
   nl.K = K;
   nl.Np = Np;
+  nl.rowmax_seen = 0;
   return 0;
 }
 
@@ -399,6 +407,14 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
                   pot->max_dyn_smem);
     a.tiles = fused_T;
     a.lpa = 1;
+    a.kmax = nl.rowmax_seen > 0 ? std::min(nl.rowmax_seen, nl.K) : nl.K;
+    a.clocks = nullptr;
+    if (pot->clocks_on) {
+      pot->clocks_ctas = S * fused_T;
+      CU_TRY(pot, pot->d_clocks.reserve(static_cast<size_t>(pot->clocks_ctas) * 16));
+      CU_TRY(pot, cudaMemsetAsync(pot->d_clocks.p, 0, sizeof(long long) * pot->clocks_ctas * 16, pot->stream));
+      a.clocks = pot->d_clocks.p;
+    }
   } else {
     rc = check_smem(pot, N, a.maxCells, &smem);
     if (rc) return rc;
@@ -419,10 +435,13 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
 #ifdef EONB200_EMU
       EONB200_LAUNCH_CLUSTER(k_eam_fused, grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
 #else
+      // register budgets: every walker of a few-hundred-walker batch must be resident at once
       if (fused_threads <= 128)
         EONB200_LAUNCH_CLUSTER((k_eam_fused_t<128, 7>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
-      else if (fused_threads <= 256)
-        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<256, 3>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+      else if (fused_threads <= 224)
+        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<224, 4>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+      else if (fused_threads <= 448)
+        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<448, 2>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
       else
         EONB200_LAUNCH_CLUSTER((k_eam_fused_t<512, 1>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
 #endif
@@ -453,11 +472,14 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     pot->last_stats[2] = nl.K;
     pot->last_stats[3] = need;
     pot->last_stats[4] = static_cast<long long>(pot->h_stats.p[2]);
-    if (need <= nl.K) return 0;
+    if (need <= nl.K) {
+      nl.rowmax_seen = std::max(nl.rowmax_seen, need);
+      return 0;
+    }
     if (need >= (1 << 30))
       return fail(pot, 100, "neighbour image shift outside the representable range (box much smaller than the cutoff)");
     pot->force_calls -= static_cast<unsigned long long>(S);
-    const int K = (static_cast<int>(need * 1.2) + 8 + 3) / 4 * 4;
+    const int K = (static_cast<int>(need * 1.2) + 8 + 7) / 8 * 8;
     nl.K = 0;
     rc = nl_alloc(pot, nl, S, N, K);
     if (rc) return rc;
@@ -570,7 +592,9 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
 #ifndef EONB200_EMU
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<128, 7>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
-         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<256, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<224, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<448, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
@@ -605,6 +629,26 @@ unsigned long long eonb200_kernel_launches(const EonB200Pot *pot) { return pot ?
 int eonb200_nl_stats(EonB200Pot *pot, long long out[5]) {
   if (!pot) return 1;
   for (int k = 0; k < 5; k++) out[k] = pot->last_stats[k];
+  return 0;
+}
+
+int eonb200_l2_flush(EonB200Pot *pot, size_t bytes) {
+  if (!pot) return 1;
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  CU_TRY(pot, pot->d_flush.reserve(bytes));
+  CU_TRY(pot, cudaMemsetAsync(pot->d_flush.p, 0, bytes, pot->stream));
+  return 0;
+}
+
+int eonb200_phase_clocks(EonB200Pot *pot, int enable, long long *out, long cap_ctas, long *n_ctas) {
+  if (!pot) return 1;
+  pot->clocks_on = enable ? 1 : 0;
+  if (n_ctas) *n_ctas = pot->clocks_ctas;
+  if (out && pot->d_clocks.p && pot->clocks_ctas > 0) {
+    CU_TRY(pot, cudaSetDevice(pot->device));
+    const long n = std::min(cap_ctas, pot->clocks_ctas);
+    CU_TRY(pot, cudaMemcpy(out, pot->d_clocks.p, sizeof(long long) * n * 16, cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 

@@ -248,6 +248,50 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
       : "memory");
 #endif
 }
+// Several bulk copies completing on one mbarrier: announce the total first, then issue the copies.
+__device__ __forceinline__ void mbar_expect(uint64_t *bar, uint32_t bytes) {
+#ifndef EONB200_EMU
+  const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void bulk_g2s_issue(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+#ifndef EONB200_EMU
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  const uint32_t b = static_cast<uint32_t>(__cvta_generic_to_shared(bar));
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gsrc), "r"(bytes), "r"(b)
+               : "memory");
+#else
+  memcpy(smem_dst, gsrc, bytes);
+#endif
+}
+// Ask the memory system to bring [p, p + bytes) into L2 (bytes a multiple of 16, p 16-byte aligned) / one line.
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
+#ifndef EONB200_EMU
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void l2_prefetch_line(const void *p) {
+#ifndef EONB200_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+// Loads that bypass L1 (the line may have been rewritten by another CTA of the cluster during this kernel).
+__device__ __forceinline__ int ld_cg(const int *p) {
+#ifndef EONB200_EMU
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ double ld_cg(const double *p) {
+#ifndef EONB200_EMU
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
 __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes) {
 #ifndef EONB200_EMU
   const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem_src));

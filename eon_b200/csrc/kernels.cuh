@@ -28,7 +28,9 @@ struct ForceBatchArgs {
   int maxCells;
   int lpa;
   int tiles;         // CTAs per system in the force passes
+  int kmax;          // candidate rows worth prefetching (largest row fill seen so far)
   int force_rebuild;
+  long long *clocks;  // [S * tiles][16] per-CTA phase clocks (profiling aid, may be null)
 };
 
 __device__ inline NlParams make_nl_params(const PotParams &P) {
@@ -97,6 +99,7 @@ __device__ inline void tile_prologue(const PotParams &P, const SysView &sys, Sme
     const double val = P.nl_mode == NL_MIC ? -mul_rn(sft, len) : mul_rn(sft, len);
     (axis == 0 ? sm.shx : (axis == 1 ? sm.shy : sm.shz))[k & 15] = val;
   }
+  fill_sh27(sm, sys.box[0], sys.box[4], sys.box[8]);
   if (P.kind == POT_EAM)
     for (int i = threadIdx.x; i < N; i += blockDim.x) sm.rowid[i] = sys.rowid[i];
   __syncthreads();  // mbarrier initialised before anyone waits on it
@@ -171,14 +174,40 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_pair(const PotParams *
 // with one lane per atom.  A stale list is rebuilt in place by CTA 0 of the cluster (cell-list scratch in HBM).
 // Mixed-element systems and boxes too small for the stored image shifts take the general row functions
 // (eam_pass1 / eam_pass2) inside the same kernel.
+// Per-CTA phase clocks (eonb200_phase_clocks): slot 0 globaltimer ns at entry, 1 SM id, 2.. SM cycle counter.
+__device__ __forceinline__ void phase_clock(long long *clk, int slot) {
+#ifndef EONB200_EMU
+  if (clk && threadIdx.x == 0) clk[slot] = clock64();
+#else
+  (void)clk;
+  (void)slot;
+#endif
+}
+
+struct FusedFast {  // CTA-uniform inputs of the fast path
+  const EamRowDev *row;
+  double rc2;
+  float rc2_hi;
+};
+
 template <bool SINGLE>
-__device__ __forceinline__ void eam_fused_fast(const PotParams &P, const SysView &sys, Smem &sm, int i0, int i1, unsigned T,
-                                               unsigned rank, double *F, double *U) {
+__device__ __forceinline__ void eam_fused_fast(const PotParams &P, const FusedFast &ff, const SysView &sys, Smem &sm, int i0,
+                                               int i1, unsigned T, unsigned rank, double *F, double *U, int n_first,
+                                               int (&cur)[kFilterBatch], long long *clk) {
   double acc[2] = {0.0, 0.0};
   EamLane L = {0.0, 0.0, 0.0, 0.0, 0};
   const int ifirst = i0 + static_cast<int>(threadIdx.x);
   for (int i = ifirst; i < i1; i += blockDim.x) {
-    eam_fast_density(P, sys, sm, i, L, acc);
+    int n = n_first;
+    if (!SINGLE && i != ifirst) {
+      n = ld_cg(sys.cnt + i);
+#pragma unroll
+      for (int u = 0; u < kFilterBatch; u++) cur[u] = ld_cg(sys.nbr + static_cast<size_t>(u) * sys.Np + i);
+    }
+    const int nin = eam_fast_filter(sys, sm, i, n, cur, ff.rc2_hi);
+    phase_clock(clk, 5);
+    eam_fast_density(P, ff.row, sys, sm, i, nin, L, acc);
+    phase_clock(clk, 6);
     if (T > 1) {
       for (unsigned r = 0; r < T; r++) dsmem_store(&sm.pos[i].w, r, L.dfd);
     } else {
@@ -194,6 +223,7 @@ __device__ __forceinline__ void eam_fused_fast(const PotParams &P, const SysView
     if (SINGLE) break;
   }
   block_sum<2>(acc, sm.red);
+  phase_clock(clk, 7);
   if (threadIdx.x == 0) {
     if (T > 1) {
       dsmem_store(&sm.clu[rank], 0, acc[0]);
@@ -207,6 +237,7 @@ __device__ __forceinline__ void eam_fused_fast(const PotParams &P, const SysView
     cluster_sync_all();
   else
     __syncthreads();
+  phase_clock(clk, 8);
   for (int i = ifirst; i < i1; i += blockDim.x) {
     if (!SINGLE) {
       L.fx = F[3 * i];
@@ -218,6 +249,7 @@ __device__ __forceinline__ void eam_fused_fast(const PotParams &P, const SysView
     eam_fast_force(sys, sm, i, L, F);
     if (SINGLE) break;
   }
+  phase_clock(clk, 9);
   if (rank == 0 && threadIdx.x == 0) {
     double e = 0.0, n = 0.0;
     for (unsigned r = 0; r < T; r++) {  // fixed order: reproducible energies
@@ -229,9 +261,64 @@ __device__ __forceinline__ void eam_fused_fast(const PotParams &P, const SysView
   }
 }
 
+// Stale list: CTA 0 of the cluster rebuilds it (raw positions straight from HBM, cell-list scratch in HBM).
+// (Arguments by value: a reference would force the caller's shared-memory pointers onto the stack and turn every
+// shared load of the hot path into a generic one.)
+__device__ EONB200_NOINLINE void eam_fused_rebuild(NlParams np, SysView sys, Smem sm, unsigned T, unsigned rank,
+                                                  const double *exp_tab_g) {
+  if (T > 1) cluster_sync_all();  // nobody still reads the old list
+  if (rank == 0) {
+    Smem sm2 = sm;
+    sm2.stage = const_cast<double *>(sys.R);
+    prepare_positions(np, sys, sm2, exp_tab_g);
+    __syncthreads();
+    nl_rebuild(np, sys, sm2);
+  }
+  if (T > 1)
+    cluster_sync_all();
+  else
+    __syncthreads();
+}
+
+// Coordinates below zero (EAM.cpp:56-83 shifts them up by the lowest one): redo the conversion from HBM.
+__device__ EONB200_NOINLINE double eam_fused_reconvert(SysView sys, Smem sm, double lo0, double lo1, double lo2, double L0,
+                                                      double L1, double L2, bool have) {
+  const double lo[3] = {lo0, lo1, lo2}, L[3] = {L0, L1, L2};
+  double disp2 = 0.0;
+  for (int i = threadIdx.x; i < sys.N; i += blockDim.x) {
+    double p[3];
+    for (int k = 0; k < 3; k++) {
+      p[k] = sys.R[3 * i + k] + lo[k];
+      if (L[k] > 0.0) {
+        int guard = 0;
+        while (p[k] > L[k] && guard++ < 1000000) p[k] -= L[k];
+      }
+    }
+    sm.pos[i] = make_double4(p[0], p[1], p[2], 0.0);
+    sm.posf[i] = make_float4(static_cast<float>(p[0]), static_cast<float>(p[1]), static_cast<float>(p[2]), 0.0f);
+    if (have) {
+      const double dx = p[0] - sys.rbuild[3 * i], dy = p[1] - sys.rbuild[3 * i + 1], dz = p[2] - sys.rbuild[3 * i + 2];
+      disp2 = fmax(disp2, dx * dx + dy * dy + dz * dz);
+    }
+  }
+  return block_max1(disp2, sm.red);
+}
+
 // Mixed elements / small boxes: the general row functions, dF/drho exchanged through HBM.
-__device__ EONB200_NOINLINE void eam_fused_general(const PotParams &P, const SysView &sys, Smem &sm, int flags, int i0, int i1,
+__device__ EONB200_NOINLINE void eam_fused_general(const PotParams *Pp, SysView sys, Smem sm, bool tab_ok, int i0, int i1,
                                                   unsigned T, unsigned rank, double *F, double *U, int N) {
+  const PotParams &P = *Pp;
+  if (threadIdx.x == 0) {
+    Geom &g = *sm.geom;
+    for (int k = 0; k < 9; k++) g.H[k] = sys.box[k];
+    g.tab_ok = tab_ok ? 1 : 0;
+  }
+  const int flags = eam_assign_rows(P, sys, sm.rowid, sm.red);  // ends with a barrier: geometry visible
+  if (flags & 2) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
+    for (int k = 3 * i0 + threadIdx.x; k < 3 * i1; k += blockDim.x) F[k] = 0.0;
+    if (rank == 0 && threadIdx.x == 0) *U = nan("");
+    return;
+  }
   double acc[2] = {0.0, 0.0};
   if (flags & 1)
     eam_pass1<true>(P, sys, sm, 1, i0, i1, sys.dfd, acc);
@@ -275,37 +362,168 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   const PotParams &P = *Pp;
   const SysView sys = batch_sys(nl, a, s);
   Smem sm = carve_smem_fused(smem_raw, a.N, a.maxCells, sys.cellscratch);
-  if (threadIdx.x == 0) mbar_init(sm.mbar, 1);
-  __syncthreads();
-  uint32_t phase = 0;
+  const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
+  // warp-granular split of the walker's atoms over the cluster
+  const int Wn = (N + 31) >> 5;
+  const int w0 = static_cast<int>(rank) * Wn / static_cast<int>(T), w1 = (static_cast<int>(rank) + 1) * Wn / static_cast<int>(T);
+  const int i0 = w0 * 32, i1 = min(N, w1 * 32);
+  const int ifirst = i0 + tid;
+  long long *clk = a.clocks ? a.clocks + (static_cast<size_t>(s) * T + rank) * 16 : nullptr;
+#ifndef EONB200_EMU
+  if (clk && tid == 0) {
+    unsigned long long gt;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    clk[0] = static_cast<long long>(gt);
+    clk[1] = smid;
+    clk[2] = clock64();
+  }
+#endif
+
+  // ---- get every HBM access of the prologue in flight at once ----------------------------------------------
+  double *raw = reinterpret_cast<double *>(sm.pos) + (N + (N & 1));  // lands in the tail of the position block
+  const int D = 3 * N;
+  const int nd = ((D & 1) && sys.Rcap > D) ? D + 1 : D;
+  const uint32_t rbytes = static_cast<uint32_t>(nd) * 8u;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(sys.R) & 15u) == 0) && (rbytes % 16u == 0);
+  if (tid == 0) {
+    mbar_init(sm.mbar, 1);
+    if (aligned) {
+      mbar_expect(sm.mbar, rbytes + 1024u);
+      bulk_g2s_issue(raw, sys.R, rbytes, sm.mbar);
+      bulk_g2s_issue(sm.exp_tab, P.exp_tab, 1024u, sm.mbar);
+    }
+  }
+  const double Lbox[3] = {sys.box[0], sys.box[4], sys.box[8]};  // EAM.cpp:31 reads the diagonal only
+  const bool have = ld_cg(sys.state) != 0;
+  const int z0 = sys.Z[0];
+  int n_first = 0;
+  int cur[kFilterBatch];
+  if (ifirst < i1) {
+    n_first = ld_cg(sys.cnt + ifirst);
+#pragma unroll
+    for (int u = 0; u < kFilterBatch; u++) cur[u] = ld_cg(sys.nbr + static_cast<size_t>(u) * sys.Np + ifirst);
+  }
+  {  // L2 prefetch behind the loads the prologue waits for, one 128-byte line per lane and instruction: the list's
+     // build positions, the atomic numbers, then this CTA's slice of the candidate rows (one line per warp of atoms)
+    for (int o = tid * 16; o < D; o += nt * 16) l2_prefetch_line(sys.rbuild + o);
+    for (int o = tid * 32; o < N; o += nt * 32) l2_prefetch_line(sys.Z + o);
+    const int lines_per_row = w1 - w0;
+    const int kmax = a.kmax < sys.K ? a.kmax : sys.K;
+    const int nlines = (kmax - kFilterBatch) * lines_per_row;  // the first rows are being loaded into registers already
+    for (int q = tid; q < nlines; q += nt) {
+      const int k = kFilterBatch + q / lines_per_row, seg = q % lines_per_row;
+      l2_prefetch_line(sys.nbr + static_cast<size_t>(k) * sys.Np + i0 + 32 * seg);
+    }
+  }
+  fill_sh27(sm, Lbox[0], Lbox[1], Lbox[2]);
+  __syncthreads();  // mbarrier initialised
+  if (aligned) {
+    mbar_wait(sm.mbar, 0);
+  } else {
+    for (int k = tid; k < D; k += nt) raw[k] = sys.R[k];
+    for (int k = tid; k < 128; k += nt) sm.exp_tab[k] = P.exp_tab[k];
+    __syncthreads();
+  }
+
+  phase_clock(clk, 3);
+  // ---- raw coordinates -> wrapped positions (double + float), in place; Verlet displacement; element check ----
+  // pos[i] overlaps only raw[i'] with i' <= i, so a round reads its atoms into registers, meets at a barrier and
+  // then writes; later rounds read higher atoms only.
+  double red6[6] = {-1e300, -1e300, -1e300, 0.0, 0.0, 0.0};  // max(-x), max(-y), max(-z), disp^2, mixed elements
+  for (int base = 0; base < N; base += 4 * nt) {
+    double q[4][3];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = base + u * nt + tid;
+      if (i < N) {
+        q[u][0] = raw[3 * i];
+        q[u][1] = raw[3 * i + 1];
+        q[u][2] = raw[3 * i + 2];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = base + u * nt + tid;
+      if (i < N) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          red6[k] = fmax(red6[k], -q[u][k]);
+          if (Lbox[k] > 0.0) {
+            int guard = 0;
+            while (q[u][k] > Lbox[k] && guard++ < 1000000) q[u][k] -= Lbox[k];  // EAM.cpp:86-90
+          }
+        }
+        sm.pos[i] = make_double4(q[u][0], q[u][1], q[u][2], 0.0);
+        sm.posf[i] = make_float4(static_cast<float>(q[u][0]), static_cast<float>(q[u][1]), static_cast<float>(q[u][2]), 0.0f);
+        if (have) {
+          const double dx = q[u][0] - ld_cg(sys.rbuild + 3 * i), dy = q[u][1] - ld_cg(sys.rbuild + 3 * i + 1),
+                       dz = q[u][2] - ld_cg(sys.rbuild + 3 * i + 2);
+          red6[3] = fmax(red6[3], dx * dx + dy * dy + dz * dz);
+        }
+        if (sys.Z[i] != z0) red6[4] = 1.0;
+      }
+    }
+  }
+  if (tid == 0) {  // the ghost atom the row padding points at: far outside every cutoff
+    sm.pos[N] = make_double4(1e150, 1e150, 1e150, 0.0);
+    sm.posf[N] = make_float4(1e18f, 1e18f, 1e18f, 0.0f);
+  }
+  {
+    const int op[6] = {RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX};
+    block_reduce<6>(red6, op, sm.red);
+  }
+  phase_clock(clk, 4);
+  double disp2 = red6[3];
+  if (red6[0] > 0.0 || red6[1] > 0.0 || red6[2] > 0.0) {
+    disp2 = eam_fused_reconvert(sys, sm, fmax(red6[0], 0.0), fmax(red6[1], 0.0), fmax(red6[2], 0.0), Lbox[0], Lbox[1], Lbox[2],
+                                have);
+  }
   const NlParams np = make_nl_params(P);
-  const bool rebuild = nl_stage_check(np, sys, sm, phase, a.force_rebuild != 0, P.exp_tab);
+  const double lim = 0.5 * np.skin;
+  const bool rebuild = a.force_rebuild != 0 || !have || np.skin <= 0.0 || !(disp2 <= lim * lim);
   if (rebuild) {  // the same decision in every CTA of the cluster
-    if (T > 1) cluster_sync_all();  // nobody still reads the old list state
-    if (rank == 0) nl_rebuild(np, sys, sm);
-    if (T > 1) cluster_sync_all();
-  } else if (rank == 0 && threadIdx.x == 0) {
+    eam_fused_rebuild(np, sys, sm, T, rank, P.exp_tab);
+    if (ifirst < i1) {
+      n_first = ld_cg(sys.cnt + ifirst);
+#pragma unroll
+      for (int u = 0; u < kFilterBatch; u++) cur[u] = ld_cg(sys.nbr + static_cast<size_t>(u) * sys.Np + ifirst);
+    }
+  } else if (rank == 0 && tid == 0) {
     atomicAdd(&sys.stats[1], 1ULL);
   }
-  const int flags = eam_assign_rows(P, sys, sm.rowid, sm.red);
-  // warp-granular split of the walker's atoms over the cluster
-  const int Wn = (a.N + 31) >> 5;
-  const int w0 = static_cast<int>(rank) * Wn / static_cast<int>(T), w1 = (static_cast<int>(rank) + 1) * Wn / static_cast<int>(T);
-  const int i0 = w0 * 32, i1 = min(a.N, w1 * 32);
   double *F = a.F + static_cast<size_t>(s) * a.strideR;
-  if (flags & 2) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
-    for (int k = 3 * i0 + threadIdx.x; k < 3 * i1; k += blockDim.x) F[k] = 0.0;
-    if (rank == 0 && threadIdx.x == 0) a.U[s] = nan("");
-    return;
-  }
-  if (!(flags & 1) && sm.geom->tab_ok && P.eam_fast_ok) {
-    if (i1 - i0 <= static_cast<int>(blockDim.x))
-      eam_fused_fast<true>(P, sys, sm, i0, i1, T, rank, F, a.U + s);
+  const bool mixed = red6[4] != 0.0;
+  const double need = 2.0 * P.rc_list + P.skin;  // stored folds stay the reference's minimum image
+  const bool tab_ok = Lbox[0] >= need && Lbox[1] >= need && Lbox[2] >= need;
+  if (!mixed && tab_ok && P.eam_fast_ok) {
+    int r0 = -1;
+    for (int q = 0; q < P.n_rows; q++)
+      if (P.rows[q].Z == z0) {
+        r0 = q;
+        break;
+      }
+    if (r0 < 0) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
+      for (int k = 3 * i0 + tid; k < 3 * i1; k += nt) F[k] = 0.0;
+      if (rank == 0 && tid == 0) a.U[s] = nan("");
+      return;
+    }
+    FusedFast ff;
+    ff.row = &P.rows[r0];
+    ff.rc2 = ff.row->rc2;
+    const float band = eam_filter_band(fmax(fmax(Lbox[0], Lbox[1]), Lbox[2]), ff.row->r_cut);
+    ff.rc2_hi = static_cast<float>(ff.rc2) + band;
+    if (i1 - i0 <= nt)
+      eam_fused_fast<true>(P, ff, sys, sm, i0, i1, T, rank, F, a.U + s, n_first, cur, clk);
     else
-      eam_fused_fast<false>(P, sys, sm, i0, i1, T, rank, F, a.U + s);
+      eam_fused_fast<false>(P, ff, sys, sm, i0, i1, T, rank, F, a.U + s, n_first, cur, clk);
+    phase_clock(clk, 10);
     return;
   }
-  eam_fused_general(P, sys, sm, flags, i0, i1, T, rank, F, a.U + s, a.N);
+  // general rows: full element table, geometry for mic_vec
+  eam_fused_general(Pp, sys, sm, tab_ok, i0, i1, T, rank, F, a.U + s, N);
 }
 
 // Register budgets per CTA size: small CTAs must fit seven to an SM (all walkers resident in one wave).

@@ -72,6 +72,16 @@ __device__ inline void stage_raw_positions(const SysView &sys, Smem &sm, uint32_
   __syncthreads();
 }
 
+// NL_MIC image offsets: id = (fx + 1) + 3 (fy + 1) + 9 (fz + 1) -> -(fx Lx, fy Ly, fz Lz)  (EAM.cpp:157-168)
+__device__ inline void fill_sh27(const Smem &sm, double Lx, double Ly, double Lz) {
+  for (int k = threadIdx.x; k < 27; k += blockDim.x) {
+    const double fx = static_cast<double>(k % 3 - 1), fy = static_cast<double>((k / 3) % 3 - 1), fz = static_cast<double>(k / 9 - 1);
+    const double4 v = make_double4(-mul_rn(fx, Lx), -mul_rn(fy, Ly), -mul_rn(fz, Lz), 0.0);
+    sm.sh27[k] = v;
+    if (sm.sh27f) sm.sh27f[k] = make_float4(static_cast<float>(v.x), static_cast<float>(v.y), static_cast<float>(v.z), 0.0f);
+  }
+}
+
 // Geometry of the box + positions in the layout the predicate wants (sm.pos):
 //   NL_VESIN: raw coordinates.   NL_MIC: EAM.cpp:56-90 shifted / wrapped coordinates.
 // Also fills the shift tables and the exp table, and returns (to every thread) the largest squared
@@ -117,6 +127,7 @@ __device__ inline double prepare_positions(const NlParams &np, const SysView &sy
     const double val = np.mode == NL_MIC ? -mul_rn(sft, len) : mul_rn(sft, len);
     (axis == 0 ? sm.shx : (axis == 1 ? sm.shy : sm.shz))[k & 15] = val;
   }
+  fill_sh27(sm, g.H[0], g.H[4], g.H[8]);
   double disp2 = 0.0;
   const double L[3] = {g.H[0], g.H[4], g.H[8]};  // EAM.cpp:31 reads the diagonal only
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -396,7 +407,7 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
               if (fz > 0) dz -= g.H[8]; else if (fz < 0) dz += g.H[8];
               const double r2 = norm2_rn(dx, dy, dz);
               if (!(r2 <= np.rc2)) continue;
-              emit(pack_nbr(j, fx, fy, fz), r2 <= np.rc_core2);
+              emit(pack_mic(j, fx, fy, fz), r2 <= np.rc_core2);
             } else {
               const int wj = sm.wrapc[j];
               const int Sx = sx + wix - ((wj & 1023) - 512);
@@ -430,6 +441,10 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
       const int moves = nshell < holes ? nshell : holes;
       for (int t = 0; t < moves; t++)
         sys.nbr[static_cast<size_t>(ncore + t) * Np + i] = sys.nbr[static_cast<size_t>(K - 1 - t) * Np + i];
+    }
+    if (np.mode == NL_MIC && count <= K) {
+      // pad to a multiple of 8 with codes of the far-away ghost atom N (fused EAM filter: no bounds tests)
+      for (int k = count; (k & 7) && k < K; k++) sys.nbr[static_cast<size_t>(k) * Np + i] = pack_mic(N, 0, 0, 0);
     }
     sys.cnt[i] = count <= K ? count : 0;
     my_max = max(my_max, count);

@@ -110,10 +110,10 @@ __device__ __forceinline__ void mic_vec(const Smem &sm, int code, const double4 
   dy = pi.y - pj.y;
   dz = pi.z - pj.z;
   if (g.tab_ok) {
-    const unsigned s = static_cast<unsigned>(code) >> kNbrIndexBits;
-    dx += sm.shx[s & 15];
-    dy += sm.shy[(s >> 4) & 15];
-    dz += sm.shz[(s >> 8) & 15];
+    const double4 sh = sm.sh27[static_cast<unsigned>(code) >> kNbrIndexBits];
+    dx += sh.x;
+    dy += sh.y;
+    dz += sh.z;
   } else {
     const double Lx = g.H[0], Ly = g.H[4], Lz = g.H[8];
     if (dx > 0.5 * Lx) dx -= Lx; else if (dx < -0.5 * Lx) dx += Lx;
@@ -353,9 +353,10 @@ __device__ EONB200_NOINLINE void eam_pass2(const PotParams &P, const SysView &sy
 
 // ---- EAM, single element, one lane per atom: filter -> density -> (barrier) -> force ----------------------------
 // The fast path of the fused kernel.  Per atom i (one thread):
-//   filter   every cached candidate is re-tested with the reference's own predicate (EAM.cpp:152-172, un-fused,
-//            inclusive cutoff); survivors are compacted to the front of the atom's column of sys.nbr2, so the
-//            lanes of a warp run the expensive body with (nearly) all lanes busy instead of stalling on the skin shell;
+//   filter   every cached candidate is screened in single precision against rc^2 +- a rounding band; inside the
+//            band the reference's own predicate decides (EAM.cpp:152-172, double, un-fused, inclusive cutoff).
+//            Survivors are compacted to the front of the atom's column of sys.nbr2, so the lanes of a warp run the
+//            expensive body with (nearly) all lanes busy instead of idling through the skin shell;
 //   density  per surviving ordered pair: r, the three exponentials (EAM.cpp:174-215); rho_i += g(r); the pair's
 //            g'(r)/r goes to sys.pairA (L2 resident, 8 B per pair); the Morse pair force is applied right away;
 //            then F(rho_i), F'(rho_i) by Horner (EAM.cpp:349-365);
@@ -384,8 +385,8 @@ __device__ __forceinline__ double exp_tab_fast(double x, const double *T) {
   q = fma(q, r, 0.5);
   q = fma(q, r, 1.0);
   const double res = fma(t, q * r, t);
-  const long long e = static_cast<long long>(k >> 7) << 52;
 #ifdef EONB200_EMU
+  const long long e = static_cast<long long>(k >> 7) << 52;
   long long bits;
   memcpy(&bits, &res, 8);
   bits += e;
@@ -393,17 +394,32 @@ __device__ __forceinline__ double exp_tab_fast(double x, const double *T) {
   memcpy(&out, &bits, 8);
   return out;
 #else
-  return __longlong_as_double(__double_as_longlong(res) + e);
+  // times 2^(k >> 7): one 32-bit add on the exponent word
+  return __hiloint2double(__double2hiint(res) + ((k >> 7) << 20), __double2loint(res));
 #endif
 }
 
-// d = r_i - r_j folded by the image recorded at build time (shift tables valid: Geom::tab_ok).
+// 1/sqrt(x) for normal positive x (pair distances): hardware seed + one third-order step, without the library's
+// special-case branch.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+#ifdef EONB200_EMU
+  return 1.0 / sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(x * y, -y, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  return fma(c * e, y, y);
+#endif
+}
+
+// d = r_i - r_j folded by the image recorded at build time (image table valid: Geom::tab_ok).
 __device__ __forceinline__ void mic_vec_tab(const Smem &sm, int code, const double4 &pi, const double4 &pj, double &dx,
                                             double &dy, double &dz) {
-  const unsigned s = static_cast<unsigned>(code) >> kNbrIndexBits;
-  dx = (pi.x - pj.x) + sm.shx[s & 15];
-  dy = (pi.y - pj.y) + sm.shy[(s >> 4) & 15];
-  dz = (pi.z - pj.z) + sm.shz[(s >> 8) & 15];
+  const double4 sh = sm.sh27[static_cast<unsigned>(code) >> kNbrIndexBits];
+  dx = (pi.x - pj.x) + sh.x;
+  dy = (pi.y - pj.y) + sh.y;
+  dz = (pi.z - pj.z) + sh.z;
 }
 
 struct EamLane {   // what one atom's thread carries from the density pass into the force pass
@@ -412,52 +428,84 @@ struct EamLane {   // what one atom's thread carries from the density pass into 
   int nin;            // surviving (in-cutoff) ordered pairs of this atom
 };
 
-__device__ __forceinline__ void eam_fast_density(const PotParams &P, const SysView &sys, const Smem &sm, int i, EamLane &L,
-                                                 double (&acc)[2]) {
-  const double *T = sm.exp_tab;
-  const EamRowDev *pr = &P.rows[sm.rowid[0]];
-  const double rc2 = pr->rc2;
-  const int Np = sys.Np;
-  const double4 pi = sm.pos[i];
-  const int n = sys.cnt[i];
+constexpr int kFilterBatch = 8;  // candidate codes a lane keeps in flight; NL_MIC rows are padded to a multiple of it
+constexpr int kForceBatch = 4;   // same for the force pass over the compacted pairs
+
+// Single-precision screening margin above rc^2: beyond it the float distance rejects, everything else goes on to
+// the density pass, which applies the reference's own predicate (EAM.cpp:152-172, double, un-fused, inclusive
+// cutoff) to the exact distance it computes anyway.  |p| <= L after the wrap, so every float coordinate is off by
+// at most 2^-24 L and the float r^2 by well under 1e-6 (L + rc) rc; the margin keeps an 8x reserve over that.
+__device__ __forceinline__ float eam_filter_band(double Lmax, double rc) {
+  return static_cast<float>(8.0e-6 * (Lmax + rc) * rc);
+}
+
+// Filter of atom i: cur[] holds the first kFilterBatch codes of its column (already loaded).  Rows are padded to
+// a multiple of kFilterBatch with codes of the far-away ghost atom N, so no per-candidate bounds test is needed.
+__device__ __forceinline__ int eam_fast_filter(const SysView &sys, const Smem &sm, int i, int n, int (&cur)[kFilterBatch],
+                                               float rc2_hi) {
+  const size_t step = static_cast<size_t>(sys.Np);
   const int *row = sys.nbr + i;
   int *row2 = sys.nbr2 + i;
-  double *rowA = sys.pairA + i;
-  // -- filter: batches of four candidate codes in flight
+  const float4 pif = sm.posf[i];
   int nin = 0;
-  for (int k0 = 0; k0 < n; k0 += 4) {
-    int c[4];
+  for (int k0 = 0; k0 < n; k0 += kFilterBatch) {
+    int nxt[kFilterBatch];
+    row += kFilterBatch * step;
+    if (k0 + kFilterBatch < n) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) c[u] = (k0 + u < n) ? row[static_cast<size_t>(k0 + u) * Np] : -1;
+      for (int u = 0; u < kFilterBatch; u++) nxt[u] = ld_cg(row + u * step);
+    }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (c[u] != -1) {
-        const double4 pj = sm.pos[c[u] & kNbrIndexMask];
-        double dx, dy, dz;
-        mic_vec_tab(sm, c[u], pi, pj, dx, dy, dz);
-        const double r2 = norm2_rn(dx, dy, dz);
-        if (!(r2 > rc2)) {  // EAM.cpp:172 (inclusive cutoff)
-          row2[static_cast<size_t>(nin) * Np] = c[u];
-          nin++;
-        }
+    for (int u = 0; u < kFilterBatch; u++) {
+      const int c = cur[u];
+      const float4 shf = sm.sh27f[static_cast<unsigned>(c) >> kNbrIndexBits];
+      const float4 pjf = sm.posf[c & kNbrIndexMask];
+      const float dxf = (pif.x - pjf.x) + shf.x;
+      const float dyf = (pif.y - pjf.y) + shf.y;
+      const float dzf = (pif.z - pjf.z) + shf.z;
+      const float r2f = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
+      if (r2f <= rc2_hi) {
+        *row2 = c;
+        row2 += step;
+        nin++;
       }
     }
+#pragma unroll
+    for (int u = 0; u < kFilterBatch; u++) cur[u] = nxt[u];
   }
-  // -- density / pair cache over the survivors
+  return nin;
+}
+
+__device__ __forceinline__ void eam_fast_density(const PotParams &P, const EamRowDev *pr, const SysView &sys, const Smem &sm,
+                                                 int i, int nin, EamLane &L, double (&acc)[2]) {
+  const double *T = sm.exp_tab;
+  const size_t step = static_cast<size_t>(sys.Np);
+  const double4 pi = sm.pos[i];
+  int *row2 = sys.nbr2 + i;
+  double *rowA = sys.pairA + i;
+  const double rc2 = pr->rc2;
   const double nb1 = -pr->beta1, nb2x2 = -2.0 * pr->beta2, nb2x1024 = -1024.0 * pr->beta2;
   const double naM = -pr->alphaM, aMRm = pr->alphaM * pr->Rm, hDm = 0.5 * pr->Dm;
   // sign of the reference's own pair force (EAM.cpp:203-215) or of -grad U
   const double nK2 = -(P.eam_conservative ? 1.0 : -1.0) * 2.0 * pr->alphaM * pr->Dm;
   double dens = 0.0, e_acc = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
-  int cnext = nin > 0 ? row2[0] : 0;
+  int npairs = 0;
+  int cnext = nin > 0 ? ld_cg(row2) : 0;
   for (int kk = 0; kk < nin; kk++) {
     const int code = cnext;
-    if (kk + 1 < nin) cnext = row2[static_cast<size_t>(kk + 1) * Np];
+    row2 += step;
+    if (kk + 1 < nin) cnext = ld_cg(row2);
     const double4 pj = sm.pos[code & kNbrIndexMask];
     double dx, dy, dz;
     mic_vec_tab(sm, code, pi, pj, dx, dy, dz);
     const double r2 = norm2_rn(dx, dy, dz);
-    const double invr = rsqrt_f64(r2);
+    if (r2 > rc2) {  // EAM.cpp:172 -- only pairs inside the single-precision margin of the filter get here
+      *rowA = 0.0;
+      rowA += step;
+      continue;
+    }
+    npairs++;
+    const double invr = rsqrt_fast(r2);
     const double r = r2 * invr;
     const double r4 = r2 * r2;
     const double e1 = exp_tab_fast(nb1 * r, T);
@@ -468,13 +516,21 @@ __device__ __forceinline__ void eam_fast_density(const PotParams &P, const SysVi
     dens = fma(r6, rho_pair, dens);
     const double u = fma(nb2x1024, e2, nb1 * e1);
     const double gder = fma(6.0 * (r4 * r), rho_pair, r6 * u);
-    rowA[static_cast<size_t>(kk) * Np] = gder * invr;
+    *rowA = gder * invr;
+    rowA += step;
     const double dm = 1.0 - ex;
     const double nB = (nK2 * dm) * (ex * invr);  // -(+-phi'(r)/r)
     fx = fma(nB, dx, fx);
     fy = fma(nB, dy, fy);
     fz = fma(nB, dz, fz);
     e_acc = fma(hDm, fma(dm, dm, -1.0), e_acc);  // half of Dm (d^2 - 1): the pair is seen from both ends
+  }
+  // pad the compacted column to a multiple of kForceBatch with null pairs (weight 0, partner = the atom itself)
+  for (int kk = nin; kk & (kForceBatch - 1); kk++) {
+    *row2 = i | (13 << kNbrIndexBits);
+    *rowA = 0.0;
+    row2 += step;
+    rowA += step;
   }
   e_acc += eam_embed(pr->c, dens);
   L.dfd = eam_dembed(pr->dc, dens);
@@ -483,38 +539,54 @@ __device__ __forceinline__ void eam_fast_density(const PotParams &P, const SysVi
   L.fz = fz;
   L.nin = nin;
   acc[0] += e_acc;
-  acc[1] += static_cast<double>(nin);
+  acc[1] += static_cast<double>(npairs);
 }
 
 // sm.pos[j].w must hold F'(rho_j) of every atom of the walker.
 __device__ __forceinline__ void eam_fast_force(const SysView &sys, const Smem &sm, int i, const EamLane &L, double *F) {
-  const int Np = sys.Np;
+  constexpr int B = kForceBatch;
+  const size_t step = static_cast<size_t>(sys.Np);
   const double4 pi = sm.pos[i];
   const int *row2 = sys.nbr2 + i;
   const double *rowA = sys.pairA + i;
   double fx = L.fx, fy = L.fy, fz = L.fz;
   const double dfi = L.dfd;
   const int nin = L.nin;
-  for (int k0 = 0; k0 < nin; k0 += 4) {
-    int c[4];
-    double A[4];
+  int c[B];
+  double A[B];
+  if (nin > 0) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const bool ok = k0 + u < nin;
-      c[u] = ok ? row2[static_cast<size_t>(k0 + u) * Np] : -1;
-      A[u] = ok ? rowA[static_cast<size_t>(k0 + u) * Np] : 0.0;
+    for (int u = 0; u < B; u++) {
+      c[u] = ld_cg(row2 + u * step);
+      A[u] = ld_cg(rowA + u * step);
+    }
+  }
+  for (int k0 = 0; k0 < nin; k0 += B) {
+    int cn[B];
+    double An[B];
+    row2 += B * step;
+    rowA += B * step;
+    if (k0 + B < nin) {
+#pragma unroll
+      for (int u = 0; u < B; u++) {
+        cn[u] = ld_cg(row2 + u * step);
+        An[u] = ld_cg(rowA + u * step);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      if (c[u] != -1) {
-        const double4 pj = sm.pos[c[u] & kNbrIndexMask];
-        double dx, dy, dz;
-        mic_vec_tab(sm, c[u], pi, pj, dx, dy, dz);
-        const double ns = -(dfi + pj.w) * A[u];
-        fx = fma(ns, dx, fx);
-        fy = fma(ns, dy, fy);
-        fz = fma(ns, dz, fz);
-      }
+    for (int u = 0; u < B; u++) {
+      const double4 pj = sm.pos[c[u] & kNbrIndexMask];
+      double dx, dy, dz;
+      mic_vec_tab(sm, c[u], pi, pj, dx, dy, dz);
+      const double ns = -(dfi + pj.w) * A[u];
+      fx = fma(ns, dx, fx);
+      fy = fma(ns, dy, fy);
+      fz = fma(ns, dz, fz);
+    }
+#pragma unroll
+    for (int u = 0; u < B; u++) {
+      c[u] = cn[u];
+      A[u] = An[u];
     }
   }
   F[3 * i] = fx;

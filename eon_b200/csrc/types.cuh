@@ -50,6 +50,12 @@ __device__ __host__ __forceinline__ void unpack_nbr(int code, int &j, int &sx, i
   sz = ((s >> 8) & 15) - 8;
 }
 
+// NL_MIC lists (EAM.cpp's single minimum image) only ever fold by -1, 0 or +1 box lengths per axis: their codes carry
+// one image id in [0, 27) above the index, which selects a ready-made Cartesian offset (Smem::sh27).
+__device__ __host__ __forceinline__ int pack_mic(int j, int fx, int fy, int fz) {
+  return j | (((fx + 1) + 3 * (fy + 1) + 9 * (fz + 1)) << kNbrIndexBits);
+}
+
 // Cached neighbour lists of a batch of systems (one row block per system).
 struct NlBatch {
   int *nbr;        // [S][K][Np]  packed (j, shift); slot-major so that lanes = atoms read coalesced
@@ -160,7 +166,10 @@ struct Smem {
   uint64_t *mbar;
   Geom *geom;
   double *exp_tab;   // [128] 2^(j/128)
-  double *shx, *shy, *shz;  // [16] each: image shift s in [-8, 7] -> Cartesian offset along the axis
+  double *shx, *shy, *shz;  // [16] each: image shift s in [-8, 7] -> Cartesian offset along the axis (NL_VESIN)
+  double4 *sh27;     // [27] NL_MIC: image id -> offset added to r_i - r_j (fold +1 means "d > L/2 -> d -= L")
+  float4 *sh27f;     // [27] single-precision copy (fused kernel pre-filter)
+  float4 *posf;      // [N]   fused kernel: single-precision copy of the positions (pre-filter)
   double *clu;       // [2 * 8] fused kernel: energy / pair-count partials of the CTAs of a cluster (rank 0 sums them)
   int maxCells;
 };
@@ -178,7 +187,7 @@ __host__ __device__ inline size_t smem_bytes(int N, int maxCells) {
   b += align_up(static_cast<size_t>(N), 128);
   b += 128;  // mbarrier
   b += align_up(sizeof(Geom), 128);
-  b += sizeof(double) * (128 + 48);
+  b += sizeof(double) * (128 + 48) + sizeof(double4) * 28;
   return b;
 }
 
@@ -190,7 +199,7 @@ __host__ __device__ inline size_t smem_bytes_tile(int N) {
   b += align_up(static_cast<size_t>(N), 128);
   b += 128;
   b += align_up(sizeof(Geom), 128);
-  b += sizeof(double) * (128 + 48);
+  b += sizeof(double) * (128 + 48) + sizeof(double4) * 28;
   return b;
 }
 
@@ -211,9 +220,12 @@ __device__ inline Smem carve_smem_tile(unsigned char *base, int N) {
   s.shx = s.exp_tab + 128;
   s.shy = s.shx + 16;
   s.shz = s.shy + 16;
+  s.sh27 = reinterpret_cast<double4 *>(s.shz + 16);
+  s.sh27f = nullptr;
   s.dfd = nullptr;
   s.stage = nullptr;
   s.clu = nullptr;
+  s.posf = nullptr;
   s.cell_of = s.wrapc = s.order = s.cell_start = s.cell_fill = nullptr;
   s.maxCells = 0;
   return s;
@@ -223,14 +235,14 @@ __device__ inline Smem carve_smem_tile(unsigned char *base, int N) {
 // in-kernel rebuild lives in HBM (SysView::cellscratch) so that it does not cost shared memory on every launch.
 __host__ __device__ inline size_t smem_bytes_fused(int N) {
   size_t b = 0;
-  b += align_up(sizeof(double4) * N, 128);
+  b += align_up(sizeof(double4) * (N + 1) + 32, 128);  // positions; the raw coordinates land in the tail and are converted in place
+  b += align_up(sizeof(float4) * (N + 1), 128);
   b += align_up(sizeof(double) * 8 * kMaxWarps, 128);
-  b += align_up(sizeof(double) * (3 * static_cast<size_t>(N) + 2), 128);
   b += align_up(static_cast<size_t>(N), 128);
   b += 128;  // mbarrier
   b += 128;  // cluster partials
   b += align_up(sizeof(Geom), 128);
-  b += sizeof(double) * (128 + 48);
+  b += sizeof(double) * (128 + 48) + sizeof(double4) * 28 + sizeof(float4) * 28;
   return b;
 }
 
@@ -243,11 +255,11 @@ __device__ inline Smem carve_smem_fused(unsigned char *base, int N, int maxCells
   Smem s;
   size_t o = 0;
   s.pos = reinterpret_cast<double4 *>(base + o);
-  o += align_up(sizeof(double4) * N, 128);
+  o += align_up(sizeof(double4) * (N + 1) + 32, 128);
+  s.posf = reinterpret_cast<float4 *>(base + o);
+  o += align_up(sizeof(float4) * (N + 1), 128);
   s.red = reinterpret_cast<double *>(base + o);
   o += align_up(sizeof(double) * 8 * kMaxWarps, 128);
-  s.stage = reinterpret_cast<double *>(base + o);
-  o += align_up(sizeof(double) * (3 * static_cast<size_t>(N) + 2), 128);
   s.rowid = base + o;
   o += align_up(static_cast<size_t>(N), 128);
   s.mbar = reinterpret_cast<uint64_t *>(base + o);
@@ -260,7 +272,10 @@ __device__ inline Smem carve_smem_fused(unsigned char *base, int N, int maxCells
   s.shx = s.exp_tab + 128;
   s.shy = s.shx + 16;
   s.shz = s.shy + 16;
+  s.sh27 = reinterpret_cast<double4 *>(s.shz + 16);
+  s.sh27f = reinterpret_cast<float4 *>(s.sh27 + 28);
   s.dfd = nullptr;
+  s.stage = nullptr;
   const size_t Np = (static_cast<size_t>(N) + 31) / 32 * 32;
   const size_t Cp = (static_cast<size_t>(maxCells) + 1 + 31) / 32 * 32;
   s.cell_of = scratch;
@@ -303,7 +318,10 @@ __device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells) {
   s.shx = s.exp_tab + 128;
   s.shy = s.shx + 16;
   s.shz = s.shy + 16;
+  s.sh27 = reinterpret_cast<double4 *>(s.shz + 16);
+  s.sh27f = nullptr;
   s.clu = nullptr;
+  s.posf = nullptr;
   s.maxCells = maxCells;
   return s;
 }

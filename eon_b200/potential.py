@@ -245,5 +245,19 @@ class B200Potential:
         self._lib.eonb200_last_force_ms(self._h, out)
         return out[0], out[1]
 
+    def l2_flush(self, nbytes: int = 512 << 20):
+        """Queue an L2-evicting memset on the potential's stream (returns immediately)."""
+        self._check(self._lib.eonb200_l2_flush(self._h, int(nbytes)))
+
+    def phase_clocks(self, enable: bool = True):
+        """Per-CTA phase clocks of the last fused EAM launch -> int64 array [n_ctas, 16] (see eonb200_phase_clocks)."""
+        n = C.c_long(0)
+        self._check(self._lib.eonb200_phase_clocks(self._h, 1 if enable else 0, None, 0, C.byref(n)))
+        out = np.zeros((max(int(n.value), 0), 16), dtype=np.int64)
+        if n.value > 0:
+            self._check(self._lib.eonb200_phase_clocks(self._h, 1 if enable else 0,
+                                                       out.ctypes.data_as(C.POINTER(C.c_longlong)), n.value, C.byref(n)))
+        return out
+
     def measure_fp64_peak(self, repeats: int = 5) -> float:
         return float(self._lib.eonb200_measure_fp64_peak(self._h, repeats))

@@ -237,6 +237,16 @@ EONB200_API int eonb200_nl_stats(EonB200Pot *pot, long long out[5]);
  * out[0] = k_prepare (staging, Verlet check, cell-list rebuilds), out[1] = the force pass kernel(s). */
 EONB200_API int eonb200_last_force_ms(EonB200Pot *pot, double out[2]);
 
+/* Measurement aid: overwrite `bytes` of scratch HBM on the handle's stream (asynchronously), which evicts the L2
+ * cache (126 MB on B200) ahead of the next evaluation without letting the stream run dry. */
+EONB200_API int eonb200_l2_flush(EonB200Pot *pot, size_t bytes);
+
+/* Profiling aid of the fused EAM kernel: with `enable` != 0 the next launches record, per CTA, 16 words
+ * (0: %globaltimer ns at entry, 1: SM id, 2..10: SM cycle counter at entry / positions landed / conversion and
+ * Verlet check done / filter done / density done / CTA density done / cluster barrier passed / force done / exit;
+ * thread 0 of the CTA).  Copies the last launch's records (n_ctas = nSystems * CTAs per system) to `out`. */
+EONB200_API int eonb200_phase_clocks(EonB200Pot *pot, int enable, long long *out, long cap_ctas, long *n_ctas);
+
 #ifdef __cplusplus
 }
 #endif

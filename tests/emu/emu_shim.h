@@ -115,6 +115,10 @@ struct double4 {
   double x, y, z, w;
 };
 inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
+struct float4 {
+  float x, y, z, w;
+};
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 using std::max;
 using std::min;
 
