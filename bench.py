@@ -253,7 +253,9 @@ def run_b200(args):
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
         return float(t.item())
 
-    first = rank * N_WALKERS
+    from eon_b200 import sharding
+    first, last = sharding.shard_range(N_WALKERS * world, rank, world)  # weak scaling: 256 walkers per GPU
+    assert last - first == N_WALKERS
     struct, sets = force_workload(first)
     N, W = struct.n_atoms, N_WALKERS
     pot = B200Potential("eam", device=local_rank, skin=args.skin, tiles_override=args.tiles, lpa_override=args.lpa)
@@ -367,9 +369,14 @@ def run_b200(args):
         barrier()
         wk.saddle_search(prm, E0)
         ms = reduce_max(wk.last_ms)
-        h = wk.harvest(geometry=False)
-        good = reduce_sum(float((h.status == 0).sum()))
-        fcalls = reduce_sum(float(h.force_calls.sum()))
+        h_local = wk.harvest(geometry=False)
+        good = reduce_sum(float((h_local.status == 0).sum()))
+        fcalls = reduce_sum(float(h_local.force_calls.sum()))
+        h = sharding.harvest(h_local, dst=0)  # the path's only exchange: results of all ranks, walker order, on rank 0
+        if h is None:
+            h = h_local
+        elif world > 1:
+            assert h.status.shape[0] == W * world and int((h.status == 0).sum()) == int(good)
         search = {"searches_per_hour": good / (ms * 1e-3) * 3600.0, "unit": "status-0 saddle searches/hour",
                   "walkers": int(W * world), "status_good": int(good), "ms": ms,
                   "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(h.status, return_counts=True))},
