@@ -316,15 +316,23 @@ def run_b200(args):
     pot0.close()
 
     # e2e: host buffers through the plugin call (H2D + kernels + D2H inside the timed region)
+    # The caller owns its buffers, as eOn's Matter does: position sets and one force array live for the whole run, and
+    # the handle is asked to page-lock them (pin_host_buffers) instead of staging every call.
+    epot = B200Potential("eam", device=local_rank, skin=args.skin, tiles_override=args.tiles, lpa_override=args.lpa,
+                         pin_host_buffers=1)
     h_R = [np.ascontiguousarray(sets[k].reshape(W, 3 * N)) for k in range(N_POSITION_SETS)]
-    for k in range(2):
-        pot.forceBatch(W, N, h_R[k % N_POSITION_SETS], struct.atomic_nrs, struct.cell.reshape(9))
+    h_F = np.empty((W, 3 * N), dtype=np.float64)
+    for k in range(N_POSITION_SETS + 1):
+        epot.forceBatch(W, N, h_R[k % N_POSITION_SETS], struct.atomic_nrs, struct.cell.reshape(9), out=h_F)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        pot.forceBatch(W, N, h_R[k % N_POSITION_SETS], struct.atomic_nrs, struct.cell.reshape(9))
+        _, e_U, _ = epot.forceBatch(W, N, h_R[k % N_POSITION_SETS], struct.atomic_nrs, struct.cell.reshape(9), out=h_F)
     torch.cuda.synchronize()
     e2e_s = reduce_max(time.perf_counter() - t0)
+    # same position set as the last device-resident step above: the host path must return the same energies
+    assert np.allclose(e_U, d_U.cpu().numpy(), rtol=0.0, atol=1e-8), "e2e energies differ from the device-resident run"
+    epot.close()
     e2e_value = units / e2e_s
     h2d = W * (3 * N * 8 + (3 * N % 2) * 8 + N * 4 + 72)
     d2h = W * (3 * N * 8 + (3 * N % 2) * 8 + 8)
@@ -388,6 +396,25 @@ def run_b200(args):
             cpu_s, _ = cpu_search_baseline(s2, Rmin, E0, max(8, os.cpu_count() or 1))
             search["cpu_baseline"] = cpu_s
         wk.close()
+        # A launch of 256 walkers lasts as long as its slowest walker (a chain of ~10^3 dependent force calls) and
+        # leaves most SMs idle; the same job with four times the walkers shows the throughput the device has left.
+        W4 = 4 * W
+        wk4 = Walkers(spot, s2.atomic_nrs, s2.fixed, s2.cell, np.broadcast_to(Rmin.reshape(1, -1), (W4, 3 * N)).copy())
+        R4 = np.empty((W4, N, 3))
+        M4 = np.empty((W4, N, 3))
+        for k in range(W4):
+            R4[k], M4[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"], cfg["seed"] + 4 * first + k)
+        wk4.set(positions=R4, modes=M4)
+        barrier()
+        wk4.saddle_search(prm, E0)
+        ms4 = reduce_max(wk4.last_ms)
+        h4 = wk4.harvest(geometry=False)
+        good4 = reduce_sum(float((h4.status == 0).sum()))
+        fc4 = reduce_sum(float(h4.force_calls.sum()))
+        search["walkers_x4"] = {"walkers": int(W4 * world), "ms": ms4, "status_good": int(good4),
+                                "searches_per_hour": good4 / (ms4 * 1e-3) * 3600.0,
+                                "atom_force_evals_per_s": fc4 * N / (ms4 * 1e-3)}
+        wk4.close()
         spot.close()
 
     cpu = None

@@ -97,6 +97,7 @@ struct EonB200Pot {
   PinBuf<double> hR, hF, hU, hbox;
   PinBuf<int> hZ;
   std::vector<double> last_boxes;
+  std::vector<std::pair<const char *, size_t>> pinned;  // caller ranges page-locked by this handle (pin_host_buffers)
   NlStore nl;  // cache of the stateless batch slots
   unsigned long long force_calls = 0, launches = 0;
   long long last_stats[5] = {0, 0, 0, 0, 0};
@@ -378,6 +379,38 @@ int check_smem(EonB200Pot *pot, long N, int maxCells, size_t *bytes) {
   return 0;
 }
 
+// pin_host_buffers: are the S per-system arrays one contiguous block?  Then page-lock it (once) for direct DMA.
+template <typename T>
+bool rows_contiguous(T *const *rows, long S, size_t elems) {
+  for (long s = 1; s < S; s++)
+    if (rows[s] != rows[0] + static_cast<size_t>(s) * elems) return false;
+  return true;
+}
+
+bool pin_range(EonB200Pot *pot, const void *p, size_t bytes) {
+#ifdef EONB200_EMU
+  (void)pot;
+  (void)p;
+  (void)bytes;
+  return false;
+#else
+  if (!pot->cfg.pin_host_buffers || bytes == 0) return false;
+  const char *b = static_cast<const char *>(p);
+  for (auto &r : pot->pinned)
+    if (b >= r.first && b + bytes <= r.first + r.second) return true;
+  if (pot->pinned.size() >= 32) {  // bounded cache: drop the oldest registration
+    cudaHostUnregister(const_cast<char *>(pot->pinned.front().first));
+    pot->pinned.erase(pot->pinned.begin());
+  }
+  if (cudaHostRegister(const_cast<char *>(b), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+    cudaGetLastError();  // e.g. overlaps a range somebody else registered: fall back to staging
+    return false;
+  }
+  pot->pinned.emplace_back(b, bytes);
+  return true;
+#endif
+}
+
 // Launch the batched force evaluation on device-resident arrays; handles truncated lists by
 // regrowing the row capacity and re-running.  Synchronises when it has to look at the flags.
 int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double *h_box0, bool sync_and_check) {
@@ -587,6 +620,10 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
     pot->max_dyn_smem = limit - worst_static - 1024;
     ok = cudaFuncSetAttribute(reinterpret_cast<const void *>(k_walkers), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
+#ifndef EONB200_EMU
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_walkers_x2), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+#endif
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_prepare), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
 #ifndef EONB200_EMU
@@ -616,6 +653,9 @@ void eonb200_destroy(EonB200Pot *pot) {
   if (!pot) return;
   cudaSetDevice(pot->device);
   if (pot->stream) cudaStreamSynchronize(pot->stream);
+#ifndef EONB200_EMU
+  for (auto &r : pot->pinned) cudaHostUnregister(const_cast<char *>(r.first));
+#endif
   for (int k = 0; k < 3; k++)
     if (pot->ev[k]) cudaEventDestroy(pot->ev[k]);
   if (pot->stream) cudaStreamDestroy(pot->stream);
@@ -688,15 +728,23 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   CU_TRY(pot, pot->hbox.reserve(S * 9));
   CU_TRY(pot, pot->hZ.reserve(S * N));
   bool box_changed = pot->last_boxes.size() != static_cast<size_t>(S) * 9;
+  const bool direct_in = rows_contiguous(positions, S, D) && pin_range(pot, positions[0], S * D * sizeof(double));
+  const bool direct_out = rows_contiguous(forces, S, D) && pin_range(pot, forces[0], S * D * sizeof(double));
   for (long s = 0; s < S; s++) {
-    memcpy(pot->hR.p + s * strideR, positions[s], D * sizeof(double));
-    if (strideR > D) pot->hR.p[s * strideR + D] = 0.0;
+    if (!direct_in) {
+      memcpy(pot->hR.p + s * strideR, positions[s], D * sizeof(double));
+      if (strideR > D) pot->hR.p[s * strideR + D] = 0.0;
+    }
     memcpy(pot->hZ.p + s * N, atomicNrs[s], N * sizeof(int));
     memcpy(pot->hbox.p + s * 9, boxes[s], 9 * sizeof(double));
   }
   if (!box_changed) box_changed = memcmp(pot->last_boxes.data(), pot->hbox.p, S * 9 * sizeof(double)) != 0;
   if (box_changed) pot->last_boxes.assign(pot->hbox.p, pot->hbox.p + S * 9);
-  CU_TRY(pot, cudaMemcpyAsync(pot->dR.p, pot->hR.p, S * strideR * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  if (direct_in)  // straight from the caller's page-locked block, re-pitched to the 16-byte aligned device rows
+    CU_TRY(pot, cudaMemcpy2DAsync(pot->dR.p, strideR * sizeof(double), positions[0], D * sizeof(double), D * sizeof(double),
+                                  static_cast<size_t>(S), cudaMemcpyHostToDevice, pot->stream));
+  else
+    CU_TRY(pot, cudaMemcpyAsync(pot->dR.p, pot->hR.p, S * strideR * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
   CU_TRY(pot, cudaMemcpyAsync(pot->dZ.p, pot->hZ.p, S * N * sizeof(int), cudaMemcpyHostToDevice, pot->stream));
   CU_TRY(pot, cudaMemcpyAsync(pot->dbox.p, pot->hbox.p, S * 9 * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
   ForceBatchArgs a;
@@ -714,11 +762,15 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   a.force_rebuild = box_changed ? 1 : 0;
   int rc = run_force_batch(pot, pot->nl, a, pot->hbox.p, true);
   if (rc) return rc;
-  CU_TRY(pot, cudaMemcpyAsync(pot->hF.p, pot->dF.p, S * strideR * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+  if (direct_out)
+    CU_TRY(pot, cudaMemcpy2DAsync(forces[0], D * sizeof(double), pot->dF.p, strideR * sizeof(double), D * sizeof(double),
+                                  static_cast<size_t>(S), cudaMemcpyDeviceToHost, pot->stream));
+  else
+    CU_TRY(pot, cudaMemcpyAsync(pot->hF.p, pot->dF.p, S * strideR * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
   CU_TRY(pot, cudaMemcpyAsync(pot->hU.p, pot->dU.p, S * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
   CU_TRY(pot, cudaStreamSynchronize(pot->stream));
   for (long s = 0; s < S; s++) {
-    memcpy(forces[s], pot->hF.p + s * strideR, D * sizeof(double));
+    if (!direct_out) memcpy(forces[s], pot->hF.p + s * strideR, D * sizeof(double));
     energies[s] = pot->hU.p[s];
     if (variances) variances[s] = 0.0;
   }
@@ -1097,7 +1149,12 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
     CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
     NlBatch view = nl_view(pot, w->nl);
     CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
-    EONB200_LAUNCH(k_walkers, static_cast<unsigned>(W), threads, smem, pot->stream, pot->dP.p, view, wa, wl, w->prm.p);
+#ifndef EONB200_EMU
+    if (threads <= 448 && 2 * (smem + 17 * 1024) <= 220 * 1024 && W > pot->sm_count && pot->cfg.lpa_override != 99)
+      EONB200_LAUNCH(k_walkers_x2, static_cast<unsigned>(W), threads, smem, pot->stream, pot->dP.p, view, wa, wl, w->prm.p);
+    else
+#endif
+      EONB200_LAUNCH(k_walkers, static_cast<unsigned>(W), threads, smem, pot->stream, pot->dP.p, view, wa, wl, w->prm.p);
     CU_TRY(pot, cudaEventRecord(pot->ev[2], pot->stream));
     pot->launches += 1;
     CU_TRY(pot, cudaGetLastError());
@@ -1124,7 +1181,7 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
       }
       return 0;
     }
-    const int K = (static_cast<int>(need * 1.3) + 8 + 3) / 4 * 4;
+    const int K = (static_cast<int>(need * 1.3) + 8 + 7) / 8 * 8;
     w->nl.K = 0;
     rc = nl_alloc(pot, w->nl, W, N, K);
     if (rc) return rc;

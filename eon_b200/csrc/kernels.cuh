@@ -405,20 +405,17 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
 #pragma unroll
     for (int u = 0; u < kFilterBatch; u++) cur[u] = ld_cg(sys.nbr + static_cast<size_t>(u) * sys.Np + ifirst);
   }
+  phase_clock(clk, 11);
   {  // L2 prefetch behind the loads the prologue waits for, one 128-byte line per lane and instruction: the list's
-     // build positions, the atomic numbers, then this CTA's slice of the candidate rows (one line per warp of atoms)
+     // build positions and the atomic numbers (needed by the conversion below)
     for (int o = tid * 16; o < D; o += nt * 16) l2_prefetch_line(sys.rbuild + o);
     for (int o = tid * 32; o < N; o += nt * 32) l2_prefetch_line(sys.Z + o);
-    const int lines_per_row = w1 - w0;
-    const int kmax = a.kmax < sys.K ? a.kmax : sys.K;
-    const int nlines = (kmax - kFilterBatch) * lines_per_row;  // the first rows are being loaded into registers already
-    for (int q = tid; q < nlines; q += nt) {
-      const int k = kFilterBatch + q / lines_per_row, seg = q % lines_per_row;
-      l2_prefetch_line(sys.nbr + static_cast<size_t>(k) * sys.Np + i0 + 32 * seg);
-    }
   }
+  phase_clock(clk, 12);
   fill_sh27(sm, Lbox[0], Lbox[1], Lbox[2]);
+  phase_clock(clk, 13);
   __syncthreads();  // mbarrier initialised
+  phase_clock(clk, 14);
   if (aligned) {
     mbar_wait(sm.mbar, 0);
   } else {
@@ -428,6 +425,16 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   }
 
   phase_clock(clk, 3);
+  {  // ... and, once the positions have landed, this CTA's slice of the remaining candidate rows (one line per warp
+     // of atoms and row); the first kFilterBatch rows are in registers already
+    const int lines_per_row = w1 - w0;
+    const int kmax = a.kmax < sys.K ? a.kmax : sys.K;
+    const int nlines = (kmax - kFilterBatch) * lines_per_row;
+    for (int q = tid; q < nlines; q += nt) {
+      const int k = kFilterBatch + q / lines_per_row, seg = q % lines_per_row;
+      l2_prefetch_line(sys.nbr + static_cast<size_t>(k) * sys.Np + i0 + 32 * seg);
+    }
+  }
   // ---- raw coordinates -> wrapped positions (double + float), in place; Verlet displacement; element check ----
   // pos[i] overlaps only raw[i'] with i' <= i, so a round reads its atoms into registers, meets at a barrier and
   // then writes; later rounds read higher atoms only.
@@ -588,8 +595,8 @@ __device__ inline void setup_ctx(Ctx &c, const PotParams *Pp, const NlBatch &nl,
 }
 
 // Resident walkers: the whole job of a walker runs inside one CTA, start to finish.
-__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_walkers(const PotParams *__restrict__ Pp, NlBatch nl, WalkerArrays wa,
-                                                                  WalkerLaunch wl, const EonB200SearchParams *__restrict__ prm_g) {
+__device__ __forceinline__ void walkers_body(const PotParams *__restrict__ Pp, const NlBatch &nl, const WalkerArrays &wa,
+                                             const WalkerLaunch &wl, const EonB200SearchParams *__restrict__ prm_g) {
   EONB200_DYN_SMEM(smem_raw);
   __shared__ EonB200SearchParams prm_sh;
   __shared__ double cell_sh[19];
@@ -644,6 +651,20 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_walkers(const PotParam
     wa.convergence[w] = conv;
   }
 }
+
+__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_walkers(const PotParams *__restrict__ Pp, NlBatch nl, WalkerArrays wa,
+                                                                  WalkerLaunch wl, const EonB200SearchParams *__restrict__ prm_g) {
+  walkers_body(Pp, nl, wa, wl, prm_g);
+}
+
+#ifndef EONB200_EMU
+// Two walkers per SM: the search is a chain of short latency-bound steps (block reductions, vector updates out of
+// L2), so a second resident CTA hides more than the tighter register budget costs.
+__global__ void __launch_bounds__(448, 2) k_walkers_x2(const PotParams *__restrict__ Pp, NlBatch nl, WalkerArrays wa,
+                                                       WalkerLaunch wl, const EonB200SearchParams *__restrict__ prm_g) {
+  walkers_body(Pp, nl, wa, wl, prm_g);
+}
+#endif
 
 // Register-resident DFMA chain: the non-tensor FP64 roofline denominator.
 __global__ void k_dfma_peak(double *out, int iters) {

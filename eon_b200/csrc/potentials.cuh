@@ -594,6 +594,57 @@ __device__ __forceinline__ void eam_fast_force(const SysView &sys, const Smem &s
   F[3 * i + 2] = fz;
 }
 
+// Whole walker in one CTA (resident kernels): the same filter / density / force lane functions as the fused kernel,
+// thread-strided over the atoms; forces to sm.stage.  sm.pos holds the prepared positions.
+__device__ EONB200_NOINLINE double walker_forces_eam_fast(const PotParams &P, const EamRowDev *row, const SysView &sys, Smem sm) {
+  const int N = sys.N;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < N; i += nt) {
+    const double4 p = sm.pos[i];
+    sm.posf[i] = make_float4(static_cast<float>(p.x), static_cast<float>(p.y), static_cast<float>(p.z), 0.0f);
+  }
+  if (tid == 0) {  // the ghost atom the row padding points at
+    sm.pos[N] = make_double4(1e150, 1e150, 1e150, 0.0);
+    sm.posf[N] = make_float4(1e18f, 1e18f, 1e18f, 0.0f);
+  }
+  __syncthreads();
+  const Geom &g = *sm.geom;
+  const float rc2_hi = static_cast<float>(row->rc2) + eam_filter_band(fmax(fmax(g.H[0], g.H[4]), g.H[8]), row->r_cut);
+  const bool single = N <= nt;
+  double acc[2] = {0.0, 0.0};
+  EamLane L = {0.0, 0.0, 0.0, 0.0, 0};
+  for (int i = tid; i < N; i += nt) {
+    const int n = sys.cnt[i];
+    int cur[kFilterBatch];
+#pragma unroll
+    for (int u = 0; u < kFilterBatch; u++) cur[u] = sys.nbr[static_cast<size_t>(u) * sys.Np + i];
+    const int nin = eam_fast_filter(sys, sm, i, n, cur, rc2_hi);
+    eam_fast_density(P, row, sys, sm, i, nin, L, acc);
+    sm.pos[i].w = L.dfd;
+    if (!single) {
+      sm.stage[3 * i] = L.fx;
+      sm.stage[3 * i + 1] = L.fy;
+      sm.stage[3 * i + 2] = L.fz;
+      sys.dfd[i] = L.dfd;
+      sys.cnt2[i] = L.nin;
+    }
+  }
+  block_sum<2>(acc, sm.red);  // (barriers: every F'(rho) is in place)
+  for (int i = tid; i < N; i += nt) {
+    if (!single) {
+      L.fx = sm.stage[3 * i];
+      L.fy = sm.stage[3 * i + 1];
+      L.fz = sm.stage[3 * i + 2];
+      L.dfd = sys.dfd[i];
+      L.nin = sys.cnt2[i];
+    }
+    eam_fast_force(sys, sm, i, L, sm.stage);
+  }
+  __syncthreads();
+  if (tid == 0) atomicAdd(&sys.stats[2], static_cast<unsigned long long>(acc[1]));
+  return acc[0];
+}
+
 // Energy + raw forces (into sm.stage) of the whole walker staged in sm.pos -- the resident kernels' path.
 // Returns NaN if an element has no EAM row (the reference throws 14324, EAM.cpp:116-123).
 __device__ inline double walker_forces(const PotParams &P, const SysView &sys, Smem &sm, int lpa) {
@@ -607,6 +658,8 @@ __device__ inline double walker_forces(const PotParams &P, const SysView &sys, S
       return nan("");
     }
     const bool multi = (flags & 1) != 0;
+    if (!multi && sm.geom->tab_ok && P.eam_fast_ok && sm.posf != nullptr)
+      return walker_forces_eam_fast(P, &P.rows[sm.rowid[0]], sys, sm);
     if (multi)
       eam_pass1<true>(P, sys, sm, lpa, 0, N, sm.dfd, acc);
     else

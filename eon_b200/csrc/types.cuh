@@ -178,7 +178,8 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 __host__ __device__ inline size_t smem_bytes(int N, int maxCells) {
   size_t b = 0;
-  b += align_up(sizeof(double4) * N, 128);
+  b += align_up(sizeof(double4) * (N + 1), 128);
+  b += align_up(sizeof(float4) * (N + 1), 128) + sizeof(float4) * 28;
   b += align_up(sizeof(double) * 8 * kMaxWarps, 128);
   b += align_up(sizeof(double) * N, 128);
   b += align_up(sizeof(double) * (3 * static_cast<size_t>(N) + 2), 128);
@@ -291,7 +292,11 @@ __device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells) {
   Smem s;
   size_t o = 0;
   s.pos = reinterpret_cast<double4 *>(base + o);
-  o += align_up(sizeof(double4) * N, 128);
+  o += align_up(sizeof(double4) * (N + 1), 128);
+  s.posf = reinterpret_cast<float4 *>(base + o);
+  o += align_up(sizeof(float4) * (N + 1), 128);
+  s.sh27f = reinterpret_cast<float4 *>(base + o);
+  o += sizeof(float4) * 28;
   s.red = reinterpret_cast<double *>(base + o);
   o += align_up(sizeof(double) * 8 * kMaxWarps, 128);
   s.dfd = reinterpret_cast<double *>(base + o);
@@ -319,9 +324,7 @@ __device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells) {
   s.shy = s.shx + 16;
   s.shz = s.shy + 16;
   s.sh27 = reinterpret_cast<double4 *>(s.shz + 16);
-  s.sh27f = nullptr;
   s.clu = nullptr;
-  s.posf = nullptr;
   s.maxCells = maxCells;
   return s;
 }

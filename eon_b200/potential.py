@@ -92,12 +92,15 @@ class B200Potential:
             raise PotentialError(1, err.value.decode() or "eonb200_create failed")
         self.kind = int(kind)
         self.device = int(device)
+        self._pin = bool(cfg.pin_host_buffers)
+        self._pin_keepalive = []
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
             self._lib.eonb200_destroy(self._h)
             self._h = None
+            self._pin_keepalive = []
 
     def __del__(self):
         try:
@@ -163,11 +166,14 @@ class B200Potential:
         return U, F
 
     # -- Potential::forceBatch (include/eon/Potential.h:108-122) ---------------------------------
-    def forceBatch(self, nSystems: int, nAtoms: int, positions, atomicNrs, boxes):
+    def forceBatch(self, nSystems: int, nAtoms: int, positions, atomicNrs, boxes, out=None):
         """Evaluate nSystems systems of nAtoms atoms in one call.
 
         positions: [S][3N] (or [S][N][3]); atomicNrs: [S][N] or [N]; boxes: [S][9] or [9].
-        Returns (forces[S,N,3], energies[S], variances[S]).
+        Returns (forces[S,N,3], energies[S], variances[S]).  `out` = a C-contiguous float64 array of S * 3N
+        elements to receive the forces (the reference's callers own their force buffers too); with
+        ``pin_host_buffers=1`` contiguous position / force arrays are page-locked once and copied without staging,
+        and this object keeps them alive until it is closed.
         """
         S, N = int(nSystems), int(nAtoms)
         R = np.ascontiguousarray(positions, dtype=np.float64).reshape(S, 3 * N)
@@ -175,9 +181,18 @@ class B200Potential:
         Z = np.ascontiguousarray(np.broadcast_to(Z.reshape(-1, N), (S, N)))
         B = np.ascontiguousarray(boxes, dtype=np.float64)
         B = np.ascontiguousarray(np.broadcast_to(B.reshape(-1, 9), (S, 9)))
-        F = np.empty((S, 3 * N), dtype=np.float64)
+        if out is not None:
+            if out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"] or out.size != S * 3 * N:
+                raise ValueError("out must be a C-contiguous float64 array of nSystems * 3 * nAtoms elements")
+            F = out.reshape(S, 3 * N)
+        else:
+            F = np.empty((S, 3 * N), dtype=np.float64)
         U = np.empty(S, dtype=np.float64)
         V = np.empty(S, dtype=np.float64)
+        if self._pin:
+            for arr in (R, F):
+                if not any(arr is k for k in self._pin_keepalive):
+                    self._pin_keepalive.append(arr)
         # arrays of per-system pointers (the reference's `const double *const *`), built from base address + row stride
         pR, pZ, pF, pB = (_row_ptrs(R, C.c_double), _row_ptrs(Z, C.c_int), _row_ptrs(F, C.c_double),
                           _row_ptrs(B, C.c_double))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONB200_ABI_VERSION 1
+#define EONB200_ABI_VERSION 2
 
 #if defined(_WIN32)
 #define EONB200_API __declspec(dllexport)
@@ -68,6 +68,11 @@ typedef struct EonB200Config {
   int tiles_override;     /* CTAs per system in the stateless force passes, 0 -> chosen so that
                              nSystems x tiles covers the SMs a few times                       */
   int lpa_override;       /* lanes sharing one atom's neighbour row (1, 2, 4, 8), 0 -> automatic */
+  int pin_host_buffers;   /* 1: when the systems of a force_batch call lie back to back in host memory (positions[s]
+                             = positions[0] + s * 3N, same for forces), page-lock those ranges once
+                             (cudaHostRegister, cached per handle, released at destroy) and copy straight from / to
+                             them instead of staging through the handle's own pinned buffers.  The caller must keep
+                             such buffers allocated until eonb200_destroy.  0 (default): always stage.          */
 } EonB200Config;
 
 typedef struct EonB200Pot EonB200Pot; /* opaque */

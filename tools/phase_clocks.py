@@ -29,7 +29,31 @@ d = np.diff(cyc, axis=1) / 1.965e3  # us at 1965 MHz
 print("entry spread us: min %.1f med %.1f max %.1f" % (start_us.min(), np.median(start_us), start_us.max()))
 for k, nm in enumerate(names):
     print("%-12s med %.2f  p90 %.2f  max %.2f us" % (nm, np.median(d[:, k]), np.percentile(d[:, k], 90), d[:, k].max()))
+for a, b, nm in [(2, 11, "loads issued"), (11, 12, "prefetch issued"), (12, 13, "image table"), (13, 14, "barrier"), (14, 3, "tma wait")]:
+    dd = (c[:, b] - c[:, a]) / 1.965e3
+    print("  prologue %-16s med %.2f max %.2f us" % (nm, np.median(dd), dd.max()))
 tot = (cyc[:, -1] - cyc[:, 0]) / 1.965e3
 print("cta total med %.1f max %.1f; end time (start+total) max %.1f us" % (np.median(tot), tot.max(), (start_us + tot).max()))
 sm = c[:, 1].astype(int)
 print("ctas per SM: min %d max %d" % (np.bincount(sm).min(), np.bincount(sm).max()))
+
+# resident search: distribution of force calls per walker (critical path of the launch)
+if len(sys.argv) > 2:
+    from eon_b200 import Walkers, search_params, workloads as WL
+    s2, scale = bench.search_workload()
+    spot = B200Potential("eam", device=0, skin=1.0, conservative=True)
+    wk = Walkers(spot, s2.atomic_nrs, s2.fixed, s2.cell, np.broadcast_to(s2.positions.reshape(1, -1), (W, 3 * N)).copy())
+    wk.relax(search_params(opt_method=1, opt_converged_force=1e-4))
+    hmin = wk.harvest()
+    Rmin, E0 = hmin.positions[0], float(hmin.energies[0])
+    cfg = dict(WL.AKMC_AL)
+    R = np.empty((W, N, 3)); M = np.empty((W, N, 3))
+    for k in range(W):
+        R[k], M[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"], cfg["seed"] + k)
+    wk.set(positions=R, modes=M)
+    wk.saddle_search(search_params(**bench.SEARCH_PARAMS), E0)
+    h = wk.harvest(geometry=False)
+    fc = np.sort(h.force_calls)
+    print("search ms %.1f; force calls per walker: min %d med %d p90 %d max %d sum %d; iterations max %d" % (
+        wk.last_ms, fc[0], fc[len(fc) // 2], fc[int(0.9 * len(fc))], fc[-1], fc.sum(), h.iterations.max()))
+    print("us per force call on the critical path: %.1f" % (1e3 * wk.last_ms / fc[-1]))
