@@ -334,8 +334,9 @@ def run_b200(args):
     assert np.allclose(e_U, d_U.cpu().numpy(), rtol=0.0, atol=1e-8), "e2e energies differ from the device-resident run"
     epot.close()
     e2e_value = units / e2e_s
-    h2d = W * (3 * N * 8 + (3 * N % 2) * 8 + N * 4 + 72)
-    d2h = W * (3 * N * 8 + (3 * N % 2) * 8 + 8)
+    # bytes the call moves: positions in (one shared topology row and box), forces + energies + list flags out
+    h2d = W * 3 * N * 8 + N * 4 + 72
+    d2h = W * 3 * N * 8 + W * 8 + 36
 
     # roofline of the dominant kernel (k_force_batch): algorithmic flops / measured kernel time
     ms_kernel = dev_ms / args.steps

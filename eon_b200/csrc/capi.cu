@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -413,7 +414,8 @@ bool pin_range(EonB200Pot *pot, const void *p, size_t bytes) {
 
 // Launch the batched force evaluation on device-resident arrays; handles truncated lists by
 // regrowing the row capacity and re-running.  Synchronises when it has to look at the flags.
-int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double *h_box0, bool sync_and_check) {
+int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double *h_box0, bool sync_and_check,
+                    const std::function<int()> &enqueue_readback = nullptr) {
   const long S = a.S, N = a.N;
   if (nl.S < S || nl.N != N || nl.K == 0) {
     double unit[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -490,6 +492,10 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     CU_TRY(pot, cudaGetLastError());
     pot->force_calls += static_cast<unsigned long long>(S);
     if (!sync_and_check) return 0;
+    if (enqueue_readback) {  // results follow the kernel without a host round trip; a truncated list re-runs everything
+      const int rb = enqueue_readback();
+      if (rb) return rb;
+    }
     CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
     CU_TRY(pot, cudaMemcpyAsync(pot->h_stats.p, pot->d_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                 pot->stream));
@@ -705,9 +711,16 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   if (S <= 0 || N <= 0) return fail(pot, 2, "force_batch: nSystems and nAtoms must be positive");
   if (N > kNbrIndexMask) return fail(pot, 2, "force_batch: more than %d atoms per system", kNbrIndexMask);
   CU_TRY(pot, cudaSetDevice(pot->device));
+  // one topology / one box shared by all systems (the same pointer in every slot): keep a single copy
+  bool same_Z = true, same_box = true;
+  for (long s = 1; s < S; s++) {
+    same_Z = same_Z && atomicNrs[s] == atomicNrs[0];
+    same_box = same_box && boxes[s] == boxes[0];
+  }
+  const long SZ = same_Z ? 1 : S, SB = same_box ? 1 : S;
   // unknown element -> 14324 (EAM.cpp:116-123)
   if (pot->cfg.kind == EONB200_POT_EAM) {
-    for (long s = 0; s < S; s++)
+    for (long s = 0; s < SZ; s++)
       for (long i = 0; i < N; i++) {
         const int z = atomicNrs[s][i];
         bool found = false;
@@ -727,7 +740,7 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   CU_TRY(pot, pot->hU.reserve(S));
   CU_TRY(pot, pot->hbox.reserve(S * 9));
   CU_TRY(pot, pot->hZ.reserve(S * N));
-  bool box_changed = pot->last_boxes.size() != static_cast<size_t>(S) * 9;
+  bool box_changed = pot->last_boxes.size() != static_cast<size_t>(SB) * 9;
   const bool direct_in = rows_contiguous(positions, S, D) && pin_range(pot, positions[0], S * D * sizeof(double));
   const bool direct_out = rows_contiguous(forces, S, D) && pin_range(pot, forces[0], S * D * sizeof(double));
   for (long s = 0; s < S; s++) {
@@ -735,18 +748,18 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
       memcpy(pot->hR.p + s * strideR, positions[s], D * sizeof(double));
       if (strideR > D) pot->hR.p[s * strideR + D] = 0.0;
     }
-    memcpy(pot->hZ.p + s * N, atomicNrs[s], N * sizeof(int));
-    memcpy(pot->hbox.p + s * 9, boxes[s], 9 * sizeof(double));
+    if (s < SZ) memcpy(pot->hZ.p + s * N, atomicNrs[s], N * sizeof(int));
+    if (s < SB) memcpy(pot->hbox.p + s * 9, boxes[s], 9 * sizeof(double));
   }
-  if (!box_changed) box_changed = memcmp(pot->last_boxes.data(), pot->hbox.p, S * 9 * sizeof(double)) != 0;
-  if (box_changed) pot->last_boxes.assign(pot->hbox.p, pot->hbox.p + S * 9);
+  if (!box_changed) box_changed = memcmp(pot->last_boxes.data(), pot->hbox.p, SB * 9 * sizeof(double)) != 0;
+  if (box_changed) pot->last_boxes.assign(pot->hbox.p, pot->hbox.p + SB * 9);
   if (direct_in)  // straight from the caller's page-locked block, re-pitched to the 16-byte aligned device rows
     CU_TRY(pot, cudaMemcpy2DAsync(pot->dR.p, strideR * sizeof(double), positions[0], D * sizeof(double), D * sizeof(double),
                                   static_cast<size_t>(S), cudaMemcpyHostToDevice, pot->stream));
   else
     CU_TRY(pot, cudaMemcpyAsync(pot->dR.p, pot->hR.p, S * strideR * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
-  CU_TRY(pot, cudaMemcpyAsync(pot->dZ.p, pot->hZ.p, S * N * sizeof(int), cudaMemcpyHostToDevice, pot->stream));
-  CU_TRY(pot, cudaMemcpyAsync(pot->dbox.p, pot->hbox.p, S * 9 * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->dZ.p, pot->hZ.p, SZ * N * sizeof(int), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->dbox.p, pot->hbox.p, SB * 9 * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
   ForceBatchArgs a;
   memset(&a, 0, sizeof(a));
   a.S = static_cast<int>(S);
@@ -754,21 +767,23 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   a.R = pot->dR.p;
   a.strideR = static_cast<int>(strideR);
   a.Z = pot->dZ.p;
-  a.strideZ = static_cast<int>(N);
+  a.strideZ = same_Z ? 0 : static_cast<int>(N);
   a.box = pot->dbox.p;
-  a.strideBox = 9;
+  a.strideBox = same_box ? 0 : 9;
   a.F = pot->dF.p;
   a.U = pot->dU.p;
   a.force_rebuild = box_changed ? 1 : 0;
-  int rc = run_force_batch(pot, pot->nl, a, pot->hbox.p, true);
+  auto readback = [&]() -> int {
+    if (direct_out)
+      CU_TRY(pot, cudaMemcpy2DAsync(forces[0], D * sizeof(double), pot->dF.p, strideR * sizeof(double), D * sizeof(double),
+                                    static_cast<size_t>(S), cudaMemcpyDeviceToHost, pot->stream));
+    else
+      CU_TRY(pot, cudaMemcpyAsync(pot->hF.p, pot->dF.p, S * strideR * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+    CU_TRY(pot, cudaMemcpyAsync(pot->hU.p, pot->dU.p, S * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+    return 0;
+  };
+  int rc = run_force_batch(pot, pot->nl, a, pot->hbox.p, true, readback);
   if (rc) return rc;
-  if (direct_out)
-    CU_TRY(pot, cudaMemcpy2DAsync(forces[0], D * sizeof(double), pot->dF.p, strideR * sizeof(double), D * sizeof(double),
-                                  static_cast<size_t>(S), cudaMemcpyDeviceToHost, pot->stream));
-  else
-    CU_TRY(pot, cudaMemcpyAsync(pot->hF.p, pot->dF.p, S * strideR * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
-  CU_TRY(pot, cudaMemcpyAsync(pot->hU.p, pot->dU.p, S * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
-  CU_TRY(pot, cudaStreamSynchronize(pot->stream));
   for (long s = 0; s < S; s++) {
     if (!direct_out) memcpy(forces[s], pot->hF.p + s * strideR, D * sizeof(double));
     energies[s] = pot->hU.p[s];

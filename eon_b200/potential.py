@@ -36,12 +36,16 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
-def _row_ptrs(a: np.ndarray, ctype):
-    """`ctype **` over the rows of a C-contiguous 2-D array, without a Python loop over the rows."""
-    addr = a.ctypes.data + np.arange(a.shape[0], dtype=np.uint64) * np.uint64(a.strides[0])
+def _row_ptrs(a: np.ndarray, ctype, n: int = 0):
+    """`ctype **` over the rows of a C-contiguous 2-D array, without a Python loop over the rows.  A one-row array
+    with n > 1 yields n copies of that row's address (a value shared by all systems)."""
+    if n > 1 and a.shape[0] == 1:
+        addr = np.full(n, a.ctypes.data, dtype=np.uint64)
+    else:
+        addr = a.ctypes.data + np.arange(a.shape[0], dtype=np.uint64) * np.uint64(a.strides[0])
     addr = np.ascontiguousarray(addr, dtype=np.uint64)
     p = addr.ctypes.data_as(C.POINTER(C.POINTER(ctype)))
-    p._keepalive = addr
+    p._keepalive = (addr, a)
     return p
 
 
@@ -177,10 +181,11 @@ class B200Potential:
         """
         S, N = int(nSystems), int(nAtoms)
         R = np.ascontiguousarray(positions, dtype=np.float64).reshape(S, 3 * N)
-        Z = np.ascontiguousarray(atomicNrs, dtype=np.int32)
-        Z = np.ascontiguousarray(np.broadcast_to(Z.reshape(-1, N), (S, N)))
-        B = np.ascontiguousarray(boxes, dtype=np.float64)
-        B = np.ascontiguousarray(np.broadcast_to(B.reshape(-1, 9), (S, 9)))
+        # one topology / one box for all systems: every slot of the pointer array names the same row
+        Z = np.ascontiguousarray(atomicNrs, dtype=np.int32).reshape(-1, N)
+        B = np.ascontiguousarray(boxes, dtype=np.float64).reshape(-1, 9)
+        if Z.shape[0] not in (1, S) or B.shape[0] not in (1, S):
+            raise ValueError("atomicNrs / boxes must describe one system or nSystems systems")
         if out is not None:
             if out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"] or out.size != S * 3 * N:
                 raise ValueError("out must be a C-contiguous float64 array of nSystems * 3 * nAtoms elements")
@@ -194,8 +199,8 @@ class B200Potential:
                 if not any(arr is k for k in self._pin_keepalive):
                     self._pin_keepalive.append(arr)
         # arrays of per-system pointers (the reference's `const double *const *`), built from base address + row stride
-        pR, pZ, pF, pB = (_row_ptrs(R, C.c_double), _row_ptrs(Z, C.c_int), _row_ptrs(F, C.c_double),
-                          _row_ptrs(B, C.c_double))
+        pR, pZ, pF, pB = (_row_ptrs(R, C.c_double), _row_ptrs(Z, C.c_int, S), _row_ptrs(F, C.c_double),
+                          _row_ptrs(B, C.c_double, S))
         self._check(self._lib.eonb200_force_batch(self._h, S, N, pR, pZ, pF, _dp(U), _dp(V), pB))
         return F.reshape(S, N, 3), U, V
 

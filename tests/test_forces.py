@@ -182,3 +182,63 @@ def test_even_and_odd_atom_counts(backend, oracle):
             F, U, _ = pot.forceBatch(3, n, np.stack([R] * 3).reshape(3, -1), Z, d["cell"])
             for s in range(3):
                 assert_parity(F[s], U[s], F0, U0)
+
+
+@pytest.mark.parametrize("kw", [dict(tiles_override=1, threads_per_walker=64),   # several atoms per thread, one CTA
+                                dict(tiles_override=2, threads_per_walker=32),   # ... in a two-CTA cluster
+                                dict(tiles_override=4), dict(tiles_override=8)])  # one atom per thread, wide clusters
+def test_fused_eam_launch_shapes(backend, oracle, kw):
+    """Every shape of the fused EAM kernel (cluster size, atoms per thread) gives the oracle's forces, with a fresh
+    list, a reused list and a list rebuilt inside the kernel after a large displacement."""
+    from eon_b200 import workloads as WL
+    s = WL.load_structure("akmc_al.json")
+    opot = oracle.potential(oracle.POT_EAM)
+    R = WL.jitter(s.positions, 3, 0.04, seed=11)
+    R[2] += 0.9  # beyond skin / 2: in-kernel rebuild; the rigid shift also moves atoms across the cell faces
+    with B200Potential("eam", lib=backend, skin=1.0, **kw) as pot:
+        for w in (0, 1, 2, 1):
+            F, U, _ = pot.forceBatch(2, s.n_atoms, np.stack([R[w], R[0]]).reshape(2, -1), s.atomic_nrs, s.cell.reshape(9))
+            for k, ww in enumerate((w, 0)):
+                U0, F0 = oracle.force(opot, R[ww], s.atomic_nrs, s.cell)
+                assert_parity(F[k], U[k], F0, U0)
+
+
+def test_caller_owned_pinned_buffers(backend, oracle):
+    """pin_host_buffers + out=: the page-locked direct path returns what the staged path returns, bit for bit."""
+    from eon_b200 import workloads as WL
+    s = WL.load_structure("akmc_al.json")
+    R = np.ascontiguousarray(WL.jitter(s.positions, 5, 0.05, seed=3).reshape(5, -1))
+    with B200Potential("eam", lib=backend) as pot:
+        F0, U0, _ = pot.forceBatch(5, s.n_atoms, R, s.atomic_nrs, s.cell.reshape(9))
+    out = np.full((5, 3 * s.n_atoms), np.nan)
+    with B200Potential("eam", lib=backend, pin_host_buffers=1) as pot:
+        for _ in range(2):  # second call: ranges already registered
+            F1, U1, _ = pot.forceBatch(5, s.n_atoms, R, s.atomic_nrs, s.cell.reshape(9), out=out)
+            assert F1.base is out or np.shares_memory(F1, out)
+            assert np.array_equal(F1.reshape(5, -1), F0.reshape(5, -1)) and np.array_equal(U1, U0)
+        # per-system topologies and boxes still work next to the shared-row shortcut
+        Zs = np.tile(s.atomic_nrs, (5, 1))
+        Bs = np.tile(s.cell.reshape(9), (5, 1))
+        F2, U2, _ = pot.forceBatch(5, s.n_atoms, R, Zs, Bs)
+        assert np.array_equal(F2.reshape(5, -1), F0.reshape(5, -1)) and np.array_equal(U2, U0)
+    with pytest.raises(ValueError):
+        with B200Potential("eam", lib=backend) as pot:
+            pot.forceBatch(5, s.n_atoms, R, s.atomic_nrs, s.cell.reshape(9), out=np.zeros(7))
+
+
+@pytest.mark.gpu
+def test_measurement_aids(cuda_backend):
+    """eonb200_l2_flush and eonb200_phase_clocks: per-CTA clocks are monotonic through the phases."""
+    from eon_b200 import workloads as WL
+    s = WL.load_structure("akmc_al.json")
+    R = WL.jitter(s.positions, 8, 0.05, seed=5).reshape(8, -1)
+    with B200Potential("eam", lib=cuda_backend) as pot:
+        pot.forceBatch(8, s.n_atoms, R, s.atomic_nrs, s.cell.reshape(9))
+        pot.phase_clocks(True)
+        pot.l2_flush(64 << 20)
+        pot.forceBatch(8, s.n_atoms, R, s.atomic_nrs, s.cell.reshape(9))
+        c = pot.phase_clocks(False)
+        assert c.shape[0] >= 8 and c.shape[1] == 16
+        cyc = c[:, 2:11]
+        assert (np.diff(cyc[:, [0, 1, 2, 4, 5, 6, 7]], axis=1) >= 0).all()
+        assert (c[:, 1] >= 0).all() and (c[:, 1] < 1024).all()
