@@ -40,6 +40,10 @@ N_WALKERS = 256
 JITTER = 0.05
 N_POSITION_SETS = 4
 FLUSH_BYTES = 512 << 20  # > 4x the 126 MB L2
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_eam_fused launch of this workload (ncu --set full capture)
+NCU_DRAM_BYTES_PER_LAUNCH = 97.2e6
+NCU_TRAFFIC_SOURCE = ("profiles/r1c_fused_ncu_raw_selected.csv: 47.0 MB read + 50.2 MB written per launch (cold L2); "
+                      "algorithmic minimum 64 N + 8 P_o = 33.7 MB")
 SEARCH_ROW_Z = 79  # the in-tree Au row: see DESIGN.md "Search workload"
 A0_AU = 4.092320738309691  # equilibrium fcc lattice constant of the in-tree EAM Au row (oracle)
 
@@ -106,6 +110,16 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_config(n_atoms: int, world: int, skin: float, rebuilt: int) -> dict:
+    """The `config` both arms print (the reference arm times the same walkers on the host cores)."""
+    return {"workload": "examples/akmc-al: 385 Al atoms (128 fixed), in-tree EAM Al row, "
+                        f"{N_WALKERS} walkers per GPU, jitter U(-{JITTER},{JITTER}) A, {N_POSITION_SETS} position sets",
+            "walkers_per_gpu": N_WALKERS, "n_atoms": n_atoms,
+            "l2": "flushed before every step (512 MiB memset queued on the same stream, outside the events)",
+            "neighbour_list": f"Verlet skin {skin} A, cached; lists rebuilt inside the timed region: {rebuilt}",
+            "parallelism": f"walker-sharded x{world}, no collective"}
 
 
 def dist_env():
@@ -186,8 +200,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "atom-force-evals/sec", "value": value, "unit": "atom-force-evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "examples/akmc-al (385 Al atoms, in-tree EAM Al row), bounded sample per step",
-                       "walkers_per_gpu": N_WALKERS, "n_atoms": struct.n_atoms},
+            "config": dict(workload_config(struct.n_atoms, max(1, world), args.skin, 0),
+                           reference_arm="EAM.cpp of the reference tree on the host cores, bounded sample of the same "
+                                         "walkers per step (no device, no lists)"),
             "cpu_baseline": dict(info, value=value),
             "e2e": {"value": value, "unit": "atom-force-evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -351,8 +366,9 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     hbm_achieved = eam_min_bytes(pairs_per_step, W * N) / (ms_kernel * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "kernel": "k_eam_pass1 + k_eam_pass2 (+ k_prepare)", "achieved": achieved, "peak": fp64_peak / 1e12,
-                "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": None,
+    roofline = {"bound": "fp64", "kernel": "k_eam_fused (one launch per step: prologue, filter, density, force)", "achieved": achieved, "peak": fp64_peak / 1e12,
+                "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                "traffic_source": NCU_TRAFFIC_SOURCE,
                 "peak_source": "DFMA microbenchmark k_dfma_peak measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
                 "algorithmic_flops_per_launch": flops, "ordered_pairs_per_launch": pairs_per_step,
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
@@ -426,11 +442,7 @@ def run_b200(args):
         line = {"metric": "atom-force-evals/sec", "value": value, "unit": "atom-force-evals/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": dev_ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "examples/akmc-al: 385 Al atoms (128 fixed), in-tree EAM Al row, "
-                                       f"{W} walkers per GPU, jitter U(-{JITTER},{JITTER}) A, {N_POSITION_SETS} position sets",
-                           "walkers_per_gpu": W, "n_atoms": N, "l2": "flushed before every step (512 MiB memset queued on the same stream, outside the events)",
-                           "neighbour_list": f"Verlet skin {args.skin} A, cached; lists rebuilt inside the timed region: {rebuilt}",
-                           "parallelism": f"walker-sharded x{world}, no collective"},
+                "config": workload_config(N, world, args.skin, rebuilt),
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "atom-force-evals/s", "h2d_bytes_per_step": h2d,
                                           "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
                 "gpu_launches": int(launches), "roofline": roofline,

@@ -1128,6 +1128,14 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
   size_t smem;
   rc = check_smem(pot, N, wl.maxCells, &smem);
   if (rc) return rc;
+  wl.fast_smem = 0;
+  if (pot->cfg.kind == EONB200_POT_EAM) {
+    const size_t with_fast = smem_bytes(static_cast<int>(N), wl.maxCells, true);
+    if (static_cast<long>(with_fast) <= pot->max_dyn_smem) {
+      smem = with_fast;
+      wl.fast_smem = 1;
+    }
+  }
   WalkerArrays wa;
   memset(&wa, 0, sizeof(wa));
   wa.W = static_cast<int>(W);

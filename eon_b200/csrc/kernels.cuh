@@ -560,6 +560,7 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_neighbors(NlBatch nl, 
 
 struct WalkerLaunch {
   int maxCells, lpa;
+  int fast_smem;  // the dynamic shared memory has room for the fast EAM lane functions' arrays
   int job;  // 0 = Matter forces only, 1 = saddle search, 2 = relax, 3 = displace along mode, 4 = list probe
   int remove_net_force;
   double scalar;  // displacement for job 3
@@ -602,7 +603,7 @@ __device__ __forceinline__ void walkers_body(const PotParams *__restrict__ Pp, c
   __shared__ double cell_sh[19];
   const int w = blockIdx.x;
   if (w >= wa.W) return;
-  Smem sm = carve_smem(smem_raw, wa.N, wl.maxCells);
+  Smem sm = carve_smem(smem_raw, wa.N, wl.maxCells, wl.fast_smem != 0);
   if (threadIdx.x == 0) {
     mbar_init(sm.mbar, 1);
     prm_sh = *prm_g;

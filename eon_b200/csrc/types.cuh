@@ -176,10 +176,12 @@ struct Smem {
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__host__ __device__ inline size_t smem_bytes(int N, int maxCells) {
+// `fast`: also room for the single-precision copies the fast EAM lane functions filter with -- only the resident
+// walker kernel asks for it, and only when it fits.
+__host__ __device__ inline size_t smem_bytes(int N, int maxCells, bool fast = false) {
   size_t b = 0;
   b += align_up(sizeof(double4) * (N + 1), 128);
-  b += align_up(sizeof(float4) * (N + 1), 128) + sizeof(float4) * 28;
+  if (fast) b += align_up(sizeof(float4) * (N + 1), 128) + sizeof(float4) * 28;
   b += align_up(sizeof(double) * 8 * kMaxWarps, 128);
   b += align_up(sizeof(double) * N, 128);
   b += align_up(sizeof(double) * (3 * static_cast<size_t>(N) + 2), 128);
@@ -288,15 +290,19 @@ __device__ inline Smem carve_smem_fused(unsigned char *base, int N, int maxCells
   return s;
 }
 
-__device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells) {
+__device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells, bool fast = false) {
   Smem s;
   size_t o = 0;
   s.pos = reinterpret_cast<double4 *>(base + o);
   o += align_up(sizeof(double4) * (N + 1), 128);
-  s.posf = reinterpret_cast<float4 *>(base + o);
-  o += align_up(sizeof(float4) * (N + 1), 128);
-  s.sh27f = reinterpret_cast<float4 *>(base + o);
-  o += sizeof(float4) * 28;
+  s.posf = nullptr;
+  s.sh27f = nullptr;
+  if (fast) {
+    s.posf = reinterpret_cast<float4 *>(base + o);
+    o += align_up(sizeof(float4) * (N + 1), 128);
+    s.sh27f = reinterpret_cast<float4 *>(base + o);
+    o += sizeof(float4) * 28;
+  }
   s.red = reinterpret_cast<double *>(base + o);
   o += align_up(sizeof(double) * 8 * kMaxWarps, 128);
   s.dfd = reinterpret_cast<double *>(base + o);
