@@ -434,6 +434,45 @@ def run_b200(args):
         wk4.close()
         spot.close()
 
+    # BASELINE.json configs[2] as a second data point: 4096 walkers of the 2047-atom vacancy cell sharded over the
+    # ranks (the reference has no Cu EAM row -- SURVEY.md section 7 -- so the Al row runs on the Cu lattice, n = 54)
+    c3 = None
+    if not args.no_c3:
+        s3 = WL.fcc_vacancy(8, 3.615, 13)
+        N3 = s3.n_atoms
+        lo3, hi3 = sharding.shard_range(4096, rank, world)
+        W3 = hi3 - lo3
+        sets3 = [torch.from_numpy(WL.jitter(s3.positions, W3, JITTER, seed=7000 * k + lo3).reshape(W3, 3 * N3)).to(dev)
+                 for k in range(2)]
+        d_Z3 = torch.from_numpy(np.broadcast_to(s3.atomic_nrs, (W3, N3)).copy()).to(dev)
+        d_box3 = torch.from_numpy(np.broadcast_to(s3.cell.reshape(9), (W3, 9)).copy()).to(dev)
+        d_F3 = torch.empty((W3, 3 * N3), dtype=torch.float64, device=dev)
+        d_U3 = torch.empty((W3,), dtype=torch.float64, device=dev)
+        pot3 = B200Potential("eam", device=local_rank, skin=args.skin)
+
+        def step3(k):
+            pot3.forceBatchDevice(W3, N3, sets3[k % 2].data_ptr(), d_Z3.data_ptr(), d_F3.data_ptr(), d_U3.data_ptr(),
+                                  d_box3.data_ptr(), sync=True)
+            return sum(pot3.last_force_ms())
+
+        for k in range(3):
+            step3(k)
+        pairs3 = float(pot3.nl_stats()["ordered_pairs"])
+        barrier()
+        ms3 = 0.0
+        n3 = 5
+        for k in range(n3):
+            pot3.l2_flush(FLUSH_BYTES)
+            ms3 += step3(k)
+        ms3 = reduce_max(ms3) / n3
+        flops3 = reduce_sum(eam_flops(pairs3, W3 * N3))
+        c3 = {"workload": "fcc 8x8x8 vacancy cell, 2047 atoms, a = 3.615 A, in-tree EAM Al row, 4096 walkers over all ranks",
+              "walkers": 4096, "n_atoms": N3, "ms_per_step": ms3, "atom_force_evals_per_s": 4096.0 * N3 / (ms3 * 1e-3),
+              "tflops": flops3 / (ms3 * 1e-3) / 1e12,
+              "fp64_roofline_frac": flops3 / (ms3 * 1e-3) / (fp64_peak * world) if fp64_peak > 0 else None}
+        pot3.close()
+        del sets3, d_Z3, d_box3, d_F3, d_U3
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _, _ = cpu_force_baseline(struct, sets[0], 1.0, True)
@@ -448,7 +487,7 @@ def run_b200(args):
                 "gpu_launches": int(launches), "roofline": roofline,
                 "extra": {"wall_s_timed_region": t_wall, "value_hot_l2": units / world / (t_hot * 1e-3),
                           "value_fresh_list_every_step": units / world / (t_fresh * 1e-3),
-                          "fp64_peak_tflops_measured": fp64_peak / 1e12},
+                          "fp64_peak_tflops_measured": fp64_peak / 1e12, "c3": c3},
                 "search": search}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -469,6 +508,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=0, help="CTAs per walker in the force passes (0 = automatic)")
     ap.add_argument("--lpa", type=int, default=0, help="lanes per atom (0 = automatic)")
     ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the 4096 x 2047-atom data point")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -477,6 +477,8 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
         EONB200_LAUNCH_CLUSTER((k_eam_fused_t<224, 4>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
       else if (fused_threads <= 448)
         EONB200_LAUNCH_CLUSTER((k_eam_fused_t<448, 2>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+      else if (2 * (fused_smem + 1024) <= 227 * 1024)
+        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<512, 2>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
       else
         EONB200_LAUNCH_CLUSTER((k_eam_fused_t<512, 1>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
 #endif
@@ -640,6 +642,8 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<448, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<512, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
 #endif
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_pair), cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1173,7 +1177,7 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
     NlBatch view = nl_view(pot, w->nl);
     CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
 #ifndef EONB200_EMU
-    if (threads <= 448 && 2 * (smem + 17 * 1024) <= 220 * 1024 && W > pot->sm_count && pot->cfg.lpa_override != 99)
+    if (threads <= 448 && 2 * (smem + 17 * 1024) <= 220 * 1024 && W > pot->sm_count)
       EONB200_LAUNCH(k_walkers_x2, static_cast<unsigned>(W), threads, smem, pot->stream, pot->dP.p, view, wa, wl, w->prm.p);
     else
 #endif

@@ -242,3 +242,22 @@ def test_measurement_aids(cuda_backend):
         cyc = c[:, 2:11]
         assert (np.diff(cyc[:, [0, 1, 2, 4, 5, 6, 7]], axis=1) >= 0).all()
         assert (c[:, 1] >= 0).all() and (c[:, 1] < 1024).all()
+
+
+def test_c3_sized_cell(backend, oracle):
+    """BASELINE.json configs[2] geometry: fcc 8 x 8 x 8 with a vacancy (2047 atoms, a = 3.615 A, 54 neighbours inside
+    the EAM cutoff), jittered walkers, against the oracle -- the shape where a walker spans several CTAs with one
+    atom per thread of 512-thread CTAs.  Plus a size-independent property: with F = -grad U the net force vanishes."""
+    from eon_b200 import workloads as WL
+    s = WL.fcc_vacancy(8, 3.615, 13)
+    R = WL.jitter(s.positions, 2, 0.05, seed=21)
+    opot = oracle.potential(oracle.POT_EAM_NL)
+    with B200Potential("eam", lib=backend) as pot:
+        F, U, _ = pot.forceBatch(2, s.n_atoms, R.reshape(2, -1), s.atomic_nrs, s.cell.reshape(9))
+        for w in range(2):
+            U0, F0 = oracle.force(opot, R[w], s.atomic_nrs, s.cell)
+            assert_parity(F[w], U[w], F0, U0)
+        assert pot.nl_stats()["ordered_pairs"] > 2 * 2047 * 50
+    with B200Potential("eam", lib=backend, conservative=True) as pot:
+        F, U, _ = pot.forceBatch(2, s.n_atoms, R.reshape(2, -1), s.atomic_nrs, s.cell.reshape(9))
+        assert np.abs(F.sum(axis=1)).max() < 1e-9 * np.abs(F).max() * s.n_atoms
