@@ -63,7 +63,7 @@ struct PinBuf {
 };
 
 struct NlStore {
-  DevBuf<int> nbr, cnt, state, flags, done, nbr2, cnt2, cellscratch;
+  DevBuf<int> nbr, cnt, state, flags, done, nbr2, cnt2, cls, cellscratch;
   int scratch_stride = 0;
   int rowmax_seen = 0;  // largest row fill any build of this store reported (rows worth prefetching)
   DevBuf<double> rbuild, pairA, pairB, dfd, upart;
@@ -285,9 +285,11 @@ void pick_fused(const EonB200Pot *pot, long S, long N, int *T_out, int *threads_
   } else if (S * Wn < 4L * pot->sm_count) {
     T = Wn;
   } else {
-    // two CTAs per walker: with the 72-register budget four 224-thread CTAs (or two 448-thread ones) share an SM, so a
-    // few hundred walkers are all resident in one round; clusters of four no longer pack into the GPCs that way
-    T = Wn >= 8 ? 2 : 1;
+    // the fewest CTAs per walker that stay within 448 threads: under the 72-register budget two such CTAs (or four
+    // of 224 threads) share an SM, so a few hundred walkers are all resident in one round, and the prologue (whole-
+    // walker staging, Verlet check) is replicated as little as possible.  Measured on 256 x 385 atoms: one CTA per
+    // walker 79 us, two 81 us, four 108 us (clusters of four no longer pack into the GPCs in one round).
+    T = (Wn + 13) / 14;
   }
   if (pot->cfg.tiles_override > 0) T = pot->cfg.tiles_override;
   T = std::max<long>(std::max<long>(T, Tmin), 1);
@@ -333,6 +335,7 @@ int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K) {
     CU_TRY(pot, nl.pairB.reserve(static_cast<size_t>(S) * K * Np));
     CU_TRY(pot, nl.nbr2.reserve(static_cast<size_t>(S) * K * Np));
     CU_TRY(pot, nl.cnt2.reserve(static_cast<size_t>(S) * Np));
+    CU_TRY(pot, nl.cls.reserve(static_cast<size_t>(S) * Np));
     nl.scratch_stride = static_cast<int>(fused_scratch_ints(static_cast<int>(N), pick_max_cells(N)));
     CU_TRY(pot, nl.cellscratch.reserve(static_cast<size_t>(S) * nl.scratch_stride));
   }
@@ -361,6 +364,7 @@ NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
   b.pairB = nl.pairB.p;
   b.nbr2 = nl.nbr2.p;
   b.cnt2 = nl.cnt2.p;
+  b.cls = nl.cls.p;
   b.cellscratch = nl.cellscratch.p;
   b.scratch_stride = nl.scratch_stride;
   b.pos4 = nl.pos4.p;
@@ -851,6 +855,9 @@ int eonb200_neighbors(EonB200Pot *pot, long S, long N, const double *positions, 
   np.mode = NL_VESIN;
   np.rc = cutoff;
   np.rc2 = cutoff * cutoff;
+  np.rc_core2 = np.rc2;
+  np.rc_core = cutoff;
+  np.dstar = 0.0;
   np.skin = 0.0;
   for (int k = 0; k < 3; k++) np.per[k] = periodic ? (periodic[k] != 0) : 1;
   NlStore nl;

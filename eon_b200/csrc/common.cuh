@@ -27,6 +27,11 @@ constexpr int kMaxWarps = 32;
 constexpr double kPi = 3.14159265358979323846;
 constexpr double kSafeEps = 1e-300;  // include/eon/SafeMath.h:19
 
+// Branch hints: the rarely taken blocks of the hot kernels are laid out behind the hot instruction stream
+// (instruction caches are cold at every launch; each jump over an inline cold block costs a fetch round trip).
+#define EONB200_UNLIKELY(x) (__builtin_expect(!!(x), 0))
+#define EONB200_LIKELY(x) (__builtin_expect(!!(x), 1))
+
 #ifdef EONB200_EMU
 #define EONB200_NOINLINE __attribute__((noinline))
 #else

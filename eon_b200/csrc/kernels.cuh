@@ -39,6 +39,8 @@ __device__ inline NlParams make_nl_params(const PotParams &P) {
   np.rc = P.rc_list;
   np.rc2 = P.rc_list2;
   np.rc_core2 = P.cutoff2;
+  np.rc_core = P.cutoff;
+  np.dstar = 0.25 * P.skin;
   np.skin = P.skin;
   np.per[0] = np.per[1] = np.per[2] = 1;
   return np;
@@ -188,25 +190,29 @@ struct FusedFast {  // CTA-uniform inputs of the fast path
   const EamRowDev *row;
   double rc2;
   float rc2_hi;
+  bool near_build;  // every atom within NlParams::dstar of the list's build positions: certain rows skip the filter
 };
 
 template <bool SINGLE>
 __device__ __forceinline__ void eam_fused_fast(const PotParams &P, const FusedFast &ff, const SysView &sys, Smem &sm, int i0,
-                                               int i1, unsigned T, unsigned rank, double *F, double *U, int n_first,
-                                               int (&cur)[kFilterBatch], long long *clk) {
+                                               int i1, unsigned T, unsigned rank, double *F, double *U, int n0_first,
+                                               int kend_first, int (&cur)[kFilterBatch], long long *clk) {
   double acc[2] = {0.0, 0.0};
-  EamLane L = {0.0, 0.0, 0.0, 0.0, 0};
+  EamLane L = {0.0, 0.0, 0.0, 0.0, 0, 0};
   const int ifirst = i0 + static_cast<int>(threadIdx.x);
   for (int i = ifirst; i < i1; i += blockDim.x) {
-    int n = n_first;
+    int n0 = n0_first, k_end = kend_first;
     if (!SINGLE && i != ifirst) {
-      n = ld_cg(sys.cnt + i);
+      eam_filter_range(sys, i, ff.near_build, n0, k_end);
+      if (n0 < k_end) {
 #pragma unroll
-      for (int u = 0; u < kFilterBatch; u++) cur[u] = ld_cg(sys.nbr + static_cast<size_t>(u) * sys.Np + i);
+        for (int u = 0; u < kFilterBatch; u++)
+          cur[u] = ld_cg(sys.nbr + static_cast<size_t>((n0 & ~(kFilterBatch - 1)) + u) * sys.Np + i);
+      }
     }
-    const int nin = eam_fast_filter(sys, sm, i, n, cur, ff.rc2_hi);
+    const int nin = n0 < k_end ? eam_fast_filter(sys, sm, i, n0, k_end, cur, ff.rc2_hi) : 0;
     phase_clock(clk, 5);
-    eam_fast_density(P, ff.row, sys, sm, i, nin, L, acc);
+    eam_fast_density(P, ff.row, sys, sm, i, n0, nin, L, acc);
     phase_clock(clk, 6);
     if (T > 1) {
       for (unsigned r = 0; r < T; r++) dsmem_store(&sm.pos[i].w, r, L.dfd);
@@ -218,7 +224,7 @@ __device__ __forceinline__ void eam_fused_fast(const PotParams &P, const FusedFa
       F[3 * i + 1] = L.fy;
       F[3 * i + 2] = L.fz;
       sys.dfd[i] = L.dfd;
-      sys.cnt2[i] = L.nin;
+      sys.cnt2[i] = L.n0 | (L.nin << 16);
     }
     if (SINGLE) break;
   }
@@ -244,7 +250,8 @@ __device__ __forceinline__ void eam_fused_fast(const PotParams &P, const FusedFa
       L.fy = F[3 * i + 1];
       L.fz = F[3 * i + 2];
       L.dfd = sys.dfd[i];
-      L.nin = sys.cnt2[i];
+      L.n0 = sys.cnt2[i] & 0xffff;
+      L.nin = sys.cnt2[i] >> 16;
     }
     eam_fast_force(sys, sm, i, L, F);
     if (SINGLE) break;
@@ -261,18 +268,38 @@ __device__ __forceinline__ void eam_fused_fast(const PotParams &P, const FusedFa
   }
 }
 
+// The rarely taken branches of the fused kernel (rebuild, negative coordinates, general rows) are out-of-line
+// functions that take no struct arguments: marshalling SysView / Smem by value at each call site put kilobytes of
+// never-executed stores into the middle of the hot instruction stream, and with instruction caches cold at every
+// launch each jump over them cost an instruction-fetch round trip (8 us of a 90 us launch).  They rebuild their
+// views from this shared-memory copy of the launch arguments instead.
+struct FusedCold {
+  NlBatch nl;
+  ForceBatchArgs a;
+  const PotParams *Pp;
+};
+
+__device__ __forceinline__ void fused_cold_views(const FusedCold &fc, SysView &sys, Smem &sm) {
+  EONB200_DYN_SMEM(smem_raw);
+  sys = batch_sys(fc.nl, fc.a, blockIdx.y);
+  sm = carve_smem_fused(smem_raw, fc.a.N, fc.a.maxCells, sys.cellscratch);
+}
+
 // Stale list: CTA 0 of the cluster rebuilds it (raw positions straight from HBM, cell-list scratch in HBM).
 // (Arguments by value: a reference would force the caller's shared-memory pointers onto the stack and turn every
 // shared load of the hot path into a generic one.)
-__device__ EONB200_NOINLINE void eam_fused_rebuild(NlParams np, SysView sys, Smem sm, unsigned T, unsigned rank,
-                                                  const double *exp_tab_g) {
+__device__ EONB200_NOINLINE void eam_fused_rebuild(const FusedCold *fc, const PotParams *P_sh) {
+  SysView sys;
+  Smem sm;
+  fused_cold_views(*fc, sys, sm);
+  const unsigned T = gridDim.x, rank = blockIdx.x;
+  const NlParams np = make_nl_params(*P_sh);
   if (T > 1) cluster_sync_all();  // nobody still reads the old list
   if (rank == 0) {
-    Smem sm2 = sm;
-    sm2.stage = const_cast<double *>(sys.R);
-    prepare_positions(np, sys, sm2, exp_tab_g);
+    sm.stage = const_cast<double *>(sys.R);
+    prepare_positions(np, sys, sm, P_sh->exp_tab);
     __syncthreads();
-    nl_rebuild(np, sys, sm2);
+    nl_rebuild(np, sys, sm);
   }
   if (T > 1)
     cluster_sync_all();
@@ -281,9 +308,11 @@ __device__ EONB200_NOINLINE void eam_fused_rebuild(NlParams np, SysView sys, Sme
 }
 
 // Coordinates below zero (EAM.cpp:56-83 shifts them up by the lowest one): redo the conversion from HBM.
-__device__ EONB200_NOINLINE double eam_fused_reconvert(SysView sys, Smem sm, double lo0, double lo1, double lo2, double L0,
-                                                      double L1, double L2, bool have) {
-  const double lo[3] = {lo0, lo1, lo2}, L[3] = {L0, L1, L2};
+__device__ EONB200_NOINLINE double eam_fused_reconvert(const FusedCold *fc, double lo0, double lo1, double lo2, bool have) {
+  SysView sys;
+  Smem sm;
+  fused_cold_views(*fc, sys, sm);
+  const double lo[3] = {lo0, lo1, lo2}, L[3] = {sys.box[0], sys.box[4], sys.box[8]};
   double disp2 = 0.0;
   for (int i = threadIdx.x; i < sys.N; i += blockDim.x) {
     double p[3];
@@ -305,9 +334,15 @@ __device__ EONB200_NOINLINE double eam_fused_reconvert(SysView sys, Smem sm, dou
 }
 
 // Mixed elements / small boxes: the general row functions, dF/drho exchanged through HBM.
-__device__ EONB200_NOINLINE void eam_fused_general(const PotParams *Pp, SysView sys, Smem sm, bool tab_ok, int i0, int i1,
-                                                  unsigned T, unsigned rank, double *F, double *U, int N) {
-  const PotParams &P = *Pp;
+__device__ EONB200_NOINLINE void eam_fused_general(const FusedCold *fc, bool tab_ok, int i0, int i1) {
+  SysView sys;
+  Smem sm;
+  fused_cold_views(*fc, sys, sm);
+  const PotParams &P = *fc->Pp;
+  const unsigned T = gridDim.x, rank = blockIdx.x;
+  const int N = fc->a.N;
+  double *F = fc->a.F + static_cast<size_t>(blockIdx.y) * fc->a.strideR;
+  double *U = fc->a.U + blockIdx.y;
   if (threadIdx.x == 0) {
     Geom &g = *sm.geom;
     for (int k = 0; k < 9; k++) g.H[k] = sys.box[k];
@@ -359,7 +394,18 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   const int s = blockIdx.y;
   const unsigned T = gridDim.x;      // CTAs per walker == cluster size (cluster dims (T, 1, 1))
   const unsigned rank = blockIdx.x;  // == %cluster_ctarank
-  const PotParams &P = *Pp;
+  // the parameter block comes into shared memory with the first barrier: later reads (element row, cutoffs) do not
+  // pay an HBM round trip each
+  __shared__ __align__(16) unsigned long long p_sh[(sizeof(PotParams) + 7) / 8];
+  for (int k = threadIdx.x; k < static_cast<int>((sizeof(PotParams) + 7) / 8); k += blockDim.x)
+    p_sh[k] = reinterpret_cast<const unsigned long long *>(Pp)[k];
+  __shared__ FusedCold cold;
+  if (threadIdx.x == 32 % blockDim.x) {  // one lane of the second warp: off thread 0's critical path
+    cold.nl = nl;
+    cold.a = a;
+    cold.Pp = Pp;
+  }
+  const PotParams &P = *reinterpret_cast<const PotParams *>(p_sh);
   const SysView sys = batch_sys(nl, a, s);
   Smem sm = carve_smem_fused(smem_raw, a.N, a.maxCells, sys.cellscratch);
   const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
@@ -392,31 +438,24 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     if (aligned) {
       mbar_expect(sm.mbar, rbytes + 1024u);
       bulk_g2s_issue(raw, sys.R, rbytes, sm.mbar);
-      bulk_g2s_issue(sm.exp_tab, P.exp_tab, 1024u, sm.mbar);
+      bulk_g2s_issue(sm.exp_tab, Pp->exp_tab, 1024u, sm.mbar);
     }
   }
   const double Lbox[3] = {sys.box[0], sys.box[4], sys.box[8]};  // EAM.cpp:31 reads the diagonal only
   const bool have = ld_cg(sys.state) != 0;
   const int z0 = sys.Z[0];
-  int n_first = 0;
+  int cls_first = 0;
   int cur[kFilterBatch];
-  if (ifirst < i1) {
-    n_first = ld_cg(sys.cnt + ifirst);
-#pragma unroll
-    for (int u = 0; u < kFilterBatch; u++) cur[u] = ld_cg(sys.nbr + static_cast<size_t>(u) * sys.Np + ifirst);
-  }
+  if (ifirst < i1) cls_first = ld_cg(sys.cls + ifirst);
   phase_clock(clk, 11);
   {  // L2 prefetch behind the loads the prologue waits for, one 128-byte line per lane and instruction: the list's
      // build positions and the atomic numbers (needed by the conversion below)
     for (int o = tid * 16; o < D; o += nt * 16) l2_prefetch_line(sys.rbuild + o);
     for (int o = tid * 32; o < N; o += nt * 32) l2_prefetch_line(sys.Z + o);
   }
-  phase_clock(clk, 12);
   fill_sh27(sm, Lbox[0], Lbox[1], Lbox[2]);
-  phase_clock(clk, 13);
   __syncthreads();  // mbarrier initialised
-  phase_clock(clk, 14);
-  if (aligned) {
+  if (EONB200_LIKELY(aligned)) {
     mbar_wait(sm.mbar, 0);
   } else {
     for (int k = tid; k < D; k += nt) raw[k] = sys.R[k];
@@ -425,6 +464,15 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   }
 
   phase_clock(clk, 3);
+  // first filter batch of this lane's atom, assuming the common case (atoms near the list's build positions: the
+  // leading sure-in rows skip the filter); it lands while the positions are converted
+  int kend_first = (cls_first & 0xffff) + (cls_first >> 16);
+  int n0_first = (cls_first & 0xffff) & ~(kForceBatch - 1);
+  if (ifirst < i1 && n0_first < kend_first) {
+#pragma unroll
+    for (int u = 0; u < kFilterBatch; u++)
+      cur[u] = ld_cg(sys.nbr + static_cast<size_t>((n0_first & ~(kFilterBatch - 1)) + u) * sys.Np + ifirst);
+  }
   {  // ... and, once the positions have landed, this CTA's slice of the remaining candidate rows (one line per warp
      // of atoms and row); the first kFilterBatch rows are in registers already
     const int lines_per_row = w1 - w0;
@@ -484,35 +532,39 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   }
   phase_clock(clk, 4);
   double disp2 = red6[3];
-  if (red6[0] > 0.0 || red6[1] > 0.0 || red6[2] > 0.0) {
-    disp2 = eam_fused_reconvert(sys, sm, fmax(red6[0], 0.0), fmax(red6[1], 0.0), fmax(red6[2], 0.0), Lbox[0], Lbox[1], Lbox[2],
-                                have);
+  if (EONB200_UNLIKELY(red6[0] > 0.0 || red6[1] > 0.0 || red6[2] > 0.0)) {
+    disp2 = eam_fused_reconvert(&cold, fmax(red6[0], 0.0), fmax(red6[1], 0.0), fmax(red6[2], 0.0), have);
   }
   const NlParams np = make_nl_params(P);
   const double lim = 0.5 * np.skin;
   const bool rebuild = a.force_rebuild != 0 || !have || np.skin <= 0.0 || !(disp2 <= lim * lim);
-  if (rebuild) {  // the same decision in every CTA of the cluster
-    eam_fused_rebuild(np, sys, sm, T, rank, P.exp_tab);
-    if (ifirst < i1) {
-      n_first = ld_cg(sys.cnt + ifirst);
-#pragma unroll
-      for (int u = 0; u < kFilterBatch; u++) cur[u] = ld_cg(sys.nbr + static_cast<size_t>(u) * sys.Np + ifirst);
-    }
+  const bool near_build = rebuild || disp2 <= np.dstar * np.dstar;  // a fresh list is built from these very positions
+  if (EONB200_UNLIKELY(rebuild)) {  // the same decision in every CTA of the cluster
+    eam_fused_rebuild(&cold, &P);
   } else if (rank == 0 && tid == 0) {
     atomicAdd(&sys.stats[1], 1ULL);
   }
+  if (EONB200_UNLIKELY((rebuild || !near_build) && ifirst < i1)) {  // the speculative first batch was for another list / another mode
+    eam_filter_range(sys, ifirst, near_build, n0_first, kend_first);
+    if (n0_first < kend_first) {
+#pragma unroll
+      for (int u = 0; u < kFilterBatch; u++)
+        cur[u] = ld_cg(sys.nbr + static_cast<size_t>((n0_first & ~(kFilterBatch - 1)) + u) * sys.Np + ifirst);
+    }
+  }
+  phase_clock(clk, 12);
   double *F = a.F + static_cast<size_t>(s) * a.strideR;
   const bool mixed = red6[4] != 0.0;
   const double need = 2.0 * P.rc_list + P.skin;  // stored folds stay the reference's minimum image
   const bool tab_ok = Lbox[0] >= need && Lbox[1] >= need && Lbox[2] >= need;
-  if (!mixed && tab_ok && P.eam_fast_ok) {
+  if (EONB200_LIKELY(!mixed && tab_ok && P.eam_fast_ok)) {
     int r0 = -1;
     for (int q = 0; q < P.n_rows; q++)
       if (P.rows[q].Z == z0) {
         r0 = q;
         break;
       }
-    if (r0 < 0) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
+    if (EONB200_UNLIKELY(r0 < 0)) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
       for (int k = 3 * i0 + tid; k < 3 * i1; k += nt) F[k] = 0.0;
       if (rank == 0 && tid == 0) a.U[s] = nan("");
       return;
@@ -522,15 +574,17 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     ff.rc2 = ff.row->rc2;
     const float band = eam_filter_band(fmax(fmax(Lbox[0], Lbox[1]), Lbox[2]), ff.row->r_cut);
     ff.rc2_hi = static_cast<float>(ff.rc2) + band;
-    if (i1 - i0 <= nt)
-      eam_fused_fast<true>(P, ff, sys, sm, i0, i1, T, rank, F, a.U + s, n_first, cur, clk);
+    ff.near_build = near_build;
+    phase_clock(clk, 13);
+    if (EONB200_LIKELY(i1 - i0 <= nt))
+      eam_fused_fast<true>(P, ff, sys, sm, i0, i1, T, rank, F, a.U + s, n0_first, kend_first, cur, clk);
     else
-      eam_fused_fast<false>(P, ff, sys, sm, i0, i1, T, rank, F, a.U + s, n_first, cur, clk);
+      eam_fused_fast<false>(P, ff, sys, sm, i0, i1, T, rank, F, a.U + s, n0_first, kend_first, cur, clk);
     phase_clock(clk, 10);
     return;
   }
   // general rows: full element table, geometry for mic_vec
-  eam_fused_general(Pp, sys, sm, tab_ok, i0, i1, T, rank, F, a.U + s, N);
+  eam_fused_general(&cold, tab_ok, i0, i1);
 }
 
 // Register budgets per CTA size: small CTAs must fit seven to an SM (all walkers resident in one wave).

@@ -27,6 +27,10 @@ struct NlParams {
   double rc;      // list cutoff (potential cutoff + skin)
   double rc2;     // rc * rc, rounded once on the host exactly like `cutoff * cutoff`
   double rc_core2;  // the potential's own cutoff^2: rows list these pairs first, the skin shell after them
+  double rc_core;   // the potential's own cutoff
+  double dstar;     // NL_MIC rows come in three classes of certainty for displacements up to dstar (= skin / 4) from
+                    // the build positions: pairs that stay inside the cutoff, pairs that may cross it, pairs that
+                    // stay outside (a pair distance changes by at most twice the largest displacement)
   double skin;    // 0 -> rebuild on every evaluation
   int per[3];
 };
@@ -350,6 +354,28 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
     const int wix = (wi & 1023) - 512, wiy = ((wi >> 10) & 1023) - 512, wiz = ((wi >> 20) & 1023) - 512;
     // core pairs (inside the potential's cutoff) fill the row from the front, the skin shell from the back;
     // the shell is moved down behind the core afterwards, so that the lanes of a warp accept / reject together
+    // NL_MIC: three classes (see NlParams::dstar) -- sure-in from the front, sure-out from the back, the uncertain
+    // ones parked in this atom's column of nbr2 and moved in between afterwards
+    const double r_in = np.rc_core - 2.0 * np.dstar, r_out = np.rc_core + 2.0 * np.dstar;
+    const double r_in2 = r_in > 0.0 ? r_in * r_in * (1.0 - 1e-12) : -1.0, r_out2 = r_out * r_out * (1.0 + 1e-12);
+    int n0 = 0, n1 = 0, n2 = 0;
+    auto emit3 = [&](int code, double r2) {
+      const int cls = r2 < r_in2 ? 0 : (r2 > r_out2 ? 2 : 1);
+      if (n0 + n1 + n2 < K) {
+        if (cls == 0)
+          sys.nbr[static_cast<size_t>(n0) * Np + i] = code;
+        else if (cls == 2)
+          sys.nbr[static_cast<size_t>(K - 1 - n2) * Np + i] = code;
+        else
+          sys.nbr2[static_cast<size_t>(n1) * Np + i] = code;
+      }
+      if (cls == 0)
+        n0++;
+      else if (cls == 2)
+        n2++;
+      else
+        n1++;
+    };
     int ncore = 0, nshell = 0;
     auto emit = [&](int code, bool core) {
       if (ncore + nshell < K) {
@@ -407,7 +433,7 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
               if (fz > 0) dz -= g.H[8]; else if (fz < 0) dz += g.H[8];
               const double r2 = norm2_rn(dx, dy, dz);
               if (!(r2 <= np.rc2)) continue;
-              emit(pack_mic(j, fx, fy, fz), r2 <= np.rc_core2);
+              emit3(pack_mic(j, fx, fy, fz), r2);
             } else {
               const int wj = sm.wrapc[j];
               const int Sx = sx + wix - ((wj & 1023) - 512);
@@ -433,6 +459,14 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
           }
         }
       }
+    }
+    if (np.mode == NL_MIC) {
+      if (n0 + n1 + n2 <= K)
+        for (int t = 0; t < n1; t++)
+          sys.nbr[static_cast<size_t>(n0 + t) * Np + i] = sys.nbr2[static_cast<size_t>(t) * Np + i];
+      sys.cls[i] = n0 + n1 + n2 <= K ? (n0 | (n1 << 16)) : 0;  // a truncated row reads as empty (the host regrows K)
+      ncore = n0 + n1;
+      nshell = n2;
     }
     const int count = ncore + nshell;
     if (count <= K) {
@@ -462,6 +496,7 @@ __device__ inline bool nl_stage_check(const NlParams &np, const SysView &sys, Sm
                                       bool force_rebuild, const double *exp_tab_g) {
   stage_raw_positions(sys, sm, phase);
   const double disp2 = prepare_positions(np, sys, sm, exp_tab_g);
+  if (threadIdx.x == 0) sm.geom->disp2 = disp2;
   const bool have = *sys.state != 0;
   const double lim = 0.5 * np.skin;
   const bool rebuild = force_rebuild || !have || np.skin <= 0.0 || !(disp2 <= lim * lim);
@@ -494,6 +529,7 @@ __device__ inline int nl_ensure(const NlParams &np, const SysView &sys, Smem &sm
   const bool rebuild = nl_stage_check(np, sys, sm, phase, force_rebuild, exp_tab_g);
   int row_max = 0;
   if (rebuild) {
+    if (threadIdx.x == 0) sm.geom->disp2 = 0.0;  // the fresh list is built from these very positions
     row_max = nl_rebuild(np, sys, sm);
   } else if (threadIdx.x == 0) {
     atomicAdd(&sys.stats[1], 1ULL);

@@ -425,7 +425,8 @@ __device__ __forceinline__ void mic_vec_tab(const Smem &sm, int code, const doub
 struct EamLane {   // what one atom's thread carries from the density pass into the force pass
   double fx, fy, fz;  // Morse pair part of the force, accumulated in the density pass
   double dfd;         // F'(rho_i)
-  int nin;            // surviving (in-cutoff) ordered pairs of this atom
+  int n0;             // leading rows of the cached list taken as they are (pairs certain to be inside the cutoff)
+  int nin;            // pairs the filter let through (compacted in nbr2, padded to a multiple of kForceBatch)
 };
 
 constexpr int kFilterBatch = 8;  // candidate codes a lane keeps in flight; NL_MIC rows are padded to a multiple of it
@@ -439,19 +440,35 @@ __device__ __forceinline__ float eam_filter_band(double Lmax, double rc) {
   return static_cast<float>(8.0e-6 * (Lmax + rc) * rc);
 }
 
-// Filter of atom i: cur[] holds the first kFilterBatch codes of its column (already loaded).  Rows are padded to
-// a multiple of kFilterBatch with codes of the far-away ghost atom N, so no per-candidate bounds test is needed.
-__device__ __forceinline__ int eam_fast_filter(const SysView &sys, const Smem &sm, int i, int n, int (&cur)[kFilterBatch],
-                                               float rc2_hi) {
+// Which rows of atom i's cached list need the filter: with the atoms no further than NlParams::dstar from the
+// list's build positions the leading sure-in rows are taken unfiltered and the trailing sure-out rows are skipped;
+// otherwise every row is screened.
+__device__ __forceinline__ void eam_filter_range(const SysView &sys, int i, bool near_build, int &n0, int &k_end) {
+  if (near_build) {
+    const int c = ld_cg(sys.cls + i);
+    k_end = (c & 0xffff) + (c >> 16);
+    n0 = (c & 0xffff) & ~(kForceBatch - 1);  // whole force-pass batches; the few rows left over just pass the filter
+  } else {
+    n0 = 0;
+    k_end = ld_cg(sys.cnt + i);
+  }
+}
+
+// Filter of rows [k_begin, k_end) of atom i: cur[] holds rows (k_begin & ~7) .. + 7 (already loaded).  Rows past
+// k_end, up to the next multiple of 8, are valid codes too (far pairs or the ghost atom N of the row padding), so
+// there is no upper bounds test.
+__device__ __forceinline__ int eam_fast_filter(const SysView &sys, const Smem &sm, int i, int k_begin, int k_end,
+                                               int (&cur)[kFilterBatch], float rc2_hi) {
   const size_t step = static_cast<size_t>(sys.Np);
-  const int *row = sys.nbr + i;
+  const int k_first = k_begin & ~(kFilterBatch - 1);  // batches stay aligned to the row padding
+  const int *row = sys.nbr + i + static_cast<size_t>(k_first) * step;
   int *row2 = sys.nbr2 + i;
   const float4 pif = sm.posf[i];
   int nin = 0;
-  for (int k0 = 0; k0 < n; k0 += kFilterBatch) {
+  for (int k0 = k_first; k0 < k_end; k0 += kFilterBatch) {
     int nxt[kFilterBatch];
     row += kFilterBatch * step;
-    if (k0 + kFilterBatch < n) {
+    if (k0 + kFilterBatch < k_end) {
 #pragma unroll
       for (int u = 0; u < kFilterBatch; u++) nxt[u] = ld_cg(row + u * step);
     }
@@ -464,7 +481,7 @@ __device__ __forceinline__ int eam_fast_filter(const SysView &sys, const Smem &s
       const float dyf = (pif.y - pjf.y) + shf.y;
       const float dzf = (pif.z - pjf.z) + shf.z;
       const float r2f = fmaf(dzf, dzf, fmaf(dyf, dyf, dxf * dxf));
-      if (r2f <= rc2_hi) {
+      if (r2f <= rc2_hi && k0 + u >= k_begin) {
         *row2 = c;
         row2 += step;
         nin++;
@@ -477,10 +494,11 @@ __device__ __forceinline__ int eam_fast_filter(const SysView &sys, const Smem &s
 }
 
 __device__ __forceinline__ void eam_fast_density(const PotParams &P, const EamRowDev *pr, const SysView &sys, const Smem &sm,
-                                                 int i, int nin, EamLane &L, double (&acc)[2]) {
+                                                 int i, int n0, int nin, EamLane &L, double (&acc)[2]) {
   const double *T = sm.exp_tab;
   const size_t step = static_cast<size_t>(sys.Np);
   const double4 pi = sm.pos[i];
+  const int *row = sys.nbr + i;
   int *row2 = sys.nbr2 + i;
   double *rowA = sys.pairA + i;
   const double rc2 = pr->rc2;
@@ -490,16 +508,21 @@ __device__ __forceinline__ void eam_fast_density(const PotParams &P, const EamRo
   const double nK2 = -(P.eam_conservative ? 1.0 : -1.0) * 2.0 * pr->alphaM * pr->Dm;
   double dens = 0.0, e_acc = 0.0, fx = 0.0, fy = 0.0, fz = 0.0;
   int npairs = 0;
-  int cnext = nin > 0 ? ld_cg(row2) : 0;
-  for (int kk = 0; kk < nin; kk++) {
+  const int ntot = n0 + nin;
+  const int *pc = n0 > 0 ? row : row2;  // walks the cached list's leading rows, then the compacted column
+  int cnext = ntot > 0 ? ld_cg(pc) : 0;
+  for (int kk = 0; kk < ntot; kk++) {
     const int code = cnext;
-    row2 += step;
-    if (kk + 1 < nin) cnext = ld_cg(row2);
+    pc += step;
+    if (kk + 1 == n0) pc = row2;
+    if (kk + 1 < ntot) cnext = ld_cg(pc);
     const double4 pj = sm.pos[code & kNbrIndexMask];
-    double dx, dy, dz;
-    mic_vec_tab(sm, code, pi, pj, dx, dy, dz);
+    const double4 sh = sm.sh27[static_cast<unsigned>(code) >> kNbrIndexBits];
+    const double dx = (pi.x - pj.x) + sh.x;
+    const double dy = (pi.y - pj.y) + sh.y;
+    const double dz = (pi.z - pj.z) + sh.z;
     const double r2 = norm2_rn(dx, dy, dz);
-    if (r2 > rc2) {  // EAM.cpp:172 -- only pairs inside the single-precision margin of the filter get here
+    if (EONB200_UNLIKELY(r2 > rc2)) {  // EAM.cpp:172 -- only pairs inside the filter's single-precision margin get here
       *rowA = 0.0;
       rowA += step;
       continue;
@@ -525,59 +548,66 @@ __device__ __forceinline__ void eam_fast_density(const PotParams &P, const EamRo
     fz = fma(nB, dz, fz);
     e_acc = fma(hDm, fma(dm, dm, -1.0), e_acc);  // half of Dm (d^2 - 1): the pair is seen from both ends
   }
-  // pad the compacted column to a multiple of kForceBatch with null pairs (weight 0, partner = the atom itself)
-  for (int kk = nin; kk & (kForceBatch - 1); kk++) {
-    *row2 = i | (13 << kNbrIndexBits);
+  // pad the pair sequence to a multiple of kForceBatch with null pairs (weight 0, partner = the atom itself)
+  int nin_padded = nin;
+  for (int kk = ntot; kk & (kForceBatch - 1); kk++) {
+    row2[static_cast<size_t>(nin_padded) * step] = i | (13 << kNbrIndexBits);
     *rowA = 0.0;
-    row2 += step;
     rowA += step;
+    nin_padded++;
   }
   e_acc += eam_embed(pr->c, dens);
   L.dfd = eam_dembed(pr->dc, dens);
   L.fx = fx;
   L.fy = fy;
   L.fz = fz;
-  L.nin = nin;
+  L.n0 = n0;
+  L.nin = nin_padded;
   acc[0] += e_acc;
   acc[1] += static_cast<double>(npairs);
 }
 
-// sm.pos[j].w must hold F'(rho_j) of every atom of the walker.
+// sm.pos[j].w must hold F'(rho_j) of every atom of the walker.  L.n0 + L.nin is a multiple of kForceBatch.
 __device__ __forceinline__ void eam_fast_force(const SysView &sys, const Smem &sm, int i, const EamLane &L, double *F) {
   constexpr int B = kForceBatch;
   const size_t step = static_cast<size_t>(sys.Np);
   const double4 pi = sm.pos[i];
+  const int *row = sys.nbr + i;
   const int *row2 = sys.nbr2 + i;
   const double *rowA = sys.pairA + i;
   double fx = L.fx, fy = L.fy, fz = L.fz;
   const double dfi = L.dfd;
-  const int nin = L.nin;
+  const int n0 = L.n0, ntot = L.n0 + L.nin;
   int c[B];
   double A[B];
-  if (nin > 0) {
+  const int *pc = n0 > 0 ? row : row2;  // n0 is a multiple of B: a batch never straddles the two sources
+  if (ntot > 0) {
 #pragma unroll
     for (int u = 0; u < B; u++) {
-      c[u] = ld_cg(row2 + u * step);
+      c[u] = ld_cg(pc + u * step);
       A[u] = ld_cg(rowA + u * step);
     }
   }
-  for (int k0 = 0; k0 < nin; k0 += B) {
+  for (int k0 = 0; k0 < ntot; k0 += B) {
     int cn[B];
     double An[B];
-    row2 += B * step;
     rowA += B * step;
-    if (k0 + B < nin) {
+    pc += B * step;
+    if (k0 + B == n0) pc = row2;
+    if (k0 + B < ntot) {
 #pragma unroll
       for (int u = 0; u < B; u++) {
-        cn[u] = ld_cg(row2 + u * step);
+        cn[u] = ld_cg(pc + u * step);
         An[u] = ld_cg(rowA + u * step);
       }
     }
 #pragma unroll
     for (int u = 0; u < B; u++) {
       const double4 pj = sm.pos[c[u] & kNbrIndexMask];
-      double dx, dy, dz;
-      mic_vec_tab(sm, c[u], pi, pj, dx, dy, dz);
+      const double4 sh = sm.sh27[static_cast<unsigned>(c[u]) >> kNbrIndexBits];
+      const double dx = (pi.x - pj.x) + sh.x;
+      const double dy = (pi.y - pj.y) + sh.y;
+      const double dz = (pi.z - pj.z) + sh.z;
       const double ns = -(dfi + pj.w) * A[u];
       fx = fma(ns, dx, fx);
       fy = fma(ns, dy, fy);
@@ -596,7 +626,8 @@ __device__ __forceinline__ void eam_fast_force(const SysView &sys, const Smem &s
 
 // Whole walker in one CTA (resident kernels): the same filter / density / force lane functions as the fused kernel,
 // thread-strided over the atoms; forces to sm.stage.  sm.pos holds the prepared positions.
-__device__ EONB200_NOINLINE double walker_forces_eam_fast(const PotParams &P, const EamRowDev *row, const SysView &sys, Smem sm) {
+__device__ EONB200_NOINLINE double walker_forces_eam_fast(const PotParams &P, const EamRowDev *row, const SysView &sys, Smem sm,
+                                                         double dstar) {
   const int N = sys.N;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < N; i += nt) {
@@ -611,22 +642,25 @@ __device__ EONB200_NOINLINE double walker_forces_eam_fast(const PotParams &P, co
   const Geom &g = *sm.geom;
   const float rc2_hi = static_cast<float>(row->rc2) + eam_filter_band(fmax(fmax(g.H[0], g.H[4]), g.H[8]), row->r_cut);
   const bool single = N <= nt;
+  const bool near_build = g.disp2 <= dstar * dstar;
   double acc[2] = {0.0, 0.0};
-  EamLane L = {0.0, 0.0, 0.0, 0.0, 0};
+  EamLane L = {0.0, 0.0, 0.0, 0.0, 0, 0};
   for (int i = tid; i < N; i += nt) {
-    const int n = sys.cnt[i];
+    int n0, k_end;
+    eam_filter_range(sys, i, near_build, n0, k_end);
     int cur[kFilterBatch];
 #pragma unroll
-    for (int u = 0; u < kFilterBatch; u++) cur[u] = sys.nbr[static_cast<size_t>(u) * sys.Np + i];
-    const int nin = eam_fast_filter(sys, sm, i, n, cur, rc2_hi);
-    eam_fast_density(P, row, sys, sm, i, nin, L, acc);
+    for (int u = 0; u < kFilterBatch; u++)
+      cur[u] = n0 < k_end ? sys.nbr[static_cast<size_t>((n0 & ~(kFilterBatch - 1)) + u) * sys.Np + i] : 0;
+    const int nin = n0 < k_end ? eam_fast_filter(sys, sm, i, n0, k_end, cur, rc2_hi) : 0;
+    eam_fast_density(P, row, sys, sm, i, n0, nin, L, acc);
     sm.pos[i].w = L.dfd;
     if (!single) {
       sm.stage[3 * i] = L.fx;
       sm.stage[3 * i + 1] = L.fy;
       sm.stage[3 * i + 2] = L.fz;
       sys.dfd[i] = L.dfd;
-      sys.cnt2[i] = L.nin;
+      sys.cnt2[i] = L.n0 | (L.nin << 16);
     }
   }
   block_sum<2>(acc, sm.red);  // (barriers: every F'(rho) is in place)
@@ -636,7 +670,8 @@ __device__ EONB200_NOINLINE double walker_forces_eam_fast(const PotParams &P, co
       L.fy = sm.stage[3 * i + 1];
       L.fz = sm.stage[3 * i + 2];
       L.dfd = sys.dfd[i];
-      L.nin = sys.cnt2[i];
+      L.n0 = sys.cnt2[i] & 0xffff;
+      L.nin = sys.cnt2[i] >> 16;
     }
     eam_fast_force(sys, sm, i, L, sm.stage);
   }
@@ -659,7 +694,7 @@ __device__ inline double walker_forces(const PotParams &P, const SysView &sys, S
     }
     const bool multi = (flags & 1) != 0;
     if (!multi && sm.geom->tab_ok && P.eam_fast_ok && sm.posf != nullptr)
-      return walker_forces_eam_fast(P, &P.rows[sm.rowid[0]], sys, sm);
+      return walker_forces_eam_fast(P, &P.rows[sm.rowid[0]], sys, sm, 0.25 * P.skin);
     if (multi)
       eam_pass1<true>(P, sys, sm, lpa, 0, N, sm.dfd, acc);
     else

@@ -70,6 +70,7 @@ struct NlBatch {
   double *pairB;    // [S][K][Np] EAM: +-phi'(r)/r
   int *nbr2;        // [S][K][Np] fused EAM kernel: this evaluation's in-cutoff pairs, compacted per atom
   int *cnt2;        // [S][Np]    their count (only used when a thread owns more than one atom)
+  int *cls;         // [S][Np]    NL_MIC rows: sure-in count | uncertain count << 16 (NlParams::dstar)
   int *cellscratch; // [S][scratch_stride] cell-list scratch of an in-kernel rebuild (fused kernel)
   int scratch_stride;
   double4 *pos4;    // [S][Np]    prepared positions (stateless tiled kernels)
@@ -97,6 +98,7 @@ struct SysView {
   double *pairA, *pairB;  // this system's [K][Np] blocks (null for the pair potentials)
   int *nbr2;
   int *cnt2;
+  int *cls;
   int *cellscratch;
   double4 *pos4;
   double *dfd;
@@ -126,6 +128,7 @@ __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, con
   v.pairB = nl.pairB ? nl.pairB + static_cast<size_t>(s) * nl.K * nl.Np : nullptr;
   v.nbr2 = nl.nbr2 ? nl.nbr2 + static_cast<size_t>(s) * nl.K * nl.Np : nullptr;
   v.cnt2 = nl.cnt2 ? nl.cnt2 + static_cast<size_t>(s) * nl.Np : nullptr;
+  v.cls = nl.cls ? nl.cls + static_cast<size_t>(s) * nl.Np : nullptr;
   v.cellscratch = nl.cellscratch ? nl.cellscratch + static_cast<size_t>(s) * nl.scratch_stride : nullptr;
   v.pos4 = nl.pos4 ? nl.pos4 + static_cast<size_t>(s) * nl.Np : nullptr;
   v.dfd = nl.dfd ? nl.dfd + static_cast<size_t>(s) * nl.Np : nullptr;
@@ -149,6 +152,7 @@ struct Geom {
   int ncells;
   int ok;           // box invertible
   int tab_ok;       // the per-axis shift tables (Smem::shx/shy/shz) are valid for this box
+  double disp2;     // largest squared displacement of the prepared positions from the list's build positions
 };
 
 // Carve-up of the dynamic shared memory of a walker CTA.

@@ -193,10 +193,11 @@ def test_fused_eam_launch_shapes(backend, oracle, kw):
     from eon_b200 import workloads as WL
     s = WL.load_structure("akmc_al.json")
     opot = oracle.potential(oracle.POT_EAM)
-    R = WL.jitter(s.positions, 3, 0.04, seed=11)
-    R[2] += 0.9  # beyond skin / 2: in-kernel rebuild; the rigid shift also moves atoms across the cell faces
+    R = WL.jitter(s.positions, 4, 0.04, seed=11)
+    R[2] += 0.9   # beyond skin / 2: in-kernel rebuild; the rigid shift also moves atoms across the cell faces
+    R[3] = R[0] + 0.18  # between skin / 4 and skin / 2 of the list built from R[0]: every row is screened again
     with B200Potential("eam", lib=backend, skin=1.0, **kw) as pot:
-        for w in (0, 1, 2, 1):
+        for w in (0, 1, 3, 2, 1):
             F, U, _ = pot.forceBatch(2, s.n_atoms, np.stack([R[w], R[0]]).reshape(2, -1), s.atomic_nrs, s.cell.reshape(9))
             for k, ww in enumerate((w, 0)):
                 U0, F0 = oracle.force(opot, R[ww], s.atomic_nrs, s.cell)

@@ -29,9 +29,11 @@ d = np.diff(cyc, axis=1) / 1.965e3  # us at 1965 MHz
 print("entry spread us: min %.1f med %.1f max %.1f" % (start_us.min(), np.median(start_us), start_us.max()))
 for k, nm in enumerate(names):
     print("%-12s med %.2f  p90 %.2f  max %.2f us" % (nm, np.median(d[:, k]), np.percentile(d[:, k], 90), d[:, k].max()))
-for a, b, nm in [(2, 11, "loads issued"), (11, 12, "prefetch issued"), (12, 13, "image table"), (13, 14, "barrier"), (14, 3, "tma wait")]:
+for a, b, nm in [(2, 11, "entry -> loads issued"), (11, 3, "-> positions landed"), (4, 12, "check done -> list decision"),
+                 (12, 13, "-> element row / margins"), (13, 5, "-> filter done")]:
     dd = (c[:, b] - c[:, a]) / 1.965e3
-    print("  prologue %-16s med %.2f max %.2f us" % (nm, np.median(dd), dd.max()))
+    print("  detail %-28s med %.2f max %.2f us   (first CTA of each cluster: med %.2f, others: med %.2f)" % (
+        nm, np.median(dd), dd.max(), np.median(dd[0::max(1, len(c) // W)]), np.median(np.delete(dd, np.s_[0::max(1, len(c) // W)])) if len(c) > W else float("nan")))
 tot = (cyc[:, -1] - cyc[:, 0]) / 1.965e3
 print("cta total med %.1f max %.1f; end time (start+total) max %.1f us" % (np.median(tot), tot.max(), (start_us + tot).max()))
 sm = c[:, 1].astype(int)
