@@ -294,6 +294,12 @@ void pick_fused(const EonB200Pot *pot, long S, long N, int *T_out, int *threads_
   if (pot->cfg.tiles_override > 0) T = pot->cfg.tiles_override;
   T = std::max<long>(std::max<long>(T, Tmin), 1);
   T = std::min<long>(std::min<long>(T, 8), Wn);
+  if (pot->cfg.tiles_override <= 0) {  // cluster sizes 1, 2, 4, 8
+    long p2 = 1;
+    while (p2 < T) p2 *= 2;
+    T = std::min<long>(p2, 8);
+    while (T > 1 && T > Wn) T /= 2;
+  }
   long wpc = (Wn + T - 1) / T;
   // the largest slice of the warp-granular split w0 = rank * Wn / T
   for (long r = 0; r < T; r++) wpc = std::max(wpc, (r + 1) * Wn / T - r * Wn / T);
@@ -469,7 +475,6 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     NlBatch view = nl_view(pot, nl);
     CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
     if (eam) {
-      CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
       const dim3 grid(static_cast<unsigned>(fused_T), static_cast<unsigned>(S));
 #ifdef EONB200_EMU
       EONB200_LAUNCH_CLUSTER(k_eam_fused, grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
@@ -507,8 +512,12 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
                                 pot->stream));
     CU_TRY(pot, cudaStreamSynchronize(pot->stream));
     float ms0 = 0, ms1 = 0;
-    cudaEventElapsedTime(&ms0, pot->ev[0], pot->ev[1]);
-    cudaEventElapsedTime(&ms1, pot->ev[1], pot->ev[2]);
+    if (eam) {  // one kernel: no split point
+      cudaEventElapsedTime(&ms1, pot->ev[0], pot->ev[2]);
+    } else {
+      cudaEventElapsedTime(&ms0, pot->ev[0], pot->ev[1]);
+      cudaEventElapsedTime(&ms1, pot->ev[1], pot->ev[2]);
+    }
     pot->last_ms[0] = ms0;
     pot->last_ms[1] = ms1;
     const int need = pot->h_overflow.p[0];

@@ -56,6 +56,10 @@ constexpr double kSafeEps = 1e-300;  // include/eon/SafeMath.h:19
 #else
 #define EONB200_LAUNCH_CLUSTER(kernel, grid_, block_, smem_, stream_, cx_, ...)                  \
   do {                                                                                         \
+    if ((cx_) == 1) {                                                                          \
+      kernel<<<(grid_), (block_), (smem_), (stream_)>>>(__VA_ARGS__);                          \
+      break;                                                                                   \
+    }                                                                                          \
     cudaLaunchConfig_t cfg_ = {};                                                              \
     cfg_.gridDim = (grid_);                                                                    \
     cfg_.blockDim = dim3(block_);                                                              \
