@@ -522,7 +522,7 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     pot->last_ms[1] = ms1;
     const int need = pot->h_overflow.p[0];
     pot->last_stats[0] = static_cast<long long>(pot->h_stats.p[0]);
-    pot->last_stats[1] = static_cast<long long>(pot->h_stats.p[1]);
+    pot->last_stats[1] = eam ? S - static_cast<long long>(pot->h_stats.p[0]) : static_cast<long long>(pot->h_stats.p[1]);
     pot->last_stats[2] = nl.K;
     pot->last_stats[3] = need;
     pot->last_stats[4] = static_cast<long long>(pot->h_stats.p[2]);

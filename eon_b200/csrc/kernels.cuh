@@ -186,6 +186,8 @@ __device__ __forceinline__ void phase_clock(long long *clk, int slot) {
 #endif
 }
 
+constexpr int kConvAtoms = 2;  // atoms a thread converts per round of the prologue
+
 struct FusedFast {  // CTA-uniform inputs of the fast path
   const EamRowDev *row;
   double rc2;
@@ -308,11 +310,18 @@ __device__ EONB200_NOINLINE void eam_fused_rebuild(const FusedCold *fc, const Po
 }
 
 // Coordinates below zero (EAM.cpp:56-83 shifts them up by the lowest one): redo the conversion from HBM.
-__device__ EONB200_NOINLINE double eam_fused_reconvert(const FusedCold *fc, double lo0, double lo1, double lo2, bool have) {
+__device__ EONB200_NOINLINE double eam_fused_reconvert(const FusedCold *fc, bool have) {
   SysView sys;
   Smem sm;
   fused_cold_views(*fc, sys, sm);
-  const double lo[3] = {lo0, lo1, lo2}, L[3] = {sys.box[0], sys.box[4], sys.box[8]};
+  double lo[3] = {0.0, 0.0, 0.0};  // EAM.cpp:56-83: |lowest coordinate| per axis where that is negative
+  for (int i = threadIdx.x; i < sys.N; i += blockDim.x)
+    for (int k = 0; k < 3; k++) lo[k] = fmax(lo[k], -sys.R[3 * i + k]);
+  {
+    const int op[3] = {RED_MAX, RED_MAX, RED_MAX};
+    block_reduce<3>(lo, op, sm.red);
+  }
+  const double L[3] = {sys.box[0], sys.box[4], sys.box[8]};
   double disp2 = 0.0;
   for (int i = threadIdx.x; i < sys.N; i += blockDim.x) {
     double p[3];
@@ -448,10 +457,20 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   int cur[kFilterBatch];
   if (ifirst < i1) cls_first = ld_cg(sys.cls + ifirst);
   phase_clock(clk, 11);
-  {  // L2 prefetch behind the loads the prologue waits for, one 128-byte line per lane and instruction: the list's
-     // build positions and the atomic numbers (needed by the conversion below)
-    for (int o = tid * 16; o < D; o += nt * 16) l2_prefetch_line(sys.rbuild + o);
-    for (int o = tid * 32; o < N; o += nt * 32) l2_prefetch_line(sys.Z + o);
+  // build positions and atomic numbers of the atoms this thread converts in the first round (rbuild is allocated
+  // even before the first build; it is only used when a list exists)
+  double rb[kConvAtoms][3];
+  int zz[kConvAtoms];
+#pragma unroll
+  for (int u = 0; u < kConvAtoms; u++) {
+    const int i = u * nt + tid;
+    zz[u] = z0;
+    if (i < N) {
+      zz[u] = sys.Z[i];
+      rb[u][0] = ld_cg(sys.rbuild + 3 * i);
+      rb[u][1] = ld_cg(sys.rbuild + 3 * i + 1);
+      rb[u][2] = ld_cg(sys.rbuild + 3 * i + 2);
+    }
   }
   fill_sh27(sm, Lbox[0], Lbox[1], Lbox[2]);
   __syncthreads();  // mbarrier initialised
@@ -473,24 +492,30 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     for (int u = 0; u < kFilterBatch; u++)
       cur[u] = ld_cg(sys.nbr + static_cast<size_t>((n0_first & ~(kFilterBatch - 1)) + u) * sys.Np + ifirst);
   }
-  {  // ... and, once the positions have landed, this CTA's slice of the remaining candidate rows (one line per warp
-     // of atoms and row); the first kFilterBatch rows are in registers already
-    const int lines_per_row = w1 - w0;
-    const int kmax = a.kmax < sys.K ? a.kmax : sys.K;
-    const int nlines = (kmax - kFilterBatch) * lines_per_row;
-    for (int q = tid; q < nlines; q += nt) {
-      const int k = kFilterBatch + q / lines_per_row, seg = q % lines_per_row;
-      l2_prefetch_line(sys.nbr + static_cast<size_t>(k) * sys.Np + i0 + 32 * seg);
-    }
-  }
+  // (No L2 prefetch of the remaining candidate rows: a thousand prefetch.global.L2 per CTA filled the SM's miss
+  // queue and stalled every warp's loads for ~8 us -- measured with the phase clocks; the rows are fetched by the
+  // batched loads of the filter / density passes instead.)
   // ---- raw coordinates -> wrapped positions (double + float), in place; Verlet displacement; element check ----
   // pos[i] overlaps only raw[i'] with i' <= i, so a round reads its atoms into registers, meets at a barrier and
-  // then writes; later rounds read higher atoms only.
-  double red6[6] = {-1e300, -1e300, -1e300, 0.0, 0.0, 0.0};  // max(-x), max(-y), max(-z), disp^2, mixed elements
-  for (int base = 0; base < N; base += 4 * nt) {
-    double q[4][3];
+  // then writes; later rounds read higher atoms only.  (The first round's build positions and atomic numbers were
+  // requested before the bulk copy was waited for.)
+  double red3[3] = {-1e300, 0.0, 0.0};  // largest negated coordinate, largest displacement^2, mixed elements
+  for (int base = 0; base < N; base += kConvAtoms * nt) {
+    double q[kConvAtoms][3];
+    if (base > 0) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+      for (int u = 0; u < kConvAtoms; u++) {
+        const int i = base + u * nt + tid;
+        if (i < N) {
+          zz[u] = sys.Z[i];
+          rb[u][0] = ld_cg(sys.rbuild + 3 * i);
+          rb[u][1] = ld_cg(sys.rbuild + 3 * i + 1);
+          rb[u][2] = ld_cg(sys.rbuild + 3 * i + 2);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kConvAtoms; u++) {
       const int i = base + u * nt + tid;
       if (i < N) {
         q[u][0] = raw[3 * i];
@@ -500,12 +525,12 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     }
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
+    for (int u = 0; u < kConvAtoms; u++) {
       const int i = base + u * nt + tid;
       if (i < N) {
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-          red6[k] = fmax(red6[k], -q[u][k]);
+          red3[0] = fmax(red3[0], -q[u][k]);
           if (Lbox[k] > 0.0) {
             int guard = 0;
             while (q[u][k] > Lbox[k] && guard++ < 1000000) q[u][k] -= Lbox[k];  // EAM.cpp:86-90
@@ -514,11 +539,10 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
         sm.pos[i] = make_double4(q[u][0], q[u][1], q[u][2], 0.0);
         sm.posf[i] = make_float4(static_cast<float>(q[u][0]), static_cast<float>(q[u][1]), static_cast<float>(q[u][2]), 0.0f);
         if (have) {
-          const double dx = q[u][0] - ld_cg(sys.rbuild + 3 * i), dy = q[u][1] - ld_cg(sys.rbuild + 3 * i + 1),
-                       dz = q[u][2] - ld_cg(sys.rbuild + 3 * i + 2);
-          red6[3] = fmax(red6[3], dx * dx + dy * dy + dz * dz);
+          const double dx = q[u][0] - rb[u][0], dy = q[u][1] - rb[u][1], dz = q[u][2] - rb[u][2];
+          red3[1] = fmax(red3[1], dx * dx + dy * dy + dz * dz);
         }
-        if (sys.Z[i] != z0) red6[4] = 1.0;
+        if (zz[u] != z0) red3[2] = 1.0;
       }
     }
   }
@@ -527,23 +551,18 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     sm.posf[N] = make_float4(1e18f, 1e18f, 1e18f, 0.0f);
   }
   {
-    const int op[6] = {RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX, RED_MAX};
-    block_reduce<6>(red6, op, sm.red);
+    const int op[3] = {RED_MAX, RED_MAX, RED_MAX};
+    block_reduce<3>(red3, op, sm.red);
   }
   phase_clock(clk, 4);
-  double disp2 = red6[3];
-  if (EONB200_UNLIKELY(red6[0] > 0.0 || red6[1] > 0.0 || red6[2] > 0.0)) {
-    disp2 = eam_fused_reconvert(&cold, fmax(red6[0], 0.0), fmax(red6[1], 0.0), fmax(red6[2], 0.0), have);
-  }
+  double disp2 = red3[1];
+  if (EONB200_UNLIKELY(red3[0] > 0.0)) disp2 = eam_fused_reconvert(&cold, have);  // some coordinate below zero
   const NlParams np = make_nl_params(P);
   const double lim = 0.5 * np.skin;
   const bool rebuild = a.force_rebuild != 0 || !have || np.skin <= 0.0 || !(disp2 <= lim * lim);
   const bool near_build = rebuild || disp2 <= np.dstar * np.dstar;  // a fresh list is built from these very positions
-  if (EONB200_UNLIKELY(rebuild)) {  // the same decision in every CTA of the cluster
-    eam_fused_rebuild(&cold, &P);
-  } else if (rank == 0 && tid == 0) {
-    atomicAdd(&sys.stats[1], 1ULL);
-  }
+  // (lists reused = systems - lists rebuilt: counted on the host, not with one more atomic per walker here)
+  if (EONB200_UNLIKELY(rebuild)) eam_fused_rebuild(&cold, &P);  // the same decision in every CTA of the cluster
   if (EONB200_UNLIKELY((rebuild || !near_build) && ifirst < i1)) {  // the speculative first batch was for another list / another mode
     eam_filter_range(sys, ifirst, near_build, n0_first, kend_first);
     if (n0_first < kend_first) {
@@ -554,7 +573,7 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   }
   phase_clock(clk, 12);
   double *F = a.F + static_cast<size_t>(s) * a.strideR;
-  const bool mixed = red6[4] != 0.0;
+  const bool mixed = red3[2] != 0.0;
   const double need = 2.0 * P.rc_list + P.skin;  // stored folds stay the reference's minimum image
   const bool tab_ok = Lbox[0] >= need && Lbox[1] >= need && Lbox[2] >= need;
   if (EONB200_LIKELY(!mixed && tab_ok && P.eam_fast_ok)) {
