@@ -555,6 +555,9 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     block_reduce<3>(red3, op, sm.red);
   }
   phase_clock(clk, 4);
+  // Every CTA of the cluster has filled its position block before anybody stores F'(rho) into it through distributed
+  // shared memory (and is known to be running, which remote shared-memory accesses require).
+  if (T > 1) cluster_sync_all();
   double disp2 = red3[1];
   if (EONB200_UNLIKELY(red3[0] > 0.0)) disp2 = eam_fused_reconvert(&cold, have);  // some coordinate below zero
   const NlParams np = make_nl_params(P);
