@@ -408,12 +408,7 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   __shared__ __align__(16) unsigned long long p_sh[(sizeof(PotParams) + 7) / 8];
   for (int k = threadIdx.x; k < static_cast<int>((sizeof(PotParams) + 7) / 8); k += blockDim.x)
     p_sh[k] = reinterpret_cast<const unsigned long long *>(Pp)[k];
-  __shared__ FusedCold cold;
-  if (threadIdx.x == 32 % blockDim.x) {  // one lane of the second warp: off thread 0's critical path
-    cold.nl = nl;
-    cold.a = a;
-    cold.Pp = Pp;
-  }
+  __shared__ FusedCold cold;  // filled only when a cold path is about to run (see below)
   const PotParams &P = *reinterpret_cast<const PotParams *>(p_sh);
   const SysView sys = batch_sys(nl, a, s);
   Smem sm = carve_smem_fused(smem_raw, a.N, a.maxCells, sys.cellscratch);
@@ -555,12 +550,28 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     block_reduce<3>(red3, op, sm.red);
   }
   phase_clock(clk, 4);
+  const NlParams np = make_nl_params(P);
+  const double need = 2.0 * P.rc_list + P.skin;  // stored folds stay the reference's minimum image
+  const bool tab_ok = Lbox[0] >= need && Lbox[1] >= need && Lbox[2] >= need;
+  const bool mixed = red3[2] != 0.0;
+  {  // the launch arguments the cold paths read: marshalled here, once, only if one of them may run
+    const double lim0 = 0.5 * np.skin;
+    const bool may_go_cold = red3[0] > 0.0 || a.force_rebuild != 0 || !have || np.skin <= 0.0 || !(red3[1] <= lim0 * lim0) ||
+                             mixed || !tab_ok || !P.eam_fast_ok;
+    if (EONB200_UNLIKELY(may_go_cold)) {  // CTA-uniform
+      if (tid == 0) {
+        cold.nl = nl;
+        cold.a = a;
+        cold.Pp = Pp;
+      }
+      __syncthreads();
+    }
+  }
   // Every CTA of the cluster has filled its position block before anybody stores F'(rho) into it through distributed
   // shared memory (and is known to be running, which remote shared-memory accesses require).
   if (T > 1) cluster_sync_all();
   double disp2 = red3[1];
   if (EONB200_UNLIKELY(red3[0] > 0.0)) disp2 = eam_fused_reconvert(&cold, have);  // some coordinate below zero
-  const NlParams np = make_nl_params(P);
   const double lim = 0.5 * np.skin;
   const bool rebuild = a.force_rebuild != 0 || !have || np.skin <= 0.0 || !(disp2 <= lim * lim);
   const bool near_build = rebuild || disp2 <= np.dstar * np.dstar;  // a fresh list is built from these very positions
@@ -576,9 +587,6 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
   }
   phase_clock(clk, 12);
   double *F = a.F + static_cast<size_t>(s) * a.strideR;
-  const bool mixed = red3[2] != 0.0;
-  const double need = 2.0 * P.rc_list + P.skin;  // stored folds stay the reference's minimum image
-  const bool tab_ok = Lbox[0] >= need && Lbox[1] >= need && Lbox[2] >= need;
   if (EONB200_LIKELY(!mixed && tab_ok && P.eam_fast_ok)) {
     int r0 = -1;
     for (int q = 0; q < P.n_rows; q++)
