@@ -196,6 +196,8 @@ void fill_params(EonB200Pot *pot) {
     } else if (c.kind == EONB200_POT_MORSE_PT) {
       const double d = 1.0 - std::exp(-P.morse_a * (rc - P.morse_re));
       P.eshift = P.morse_De * d * d - P.morse_De;
+      // the unguarded exp of the pair loop is fine while the exponent stays far inside the double range
+      P.eam_fast_ok = std::fabs(P.morse_a) * (rc + std::fabs(P.morse_re)) < 600.0 ? 1 : 0;
     }
   }
   P.cutoff2 = P.cutoff * P.cutoff;
@@ -336,12 +338,13 @@ int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K) {
   CU_TRY(pot, nl.dfd.reserve(static_cast<size_t>(S) * Np));
   CU_TRY(pot, nl.rowid.reserve(static_cast<size_t>(S) * Np));
   CU_TRY(pot, nl.upart.reserve(static_cast<size_t>(S) * kMaxTiles * 4));
+  // certainty classes of the rows (and the scratch column the build parks the uncertain codes in): every potential
+  CU_TRY(pot, nl.nbr2.reserve(static_cast<size_t>(S) * K * Np));
+  CU_TRY(pot, nl.cls.reserve(static_cast<size_t>(S) * Np));
   if (pot->cfg.kind == EONB200_POT_EAM) {
     CU_TRY(pot, nl.pairA.reserve(static_cast<size_t>(S) * K * Np));
     CU_TRY(pot, nl.pairB.reserve(static_cast<size_t>(S) * K * Np));
-    CU_TRY(pot, nl.nbr2.reserve(static_cast<size_t>(S) * K * Np));
     CU_TRY(pot, nl.cnt2.reserve(static_cast<size_t>(S) * Np));
-    CU_TRY(pot, nl.cls.reserve(static_cast<size_t>(S) * Np));
     nl.scratch_stride = static_cast<int>(fused_scratch_ints(static_cast<int>(N), pick_max_cells(N)));
     CU_TRY(pot, nl.cellscratch.reserve(static_cast<size_t>(S) * nl.scratch_stride));
   }

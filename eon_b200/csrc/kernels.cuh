@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_prepare(const PotParam
     if (P.kind == POT_EAM) sys.rowid[i] = sm.rowid[i];
   }
   if (threadIdx.x == 0) {
-    *sys.flags = flags;
+    // bit 2: every atom is within NlParams::dstar of the list's build positions (rows certain to be outside the
+    // cutoff can be skipped, rows certain to be inside need no test)
+    *sys.flags = flags | (sm.geom->disp2 <= np.dstar * np.dstar ? 4 : 0);
     *sys.done = 0;
   }
 }
@@ -161,10 +163,11 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_pair(const PotParams *
   tile_prologue(P, sys, sm, a.tiles, i0, i1, false);
   double acc[2] = {0.0, 0.0};
   double *F = a.F + static_cast<size_t>(s) * a.strideR;
+  const bool near_build = (*sys.flags & 4) != 0;
   if (P.kind == POT_MORSE_PT)
-    pair_pass<POT_MORSE_PT>(P, sys, sm, a.lpa, i0, i1, F, acc);
+    pair_pass_inl<POT_MORSE_PT>(P, sys, sm, a.lpa, i0, i1, F, acc, near_build);
   else
-    pair_pass<POT_LJ>(P, sys, sm, a.lpa, i0, i1, F, acc);
+    pair_pass_inl<POT_LJ>(P, sys, sm, a.lpa, i0, i1, F, acc, near_build);
   tile_epilogue(sys, sm, a.tiles, acc, 0, a.U + s, true);
 }
 

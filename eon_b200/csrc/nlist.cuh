@@ -454,13 +454,16 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
                 bad_shift = true;
                 continue;
               }
-              emit(pack_nbr(j, Sx, Sy, Sz), d2 < np.rc_core2);
+              if (sys.nbr2 && sys.cls)
+                emit3(pack_nbr(j, Sx, Sy, Sz), d2);
+              else
+                emit(pack_nbr(j, Sx, Sy, Sz), d2 < np.rc_core2);
             }
           }
         }
       }
     }
-    if (np.mode == NL_MIC) {
+    if (np.mode == NL_MIC || (sys.nbr2 && sys.cls)) {
       if (n0 + n1 + n2 <= K)
         for (int t = 0; t < n1; t++)
           sys.nbr[static_cast<size_t>(n0 + t) * Np + i] = sys.nbr2[static_cast<size_t>(t) * Np + i];

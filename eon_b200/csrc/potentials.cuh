@@ -78,6 +78,67 @@ __device__ __forceinline__ double rsqrt_f64(double x) {
 #endif
 }
 
+// Exp arguments stay far above the underflow guard of exp_tab for any physical row (the host checks
+// PotParams::eam_fast_ok), so the guard is dropped here.
+__device__ __forceinline__ double exp_tab_fast(double x, const double *T) {
+  const double kInv = 184.6649652337873;
+  const double kShift = 6755399441055744.0;
+  const double kLn2Hi = 6.93147180369123816490e-01 / 128.0;
+  const double kLn2Lo = 1.90821492927058770002e-10 / 128.0;
+  double kd = fma(x, kInv, kShift);
+#ifdef EONB200_EMU
+  long long ki;
+  memcpy(&ki, &kd, 8);
+#else
+  const long long ki = __double_as_longlong(kd);
+#endif
+  kd -= kShift;
+  double r = fma(kd, -kLn2Hi, x);
+  r = fma(kd, -kLn2Lo, r);
+  const int k = static_cast<int>(ki);
+  const double t = T[k & 127];
+  double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  const double res = fma(t, q * r, t);
+#ifdef EONB200_EMU
+  const long long e = static_cast<long long>(k >> 7) << 52;
+  long long bits;
+  memcpy(&bits, &res, 8);
+  bits += e;
+  double out;
+  memcpy(&out, &bits, 8);
+  return out;
+#else
+  // times 2^(k >> 7): one 32-bit add on the exponent word
+  return __hiloint2double(__double2hiint(res) + ((k >> 7) << 20), __double2loint(res));
+#endif
+}
+
+// 1/sqrt(x) for normal positive x (pair distances): hardware seed + one third-order step, without the library's
+// special-case branch.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+#ifdef EONB200_EMU
+  return 1.0 / sqrt(x);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(x * y, -y, 1.0);
+  const double c = fma(e, 0.375, 0.5);
+  return fma(c * e, y, y);
+#endif
+}
+
+// d = r_i - r_j folded by the image recorded at build time (image table valid: Geom::tab_ok).
+__device__ __forceinline__ void mic_vec_tab(const Smem &sm, int code, const double4 &pi, const double4 &pj, double &dx,
+                                            double &dy, double &dz) {
+  const double4 sh = sm.sh27[static_cast<unsigned>(code) >> kNbrIndexBits];
+  dx = (pi.x - pj.x) + sh.x;
+  dy = (pi.y - pj.y) + sh.y;
+  dz = (pi.z - pj.z) + sh.z;
+}
+
 // ---- pair vectors --------------------------------------------------------------------------------------
 // NL_VESIN: v = (r_j - r_i) + S.H, un-fused (vesin-single-build.cpp:1199-1202).
 __device__ __forceinline__ void vesin_vec(const Smem &sm, int code, const double4 &pi, const double4 &pj, double &vx,
@@ -125,9 +186,11 @@ __device__ __forceinline__ void mic_vec(const Smem &sm, int code, const double4 
 // ---- LJ / Morse ------------------------------------------------------------------------------------------
 // Atoms [i0, i1) of the walker staged in sm.pos; forces to F[3 (i - fbase)...] (shared or global).
 // acc[0] += energy share, acc[1] += ordered pairs (per-lane partials, reduced by the caller).
-template <int KIND>
-__device__ EONB200_NOINLINE void pair_pass(const PotParams &P, const SysView &sys, const Smem &sm, int lpa, int i0, int i1,
-                                          double *F, double (&acc)[2]) {
+template <int KIND, bool FASTEXP>
+// near_build: every atom within NlParams::dstar of the list's build positions -- the leading sure-in rows skip the
+// cutoff test, the trailing sure-out rows are not visited.
+__device__ __forceinline__ void pair_pass_body(const PotParams &P, const SysView &sys, const Smem &sm, int lpa, int i0, int i1,
+                                               double *F, double (&acc)[2], bool near_build) {
   const int group = threadIdx.x / lpa, gl = threadIdx.x % lpa, ngroups = blockDim.x / lpa;
   const double rc2 = P.cutoff2, eshift = P.eshift;
   const double De = P.morse_De, ma = P.morse_a, re = P.morse_re;
@@ -138,34 +201,53 @@ __device__ EONB200_NOINLINE void pair_pass(const PotParams &P, const SysView &sy
     double fx = 0.0, fy = 0.0, fz = 0.0;
     if (i < i1) {
       const double4 pi = sm.pos[i];
-      const int n = sys.cnt[i];
-      for (int k = gl; k < n; k += lpa) {
-        const int code = sys.nbr[static_cast<size_t>(k) * sys.Np + i];
-        const double4 pj = sm.pos[code & kNbrIndexMask];
-        double vx, vy, vz;
-        vesin_vec(sm, code, pi, pj, vx, vy, vz);
-        const double d2 = norm2_rn(vx, vy, vz);
-        if (!(d2 < rc2)) continue;
-        double e, s;  // pair energy and (dU/dr)/r
-        if (KIND == POT_MORSE_PT) {
-          const double invr = rsqrt_f64(d2);
-          const double r = d2 * invr;
-          const double ex = exp_tab(-ma * (r - re), sm.exp_tab);
-          const double d = 1.0 - ex;
-          e = De * d * d - De;
-          s = (2.0 * De * ma * d * ex) * invr;
-        } else {
-          const double sr2 = psi2 / d2;
-          const double sr6 = sr2 * sr2 * sr2;
-          e = 4.0 * u0 * (sr6 * sr6 - sr6);
-          s = -24.0 * u0 * (2.0 * sr6 * sr6 - sr6) / d2;
+      int n = sys.cnt[i], n_sure = 0;
+      if (near_build && sys.cls) {
+        const int c = sys.cls[i];
+        n_sure = c & 0xffff;
+        n = n_sure + (c >> 16);
+      }
+      // eight candidate codes of this lane in flight at a time (the loads are a dependent L2 round trip otherwise)
+      constexpr int kPairBatch = 8;
+      const size_t Np = static_cast<size_t>(sys.Np);
+      for (int k0 = gl; k0 < n; k0 += kPairBatch * lpa) {
+        int cb[kPairBatch];
+#pragma unroll
+        for (int u = 0; u < kPairBatch; u++) {
+          const int kk = k0 + u * lpa;
+          cb[u] = kk < n ? sys.nbr[static_cast<size_t>(kk) * Np + i] : -1;
         }
-        // F_i = +(dU/dr) v / r with v = r_j - r_i; each unordered pair is seen from both ends
-        fx += s * vx;
-        fy += s * vy;
-        fz += s * vz;
-        e_acc += 0.5 * (e - eshift);
-        n_acc += 1.0;
+#pragma unroll
+        for (int u = 0; u < kPairBatch; u++) {
+          const int code = cb[u];
+          if (code == -1) continue;
+          const int k = k0 + u * lpa;
+          const double4 pj = sm.pos[code & kNbrIndexMask];
+          double vx, vy, vz;
+          vesin_vec(sm, code, pi, pj, vx, vy, vz);
+          const double d2 = norm2_rn(vx, vy, vz);
+          if (k >= n_sure && !(d2 < rc2)) continue;
+          double e, s;  // pair energy and (dU/dr)/r
+          if (KIND == POT_MORSE_PT) {
+            const double invr = rsqrt_fast(d2);
+            const double r = d2 * invr;
+            const double ex = FASTEXP ? exp_tab_fast(-ma * (r - re), sm.exp_tab) : exp_tab(-ma * (r - re), sm.exp_tab);
+            const double d = 1.0 - ex;
+            e = De * d * d - De;
+            s = (2.0 * De * ma * d * ex) * invr;
+          } else {
+            const double sr2 = psi2 / d2;
+            const double sr6 = sr2 * sr2 * sr2;
+            e = 4.0 * u0 * (sr6 * sr6 - sr6);
+            s = -24.0 * u0 * (2.0 * sr6 * sr6 - sr6) / d2;
+          }
+          // F_i = +(dU/dr) v / r with v = r_j - r_i; each unordered pair is seen from both ends
+          fx += s * vx;
+          fy += s * vy;
+          fz += s * vz;
+          e_acc += 0.5 * (e - eshift);
+          n_acc += 1.0;
+        }
       }
     }
     fx = group_sum_rt(fx, lpa);
@@ -179,6 +261,22 @@ __device__ EONB200_NOINLINE void pair_pass(const PotParams &P, const SysView &sy
   }
   acc[0] += e_acc;
   acc[1] += n_acc;
+}
+
+template <int KIND>
+__device__ __forceinline__ void pair_pass_inl(const PotParams &P, const SysView &sys, const Smem &sm, int lpa, int i0, int i1,
+                                              double *F, double (&acc)[2], bool near_build) {
+  if (KIND == POT_MORSE_PT && P.eam_fast_ok)  // unguarded exp: decided once, outside the pair loop
+    pair_pass_body<KIND, true>(P, sys, sm, lpa, i0, i1, F, acc, near_build);
+  else
+    pair_pass_body<KIND, false>(P, sys, sm, lpa, i0, i1, F, acc, near_build);
+}
+
+// Out-of-line instance for the resident walker kernel (its Smem view lives in the walker context anyway).
+template <int KIND>
+__device__ EONB200_NOINLINE void pair_pass(const PotParams &P, const SysView &sys, const Smem &sm, int lpa, int i0, int i1,
+                                          double *F, double (&acc)[2]) {
+  pair_pass_inl<KIND>(P, sys, sm, lpa, i0, i1, F, acc, sm.geom->disp2 <= 0.0625 * P.skin * P.skin);
 }
 
 // ---- EAM ------------------------------------------------------------------------------------------------------
@@ -361,67 +459,6 @@ __device__ EONB200_NOINLINE void eam_pass2(const PotParams &P, const SysView &sy
 //            g'(r)/r goes to sys.pairA (L2 resident, 8 B per pair); the Morse pair force is applied right away;
 //            then F(rho_i), F'(rho_i) by Horner (EAM.cpp:349-365);
 //   force    F_i -= sum_j (F'_i + F'_j) g'(r)/r d  -- no transcendental, square root or division.
-// Exp arguments stay far above the underflow guard of exp_tab for any physical row (the host checks
-// PotParams::eam_fast_ok), so the guard is dropped here.
-__device__ __forceinline__ double exp_tab_fast(double x, const double *T) {
-  const double kInv = 184.6649652337873;
-  const double kShift = 6755399441055744.0;
-  const double kLn2Hi = 6.93147180369123816490e-01 / 128.0;
-  const double kLn2Lo = 1.90821492927058770002e-10 / 128.0;
-  double kd = fma(x, kInv, kShift);
-#ifdef EONB200_EMU
-  long long ki;
-  memcpy(&ki, &kd, 8);
-#else
-  const long long ki = __double_as_longlong(kd);
-#endif
-  kd -= kShift;
-  double r = fma(kd, -kLn2Hi, x);
-  r = fma(kd, -kLn2Lo, r);
-  const int k = static_cast<int>(ki);
-  const double t = T[k & 127];
-  double q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-  q = fma(q, r, 1.0 / 6.0);
-  q = fma(q, r, 0.5);
-  q = fma(q, r, 1.0);
-  const double res = fma(t, q * r, t);
-#ifdef EONB200_EMU
-  const long long e = static_cast<long long>(k >> 7) << 52;
-  long long bits;
-  memcpy(&bits, &res, 8);
-  bits += e;
-  double out;
-  memcpy(&out, &bits, 8);
-  return out;
-#else
-  // times 2^(k >> 7): one 32-bit add on the exponent word
-  return __hiloint2double(__double2hiint(res) + ((k >> 7) << 20), __double2loint(res));
-#endif
-}
-
-// 1/sqrt(x) for normal positive x (pair distances): hardware seed + one third-order step, without the library's
-// special-case branch.
-__device__ __forceinline__ double rsqrt_fast(double x) {
-#ifdef EONB200_EMU
-  return 1.0 / sqrt(x);
-#else
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double e = fma(x * y, -y, 1.0);
-  const double c = fma(e, 0.375, 0.5);
-  return fma(c * e, y, y);
-#endif
-}
-
-// d = r_i - r_j folded by the image recorded at build time (image table valid: Geom::tab_ok).
-__device__ __forceinline__ void mic_vec_tab(const Smem &sm, int code, const double4 &pi, const double4 &pj, double &dx,
-                                            double &dy, double &dz) {
-  const double4 sh = sm.sh27[static_cast<unsigned>(code) >> kNbrIndexBits];
-  dx = (pi.x - pj.x) + sh.x;
-  dy = (pi.y - pj.y) + sh.y;
-  dz = (pi.z - pj.z) + sh.z;
-}
-
 struct EamLane {   // what one atom's thread carries from the density pass into the force pass
   double fx, fy, fz;  // Morse pair part of the force, accumulated in the density pass
   double dfd;         // F'(rho_i)
