@@ -187,7 +187,7 @@ def run_reference(args):
         return 0
     struct, sets = force_workload(0)
     positions = sets[0]
-    per_step_budget = 4.0
+    per_step_budget = min(4.0, 100.0 / max(1, args.steps))  # the whole K-step run stays within a couple of minutes
     times = []
     evals = 0
     info = None
