@@ -3,8 +3,15 @@ sys.path.insert(0, os.getcwd())
 import bench
 from eon_b200 import B200Potential
 tiles = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-struct, sets = bench.force_workload(0)
-N, W = struct.n_atoms, 256
+if "c3" in sys.argv:  # BASELINE.json configs[2] geometry, two rounds of CTAs
+    from eon_b200 import workloads as WL
+    struct = WL.fcc_vacancy(8, 3.615, 13)
+    W = 148
+    sets = np.stack([WL.jitter(struct.positions, W, 0.05, seed=1000 * k) for k in range(4)])
+else:
+    struct, sets = bench.force_workload(0)
+    W = 256
+N = struct.n_atoms
 dev = torch.device("cuda", 0)
 pot = B200Potential("eam", device=0, skin=1.0, tiles_override=tiles)
 d_R = torch.from_numpy(sets.reshape(4, W, 3 * N)).to(dev)
@@ -40,7 +47,7 @@ sm = c[:, 1].astype(int)
 print("ctas per SM: min %d max %d" % (np.bincount(sm).min(), np.bincount(sm).max()))
 
 # resident search: distribution of force calls per walker (critical path of the launch)
-if len(sys.argv) > 2:
+if "search" in sys.argv:
     from eon_b200 import Walkers, search_params, workloads as WL
     s2, scale = bench.search_workload()
     spot = B200Potential("eam", device=0, skin=1.0, conservative=True)
