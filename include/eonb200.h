@@ -65,8 +65,8 @@ typedef struct EonB200Config {
   double skin;            /* Verlet skin of the cached neighbour lists, Angstrom; < 0 -> 1.0;
                              0 -> exact list rebuilt on every evaluation                       */
   int threads_per_walker; /* CTA size override of the resident walker kernel, 0 -> from nAtoms  */
-  int tiles_override;     /* CTAs per system in the stateless force passes, 0 -> chosen so that
-                             nSystems x tiles covers the SMs a few times                       */
+  int tiles_override;     /* CTAs per system: cluster size of the fused EAM kernel (1..8), tiles of the LJ / Morse
+                             force pass (1..16); 0 -> chosen from nSystems and nAtoms                    */
   int lpa_override;       /* lanes sharing one atom's neighbour row (1, 2, 4, 8), 0 -> automatic */
   int pin_host_buffers;   /* 1: when the systems of a force_batch call lie back to back in host memory (positions[s]
                              = positions[0] + s * 3N, same for forces), page-lock those ranges once
