@@ -415,24 +415,27 @@ def run_b200(args):
             search["cpu_baseline"] = cpu_s
         wk.close()
         # A launch of 256 walkers lasts as long as its slowest walker (a chain of ~10^3 dependent force calls) and
-        # leaves most SMs idle; the same job with four times the walkers shows the throughput the device has left.
-        W4 = 4 * W
-        wk4 = Walkers(spot, s2.atomic_nrs, s2.fixed, s2.cell, np.broadcast_to(Rmin.reshape(1, -1), (W4, 3 * N)).copy())
-        R4 = np.empty((W4, N, 3))
-        M4 = np.empty((W4, N, 3))
-        for k in range(W4):
-            R4[k], M4[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"], cfg["seed"] + 4 * first + k)
-        wk4.set(positions=R4, modes=M4)
-        barrier()
-        wk4.saddle_search(prm, E0)
-        ms4 = reduce_max(wk4.last_ms)
-        h4 = wk4.harvest(geometry=False)
-        good4 = reduce_sum(float((h4.status == 0).sum()))
-        fc4 = reduce_sum(float(h4.force_calls.sum()))
-        search["walkers_x4"] = {"walkers": int(W4 * world), "ms": ms4, "status_good": int(good4),
-                                "searches_per_hour": good4 / (ms4 * 1e-3) * 3600.0,
-                                "atom_force_evals_per_s": fc4 * N / (ms4 * 1e-3)}
-        wk4.close()
+        # leaves most SMs idle after the median walker has finished; the same job with 4x and 16x the walkers shows
+        # the throughput the device reaches once finished slots are refilled.
+        for mult in (4, 16):
+            Wm = mult * W
+            wkm = Walkers(spot, s2.atomic_nrs, s2.fixed, s2.cell, np.broadcast_to(Rmin.reshape(1, -1), (Wm, 3 * N)).copy())
+            Rm = np.empty((Wm, N, 3))
+            Mm = np.empty((Wm, N, 3))
+            for k in range(Wm):
+                Rm[k], Mm[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"],
+                                           cfg["seed"] + mult * first + k)
+            wkm.set(positions=Rm, modes=Mm)
+            barrier()
+            wkm.saddle_search(prm, E0)
+            msm = reduce_max(wkm.last_ms)
+            hm = wkm.harvest(geometry=False)
+            goodm = reduce_sum(float((hm.status == 0).sum()))
+            fcm = reduce_sum(float(hm.force_calls.sum()))
+            search[f"walkers_x{mult}"] = {"walkers": int(Wm * world), "ms": msm, "status_good": int(goodm),
+                                          "searches_per_hour": goodm / (msm * 1e-3) * 3600.0,
+                                          "atom_force_evals_per_s": fcm * N / (msm * 1e-3)}
+            wkm.close()
         spot.close()
 
     # BASELINE.json configs[2] as a second data point: 4096 walkers of the 2047-atom vacancy cell sharded over the
