@@ -674,6 +674,8 @@ __device__ inline void setup_ctx(Ctx &c, const PotParams *Pp, const NlBatch &nl,
   c.phase = 0;
   c.prm = prm_sh;
   c.force_calls = 0;
+  c.tables_ready = 0;
+  c.row_flags = -1;
   c.failed = 0;
   c.remove_net_force = wl.remove_net_force;
   c.ws = wa.ws ? wa.ws + static_cast<size_t>(w) * wa.ws_stride : nullptr;

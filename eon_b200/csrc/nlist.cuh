@@ -90,7 +90,10 @@ __device__ inline void fill_sh27(const Smem &sm, double Lx, double Ly, double Lz
 //   NL_VESIN: raw coordinates.   NL_MIC: EAM.cpp:56-90 shifted / wrapped coordinates.
 // Also fills the shift tables and the exp table, and returns (to every thread) the largest squared
 // displacement of the prepared positions from the ones the cached list was built with.
-__device__ inline double prepare_positions(const NlParams &np, const SysView &sys, Smem &sm, const double *exp_tab_g) {
+// tables_ready: box geometry, exp table and image tables in shared memory are still valid from an earlier call with
+// the same box (resident walkers evaluate hundreds of configurations of one cell): only the coordinate shift is redone.
+__device__ inline double prepare_positions(const NlParams &np, const SysView &sys, Smem &sm, const double *exp_tab_g,
+                                           bool tables_ready = false) {
   const int N = sys.N;
   const bool have_list = *sys.state != 0;
   double v[3] = {1e300, 1e300, 1e300};
@@ -103,7 +106,14 @@ __device__ inline double prepare_positions(const NlParams &np, const SysView &sy
     const int op[3] = {RED_MIN, RED_MIN, RED_MIN};
     block_reduce<3>(v, op, sm.red);
   }
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && tables_ready) {
+    Geom &g = *sm.geom;
+    for (int k = 0; k < 3; k++) {
+      const double lo = v[k] > 0.0 ? 0.0 : v[k];
+      g.lo[k] = np.mode == NL_MIC ? fabs(lo) : 0.0;
+    }
+  }
+  if (threadIdx.x == 0 && !tables_ready) {
     Geom &g = *sm.geom;
     for (int k = 0; k < 9; k++) g.H[k] = sys.box[k];
     g.ok = invert3(g.H, g.Hinv) ? 1 : 0;
@@ -120,18 +130,21 @@ __device__ inline double prepare_positions(const NlParams &np, const SysView &sy
       g.tab_ok = (g.H[1] == 0.0 && g.H[2] == 0.0 && g.H[3] == 0.0 && g.H[5] == 0.0 && g.H[6] == 0.0 && g.H[7] == 0.0) ? 1 : 0;
     }
   }
-  for (int k = threadIdx.x; k < 128; k += blockDim.x) sm.exp_tab[k] = exp_tab_g[k];
+  if (!tables_ready)
+    for (int k = threadIdx.x; k < 128; k += blockDim.x) sm.exp_tab[k] = exp_tab_g[k];
   __syncthreads();
   const Geom &g = *sm.geom;
-  for (int k = threadIdx.x; k < 48; k += blockDim.x) {
-    const int axis = k >> 4;
-    const double sft = static_cast<double>((k & 15) - 8);
-    const double len = g.H[4 * axis];
-    // NL_MIC: d = r_i - r_j, fold +1 means "dx > L/2 -> dx -= L" (EAM.cpp:157-168); NL_VESIN: + s * H_kk
-    const double val = np.mode == NL_MIC ? -mul_rn(sft, len) : mul_rn(sft, len);
-    (axis == 0 ? sm.shx : (axis == 1 ? sm.shy : sm.shz))[k & 15] = val;
+  if (!tables_ready) {
+    for (int k = threadIdx.x; k < 48; k += blockDim.x) {
+      const int axis = k >> 4;
+      const double sft = static_cast<double>((k & 15) - 8);
+      const double len = g.H[4 * axis];
+      // NL_MIC: d = r_i - r_j, fold +1 means "dx > L/2 -> dx -= L" (EAM.cpp:157-168); NL_VESIN: + s * H_kk
+      const double val = np.mode == NL_MIC ? -mul_rn(sft, len) : mul_rn(sft, len);
+      (axis == 0 ? sm.shx : (axis == 1 ? sm.shy : sm.shz))[k & 15] = val;
+    }
+    fill_sh27(sm, g.H[0], g.H[4], g.H[8]);
   }
-  fill_sh27(sm, g.H[0], g.H[4], g.H[8]);
   double disp2 = 0.0;
   const double L[3] = {g.H[0], g.H[4], g.H[8]};  // EAM.cpp:31 reads the diagonal only
   for (int i = threadIdx.x; i < N; i += blockDim.x) {
@@ -496,9 +509,9 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
 // Stage positions (sm.stage raw, sm.pos in the predicate's layout) and decide whether the cached candidate
 // list still covers them (Verlet check).  CTA-uniform result; every thread has read *sys.state on return.
 __device__ inline bool nl_stage_check(const NlParams &np, const SysView &sys, Smem &sm, uint32_t &phase,
-                                      bool force_rebuild, const double *exp_tab_g) {
+                                      bool force_rebuild, const double *exp_tab_g, bool tables_ready = false) {
   stage_raw_positions(sys, sm, phase);
-  const double disp2 = prepare_positions(np, sys, sm, exp_tab_g);
+  const double disp2 = prepare_positions(np, sys, sm, exp_tab_g, tables_ready);
   if (threadIdx.x == 0) sm.geom->disp2 = disp2;
   const bool have = *sys.state != 0;
   const double lim = 0.5 * np.skin;
@@ -528,8 +541,8 @@ __device__ EONB200_NOINLINE int nl_rebuild(const NlParams &np, const SysView &sy
 // On return sm.pos holds the positions in the predicate's layout and sm.stage the raw ones.
 // Returns (to all threads) the largest row fill of a rebuild (> sys.K: the list is truncated), 0 if reused.
 __device__ inline int nl_ensure(const NlParams &np, const SysView &sys, Smem &sm, uint32_t &phase,
-                                bool force_rebuild, const double *exp_tab_g) {
-  const bool rebuild = nl_stage_check(np, sys, sm, phase, force_rebuild, exp_tab_g);
+                                bool force_rebuild, const double *exp_tab_g, bool tables_ready = false) {
+  const bool rebuild = nl_stage_check(np, sys, sm, phase, force_rebuild, exp_tab_g, tables_ready);
   int row_max = 0;
   if (rebuild) {
     if (threadIdx.x == 0) sm.geom->disp2 = 0.0;  // the fresh list is built from these very positions

@@ -719,11 +719,18 @@ __device__ EONB200_NOINLINE double walker_forces_eam_fast(const PotParams &P, co
 
 // Energy + raw forces (into sm.stage) of the whole walker staged in sm.pos -- the resident kernels' path.
 // Returns NaN if an element has no EAM row (the reference throws 14324, EAM.cpp:116-123).
-__device__ inline double walker_forces(const PotParams &P, const SysView &sys, Smem &sm, int lpa) {
+// row_flags_cache (optional): the walker's atomic numbers never change, so its element rows are assigned once.
+__device__ inline double walker_forces(const PotParams &P, const SysView &sys, Smem &sm, int lpa, int *row_flags_cache = nullptr) {
   double acc[2] = {0.0, 0.0};
   const int N = sys.N;
   if (P.kind == POT_EAM) {
-    const int flags = eam_assign_rows(P, sys, sm.rowid, sm.red);
+    int flags;
+    if (row_flags_cache && *row_flags_cache >= 0) {
+      flags = *row_flags_cache;
+    } else {
+      flags = eam_assign_rows(P, sys, sm.rowid, sm.red);
+      if (row_flags_cache) *row_flags_cache = flags;
+    }
     if (flags & 2) {
       for (int k = threadIdx.x; k < 3 * N; k += blockDim.x) sm.stage[k] = 0.0;
       __syncthreads();

@@ -79,6 +79,8 @@ struct Ctx {
   uint32_t phase;
   const EonB200SearchParams *prm;  // shared memory copy
   long long force_calls;
+  int tables_ready;  // shared-memory box geometry / exp / image tables are valid (set by the first evaluation)
+  int row_flags;     // eam_assign_rows result of this walker's (constant) atomic numbers, -1 = not computed yet
   int failed;  // potential failure (NaN energy / truncated neighbour list)
   int remove_net_force;
   double *ws;
@@ -143,8 +145,10 @@ __device__ inline void matter_set_positions_free(const Ctx &c, MatterS &m, const
 __device__ EONB200_NOINLINE void matter_compute(Ctx &c, MatterS &m) {
   if (!m.dirty) return;
   c.sys.R = m.pos;
-  if (nl_ensure(c.np, c.sys, c.sm, c.phase, false, c.P->exp_tab) > c.sys.K) c.failed = 1;  // truncated list
-  double U = walker_forces(*c.P, c.sys, c.sm, c.lpa);
+  // (box geometry / tables and the element rows of the walker are computed on its first evaluation only)
+  if (nl_ensure(c.np, c.sys, c.sm, c.phase, false, c.P->exp_tab, c.tables_ready != 0) > c.sys.K) c.failed = 1;  // truncated list
+  c.tables_ready = 1;
+  double U = walker_forces(*c.P, c.sys, c.sm, c.lpa, &c.row_flags);
   if (U != U) c.failed = 1;
   c.force_calls++;
   m.energy = U;
