@@ -1044,7 +1044,67 @@ __device__ EONB200_NOINLINE int lbfgs_step(Ctx &c, OptState &s, Objective &o, do
       have_step = true;
     }
   }
+  constexpr int kQr = 4;  // elements of q a thread keeps in registers during the two-loop recursion
   if (!have_step) {
+    if (n <= kQr * static_cast<int>(blockDim.x)) {  // (bodies below keep their original indentation)
+    // Two-loop recursion with q in registers: element k = tid + u * blockDim of every vector belongs to one thread,
+    // so each history pair costs one pass over (s_i, y_i) and one block reduction instead of three passes over q in
+    // the workspace and three barriers.  Same products, same summation order as the general version below.
+    const int loopmax = s.hist;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double qr[kQr];
+#pragma unroll
+    for (int u = 0; u < kQr; u++) {
+      const int k = tid + u * nt;
+      qr[u] = k < n ? -f[k] : 0.0;
+    }
+    for (int i = loopmax - 1; i >= 0; i--) {
+      const int slot = (s.hist_begin + i) % memory;
+      const double *si = hs + hstride * slot, *yi = hy + hstride * slot;
+      double sv[kQr], yv[kQr];
+#pragma unroll
+      for (int u = 0; u < kQr; u++) {
+        const int k = tid + u * nt;
+        sv[u] = k < n ? si[k] : 0.0;
+        yv[u] = k < n ? yi[k] : 0.0;
+      }
+      double part = 0.0;
+#pragma unroll
+      for (int u = 0; u < kQr; u++)
+        if (tid + u * nt < n) part += sv[u] * qr[u];
+      const double a = rho[slot] * block_sum1(part, c.sm.red);
+      if (tid == 0) alph[slot] = a;
+#pragma unroll
+      for (int u = 0; u < kQr; u++) qr[u] -= a * yv[u];
+    }
+#pragma unroll
+    for (int u = 0; u < kQr; u++) qr[u] *= H0;
+    for (int i = 0; i < loopmax; i++) {
+      const int slot = (s.hist_begin + i) % memory;
+      const double *si = hs + hstride * slot, *yi = hy + hstride * slot;
+      double sv[kQr], yv[kQr];
+#pragma unroll
+      for (int u = 0; u < kQr; u++) {
+        const int k = tid + u * nt;
+        sv[u] = k < n ? si[k] : 0.0;
+        yv[u] = k < n ? yi[k] : 0.0;
+      }
+      double part = 0.0;
+#pragma unroll
+      for (int u = 0; u < kQr; u++)
+        if (tid + u * nt < n) part += yv[u] * qr[u];
+      const double b = rho[slot] * block_sum1(part, c.sm.red);
+      const double a = alph[slot];
+#pragma unroll
+      for (int u = 0; u < kQr; u++) qr[u] += (a - b) * sv[u];
+    }
+#pragma unroll
+    for (int u = 0; u < kQr; u++) {
+      const int k = tid + u * nt;
+      if (k < n) q[k] = qr[u];
+    }
+    __syncthreads();
+    } else {
     const int loopmax = s.hist;
     VLOOP(k, n) q[k] = -f[k];
     __syncthreads();
@@ -1065,6 +1125,7 @@ __device__ EONB200_NOINLINE int lbfgs_step(Ctx &c, OptState &s, Objective &o, do
       const double a = alph[slot];
       VLOOP(k, n) q[k] += (a - b) * si[k];
       __syncthreads();
+    }
     }
     // d = -z
     double rr[3] = {0.0, 0.0, 0.0};  // d.d, f.f, d.f
