@@ -575,8 +575,8 @@ __device__ __forceinline__ void eam_fast_density(const PotParams &P, const EamRo
     const double r6 = r4 * r2;
     dens = fma(r6, rho_pair, dens);
     const double u = fma(nb2x1024, e2, nb1 * e1);
-    const double gder = fma(6.0 * (r4 * r), rho_pair, r6 * u);
-    *rowA = gder * invr;
+    // g'(r)/r = [6 r^5 rho_pair + r^6 u] / r = r^4 (6 rho_pair + r u)
+    *rowA = r4 * fma(r, u, 6.0 * rho_pair);
     rowA += step;
     const double dm = 1.0 - ex;
     const double nB = (nK2 * dm) * (ex * invr);  // -(+-phi'(r)/r)
