@@ -146,7 +146,7 @@ class Walkers:
         self.saddle_search(prm, reactant_energies)
         saddle = self.harvest()
         out = {"saddle": saddle}
-        for name, sign in (("min1", +1.0), ("min2", -1.0)):
+        for name, sign in (("min1", -1.0), ("min2", +1.0)):  # ProcessSearchJob.cpp:190-202: min1 = saddle - offset * mode
             self.set(positions=saddle.positions, modes=saddle.modes)
             self.displace_along_mode(sign * offset)
             self.relax(prm)
