@@ -477,6 +477,50 @@ def run_b200(args):
         pot3.close()
         del sets3, d_Z3, d_box3, d_F3, d_U3
 
+    # BASELINE.json configs[3] as a third data point: examples/akmc-pt, Morse_Pt, dimer + CG saddle searches from the
+    # least-coordinated atoms followed by the minimisation of both minima per walker, classified like ProcessSearchJob
+    c4 = None
+    if not args.no_c4:
+        from eon_b200 import displace as DP, process_search as PS
+        cfg4 = dict(WL.AKMC_PT)
+        s4 = WL.load_structure(cfg4["fixture"])
+        N4 = s4.n_atoms
+        mpot = B200Potential("morse_pt", device=local_rank, skin=args.skin)
+        wk4 = Walkers(mpot, s4.atomic_nrs, s4.fixed, s4.cell, np.broadcast_to(s4.positions.reshape(1, -1), (W, 3 * N4)).copy())
+        wk4.relax(search_params(opt_method=1, opt_converged_force=1e-4))
+        hmin4 = wk4.harvest()
+        Rmin4, E04 = hmin4.positions[0].reshape(N4, 3), float(hmin4.energies[0])
+        cand = DP.min_coordinated_atoms(mpot, Rmin4, s4.cell, s4.fixed, 3.3)
+        R4 = np.empty((W, N4, 3))
+        M4 = np.empty((W, N4, 3))
+        for k in range(W):
+            rng = np.random.default_rng(cfg4["seed"] + first + k)
+            R4[k], M4[k] = WL.displace(s4, Rmin4, int(cand[int(rng.integers(len(cand)))]), cfg4["radius"], cfg4["magnitude"],
+                                       cfg4["seed"] + first + k)
+        wk4.set(positions=R4, modes=M4)
+        prm4 = search_params(**cfg4["search"])
+        barrier()
+        t0 = time.perf_counter()
+        out4 = wk4.process_search(prm4, E04)
+        torch.cuda.synchronize()
+        wall4 = reduce_max(time.perf_counter() - t0)
+        res4 = PS.process_results(out4, Rmin4, s4.cell, s4.fixed, max_energy=10.0, displacement_positions=R4,
+                                  potential_type="MORSE_PT")
+        st4 = np.array([r["termination_reason"] for r in res4])
+        good4 = reduce_sum(float((st4 == 0).sum()))
+        fc4 = reduce_sum(float(sum(r["total_force_calls"] for r in res4)))
+        barr = [r["barrier_reactant_to_product"] for r in res4 if r["termination_reason"] == 0]
+        c4 = {"workload": "examples/akmc-pt: 343 Pt atoms (168 fixed), Morse_Pt, least-coordinated epicentres, sigma 0.1 A "
+                          "within 3.3 A, dimer + CG 1e-3, then both minima relaxed per walker; host classification as "
+                          "ProcessSearchJob (connectivity, barriers)",
+              "walkers": int(W * world), "wall_s": wall4, "processes_found": int(good4),
+              "process_searches_per_hour": good4 / wall4 * 3600.0,
+              "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(st4, return_counts=True))},
+              "force_calls": int(fc4), "atom_force_evals_per_s": fc4 * N4 / wall4,
+              "barrier_eV_min_median": [float(np.min(barr)), float(np.median(barr))] if barr else None}
+        wk4.close()
+        mpot.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _, _ = cpu_force_baseline(struct, sets[0], 1.0, True)
@@ -491,7 +535,7 @@ def run_b200(args):
                 "gpu_launches": int(launches), "roofline": roofline,
                 "extra": {"wall_s_timed_region": t_wall, "value_hot_l2": units / world / (t_hot * 1e-3),
                           "value_fresh_list_every_step": units / world / (t_fresh * 1e-3),
-                          "fp64_peak_tflops_measured": fp64_peak / 1e12, "c3": c3},
+                          "fp64_peak_tflops_measured": fp64_peak / 1e12, "c3": c3, "c4": c4},
                 "search": search}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -513,6 +557,7 @@ def main():
     ap.add_argument("--lpa", type=int, default=0, help="lanes per atom (0 = automatic)")
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the 4096 x 2047-atom data point")
+    ap.add_argument("--no-c4", action="store_true", help="skip the akmc-pt Morse process-search data point")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
