@@ -30,7 +30,8 @@ struct PotParams {
   double morse_De, morse_a, morse_re;
   int n_rows;
   int eam_conservative;
-  int eam_fast_ok;        // every row keeps its exp arguments inside exp_tab_fast's range (set by the host)
+  int eam_fast_ok;        // every EAM row (or the Morse parameters) keeps its exp arguments inside exp_tab_fast's
+                          // range (set by the host)
   const double *exp_tab;  // [128] 2^(j/128), device memory (table of the exp used by the pair loops)
   EamRowDev rows[kMaxEamRows];
 };
