@@ -41,8 +41,8 @@ JITTER = 0.05
 N_POSITION_SETS = 4
 FLUSH_BYTES = 512 << 20  # > 4x the 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_eam_fused launch of this workload (ncu --set full capture)
-NCU_DRAM_BYTES_PER_LAUNCH = 30.7e6
-NCU_TRAFFIC_SOURCE = ("profiles/r1c_fused_ncu_raw_selected.csv: 27.1 MB read + 3.6 MB written per launch (cold L2); the "
+NCU_DRAM_BYTES_PER_LAUNCH = 31.2e6
+NCU_TRAFFIC_SOURCE = ("profiles/r1c_fused_ncu_raw_selected.csv: 27.1 MB read + 4.0 MB written per launch (cold L2); the "
                       "64 N + 8 P_o = 33.7 MB of SURVEY.md 8d assume every list row is read twice from HBM -- rows certain "
                       "to be outside the cutoff are not read at all and the pair cache stays in L2")
 SEARCH_ROW_Z = 79  # the in-tree Au row: see DESIGN.md "Search workload"
