@@ -23,24 +23,32 @@ def _matter_forces(F: np.ndarray, fixed: Optional[np.ndarray], remove_net_force:
     return F
 
 
-def fd_hessian(pot, positions, atomic_nrs, box, atoms: Sequence[int], masses=None, dr: float = 0.01,
-               central: bool = False, fixed=None, remove_net_force: bool = True) -> np.ndarray:
-    """Mass-weighted, symmetrised FD Hessian over the coordinates of `atoms` (size 3 len(atoms)); `pot` is any object
-    with the ``forceBatch(nSystems, nAtoms, positions, atomicNrs, boxes)`` call of `B200Potential`."""
-    R0 = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
-    N = R0.shape[0]
-    atoms = [int(a) for a in atoms]
+def displaced_systems(positions, atoms: Sequence[int], dr: float = 0.01, central: bool = False) -> np.ndarray:
+    """The configurations ``Hessian::calculate`` evaluates (client/Hessian.cpp:150-215), one per row: the undisplaced
+    one, then +dr on each coordinate of each atom of `atoms`, then (central scheme) -dr on each."""
+    R0 = np.asarray(positions, dtype=np.float64).reshape(-1)
     size = 3 * len(atoms)
-    m = np.ones(N) if masses is None else np.asarray(masses, dtype=np.float64)
     n_sys = 1 + (2 if central else 1) * size
-    R = np.broadcast_to(R0.reshape(1, -1), (n_sys, 3 * N)).copy()
+    R = np.broadcast_to(R0, (n_sys, R0.size)).copy()
     for i in range(size):
-        col = 3 * atoms[i // 3] + i % 3
+        col = 3 * int(atoms[i // 3]) + i % 3
         R[1 + i, col] += dr
         if central:
             R[1 + size + i, col] -= dr
-    F, _, _ = pot.forceBatch(n_sys, N, R, atomic_nrs, box)
-    F = _matter_forces(np.asarray(F).reshape(n_sys, N, 3), fixed, remove_net_force)
+    return R
+
+
+def assemble_hessian(F, atoms: Sequence[int], masses=None, dr: float = 0.01, central: bool = False, fixed=None,
+                     remove_net_force: bool = True) -> np.ndarray:
+    """Hessian from the forces of `displaced_systems` (same row order): finite difference, mass weighting,
+    symmetrisation (client/Hessian.cpp:196-231)."""
+    F = np.asarray(F, dtype=np.float64)
+    n_sys = F.shape[0]
+    N = F.size // (3 * n_sys)
+    atoms = [int(a) for a in atoms]
+    size = 3 * len(atoms)
+    m = np.ones(N) if masses is None else np.asarray(masses, dtype=np.float64)
+    F = _matter_forces(F.reshape(n_sys, N, 3), fixed, remove_net_force)
     sel = np.array([[3 * a, 3 * a + 1, 3 * a + 2] for a in atoms]).reshape(-1)
     Ff = F.reshape(n_sys, 3 * N)[:, sel]
     if central:
@@ -51,3 +59,14 @@ def fd_hessian(pot, positions, atomic_nrs, box, atoms: Sequence[int], masses=Non
     eff = np.sqrt(np.outer(mm, mm))
     H = np.where(eff < 1e-300, 0.0, H / np.where(eff < 1e-300, 1.0, eff))  # safe_div(.., 0.0)
     return 0.5 * (H + H.T)
+
+
+def fd_hessian(pot, positions, atomic_nrs, box, atoms: Sequence[int], masses=None, dr: float = 0.01,
+               central: bool = False, fixed=None, remove_net_force: bool = True) -> np.ndarray:
+    """Mass-weighted, symmetrised FD Hessian over the coordinates of `atoms` (size 3 len(atoms)); `pot` is any object
+    with the ``forceBatch(nSystems, nAtoms, positions, atomicNrs, boxes)`` call of `B200Potential`."""
+    atoms = [int(a) for a in atoms]
+    R = displaced_systems(positions, atoms, dr, central)
+    n_sys, N = R.shape[0], R.shape[1] // 3
+    F, _, _ = pot.forceBatch(n_sys, N, R, atomic_nrs, box)
+    return assemble_hessian(np.asarray(F).reshape(n_sys, N, 3), atoms, masses, dr, central, fixed, remove_net_force)

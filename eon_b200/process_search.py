@@ -6,8 +6,9 @@ Pure host logic over harvested arrays: connectivity by ``Matter::compare`` (clie
 distinguishable / no-rotation branch eonclient takes for endpoints: per-atom minimum-image distance below
 ``structure_comparison.distance_difference``, net translation removed first when no atom is fixed,
 client/GeometryAnalysis.cpp:240-258), the endpoint swap, barriers and the abort rules with the reference's status
-codes (include/eon/MinModeSaddleSearch.h:29-53).  Prefactors are out of scope: the
-``prefactor.default_value`` path of the reference is taken.
+codes (include/eon/MinModeSaddleSearch.h:29-53).  `process_results` takes the ``prefactor.default_value`` path of
+the reference; `eon_b200.prefactor.apply_prefactors` then replaces it by the harmonic prefactors of
+client/Prefactor.cpp for the walkers that ended well, from one batched force call.
 """
 from __future__ import annotations
 
@@ -21,7 +22,8 @@ STATUS_BAD_HIGH_BARRIER = 8
 STATUS_BAD_MINIMA = 9
 STATUS_NEGATIVE_BARRIER = 14
 
-STATUS_TEXT = {0: "good", 3: "bad high energy", 5: "bad max iterations", 6: "bad not connected", 8: "bad high barrier",
+STATUS_TEXT = {0: "good", 3: "bad high energy", 5: "bad max iterations", 6: "bad not connected", 7: "bad prefactor",
+               8: "bad high barrier", 10: "failed prefactor",
                9: "bad minima", 11: "potential failed", 13: "nonlocal abort", 14: "negative barrier",
                16: "no negative mode at saddle", 18: "zero mode abort", 19: "optimizer error"}
 
@@ -113,7 +115,7 @@ def process_results(out: Dict[str, object], initial_positions, cell, fixed, max_
             "force_calls_prefactors": 0,
             "prefactor_reactant_to_product": prefactor_default,
             "prefactor_product_to_reactant": prefactor_default,
-            "reactant": p1, "product": p2,
+            "reactant": p1, "product": p2, "saddle": sad.positions[w].reshape(-1, 3),
         })
     return results
 
@@ -127,7 +129,7 @@ def format_results_dat(result: dict) -> str:
     """``<value> <key>`` lines in the order and number format of ``ProcessSearchJob::saveData``."""
     lines = []
     for key, val in result.items():
-        if key in ("reactant", "product"):
+        if key in ("reactant", "product", "saddle"):
             continue
         lines.append(("%.12e %s" % (val, key)) if key in _FLOAT_KEYS else ("%s %s" % (val, key)))
     return "\n".join(lines) + "\n"

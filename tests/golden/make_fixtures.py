@@ -90,7 +90,9 @@ def main():
                                  "barrier_reactant_to_product": 1.580767852306e-01,
                                  "barrier_product_to_reactant": 1.703228982960e-01,
                                  "force_calls_saddle": 31, "force_calls_minimization": 27,
-                                 "total_force_calls": 67,
+                                 "total_force_calls": 67, "force_calls_prefactors": 9,
+                                 "prefactor_reactant_to_product": 1.166188480043e+12,
+                                 "prefactor_product_to_reactant": 1.130999754565e+12,
                                  "cite": "client/unit_tests/data/reference/process_search_morse_pt.dat:1-15; "
                                          "client/unit_tests/JobIntegrationTest.cpp:1020-1069"},
         "eam_al_rgpot_point": {"energy": -5.217864, "max_force": 0.968647, "fixture": "al_fcc.json",
