@@ -15,7 +15,7 @@ MINMODE_DIMER, MINMODE_LANCZOS = 0, 1
 ROT_SD, ROT_CG, ROT_LBFGS = 0, 1, 2
 METRIC_NORM, METRIC_MAX_ATOM, METRIC_MAX_COMPONENT = 0, 1, 2
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 #: every symbol include/eonb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -27,6 +27,7 @@ SYMBOLS = [
     "eonb200_walkers_displace_along_mode", "eonb200_walkers_harvest", "eonb200_walkers_last_ms",
     "eonb200_measure_fp64_peak", "eonb200_kernel_launches", "eonb200_nl_stats",
     "eonb200_last_force_ms", "eonb200_phase_clocks", "eonb200_l2_flush",
+    "eonb200_neb_params_default", "eonb200_neb_forces", "eonb200_neb_forces_device",
 ]
 
 
@@ -34,6 +35,15 @@ class EamRow(C.Structure):
     _fields_ = [("Z", C.c_int), ("Dm", C.c_double), ("alphaM", C.c_double), ("Rm", C.c_double),
                 ("beta1", C.c_double), ("beta2", C.c_double), ("r_cut", C.c_double),
                 ("func_coeff", C.c_double * 9)]
+
+
+class NebParams(C.Structure):
+    _fields_ = [("spring_constant", C.c_double), ("k_min", C.c_double), ("k_max", C.c_double),
+                ("climbing_image", C.c_int), ("old_tangent", C.c_int), ("projection", C.c_int),
+                ("energy_weighted", C.c_int)]
+
+
+NEB_PROJECTION_NEB, NEB_PROJECTION_DNEB, NEB_PROJECTION_ELASTIC_BAND = 0, 1, 2
 
 
 class Config(C.Structure):
@@ -124,4 +134,12 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.eonb200_phase_clocks.restype = C.c_int
     lib.eonb200_l2_flush.argtypes = [_vp, C.c_size_t]
     lib.eonb200_l2_flush.restype = C.c_int
+    lib.eonb200_neb_params_default.argtypes = [C.POINTER(NebParams)]
+    lib.eonb200_neb_params_default.restype = None
+    lib.eonb200_neb_forces.argtypes = [_vp, C.c_long, C.c_long, C.c_long, C.c_long, _dp, _dp, _dp, _dp,
+                                       C.POINTER(NebParams), _dp, _dp, C.POINTER(C.c_int)]
+    lib.eonb200_neb_forces.restype = C.c_int
+    lib.eonb200_neb_forces_device.argtypes = [_vp, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, _dp, C.POINTER(NebParams), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.eonb200_neb_forces_device.restype = C.c_int
     return lib

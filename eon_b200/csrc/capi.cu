@@ -3,6 +3,7 @@
 // Host logic only; every floating-point result comes from the kernels in kernels.cuh.  There is
 // no CPU evaluation path: without a usable CUDA device eonb200_create fails.
 #include "kernels.cuh"
+#include "neb.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -100,6 +101,8 @@ struct EonB200Pot {
   std::vector<double> last_boxes;
   std::vector<std::pair<const char *, size_t>> pinned;  // caller ranges page-locked by this handle (pin_host_buffers)
   NlStore nl;  // cache of the stateless batch slots
+  DevBuf<double> neb_R, neb_F, neb_E, neb_P, neb_T;  // eonb200_neb_forces staging
+  DevBuf<int> neb_C;
   unsigned long long force_calls = 0, launches = 0;
   long long last_stats[5] = {0, 0, 0, 0, 0};
   double last_ms[2] = {0.0, 0.0};
@@ -715,6 +718,108 @@ int eonb200_phase_clocks(EonB200Pot *pot, int enable, long long *out, long cap_c
     const long n = std::min(cap_ctas, pot->clocks_ctas);
     CU_TRY(pot, cudaMemcpy(out, pot->d_clocks.p, sizeof(long long) * n * 16, cudaMemcpyDeviceToHost));
   }
+  return 0;
+}
+
+// ---- NEB band forces ---------------------------------------------------------------------
+static bool host_invert3(const double *m, double *inv) {
+  const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  if (!(std::fabs(det) > 1e-300)) return false;
+  inv[0] = c00 / det;
+  inv[1] = (m[2] * m[7] - m[1] * m[8]) / det;
+  inv[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+  inv[3] = c01 / det;
+  inv[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+  inv[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+  inv[6] = c02 / det;
+  inv[7] = (m[1] * m[6] - m[0] * m[7]) / det;
+  inv[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+  return true;
+}
+
+void eonb200_neb_params_default(EonB200NebParams *p) {
+  if (!p) return;
+  // include/eon/Parameters.h:478-489: spring.constant 5.0, weighting k_min 0.97 / k_max 9.7 (off), improved tangent,
+  // plain NEB projection; the climbing image is switched on by the caller once its trigger is met
+  p->spring_constant = 5.0;
+  p->k_min = 0.97;
+  p->k_max = 9.7;
+  p->climbing_image = 0;
+  p->old_tangent = 0;
+  p->projection = EONB200_NEB_PROJECTION_NEB;
+  p->energy_weighted = 0;
+}
+
+int eonb200_neb_forces_device(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms,
+                              const double *d_positions, const double *d_forces, const double *d_energies,
+                              const double *box, const EonB200NebParams *prm, double *d_projected, double *d_tangents,
+                              int *d_climbing) {
+  if (!pot) return 1;
+  if (nBands <= 0 || nImages <= 0 || nAtoms <= 0) return fail(pot, 2, "neb_forces: bands, images and atoms must be positive");
+  if (!d_positions || !d_forces || !d_energies || !prm || !d_projected || !d_tangents)
+    return fail(pot, 2, "neb_forces: null argument");
+  if (prm->projection < 0 || prm->projection > 2) return fail(pot, 2, "neb_forces: unknown projection %d", prm->projection);
+  if (nBands * nImages > 2147483647L / 2) return fail(pot, 2, "neb_forces: too many images");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  NebArgs a;
+  a.pos = d_positions;
+  a.frc = d_forces;
+  a.energy = d_energies;
+  a.projected = d_projected;
+  a.tangent = d_tangents;
+  a.climbing = d_climbing;
+  a.cell_ok = 0;
+  for (int k = 0; k < 9; k++) a.cell[k] = a.inv[k] = 0.0;
+  if (box) {
+    for (int k = 0; k < 9; k++) a.cell[k] = box[k];
+    a.cell_ok = host_invert3(a.cell, a.inv) ? 1 : 0;
+  }
+  a.ksp = prm->spring_constant;
+  a.k_min = prm->k_min;
+  a.k_max = prm->k_max;
+  a.images = static_cast<int>(nImages);
+  a.atoms = static_cast<int>(nAtoms);
+  a.all_free = nFreeAtoms == nAtoms ? 1 : 0;
+  a.ci_active = prm->climbing_image ? 1 : 0;
+  a.old_tangent = prm->old_tangent ? 1 : 0;
+  a.weighted = prm->energy_weighted ? 1 : 0;
+  // elastic band / doubly nudged only without energy weighting (client/NEBProjection.cpp:33-45)
+  a.projection = a.weighted ? static_cast<int>(NEB_PROJ_NEB) : prm->projection;
+  EONB200_LAUNCH(k_neb_band, static_cast<unsigned>(nBands * nImages), 256, 0, pot->stream, a);
+  CU_TRY(pot, cudaGetLastError());
+  pot->launches += 1;
+  return 0;
+}
+
+int eonb200_neb_forces(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms, const double *positions,
+                       const double *forces, const double *energies, const double *box, const EonB200NebParams *prm,
+                       double *projected, double *tangents, int *climbing) {
+  if (!pot) return 1;
+  if (nBands <= 0 || nImages <= 0 || nAtoms <= 0) return fail(pot, 2, "neb_forces: bands, images and atoms must be positive");
+  if (!positions || !forces || !energies || !prm || !projected) return fail(pot, 2, "neb_forces: null argument");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  const size_t D = 3 * static_cast<size_t>(nAtoms);
+  const size_t rows = static_cast<size_t>(nBands) * (nImages + 2), mov = static_cast<size_t>(nBands) * nImages;
+  CU_TRY(pot, pot->neb_R.reserve(rows * D));
+  CU_TRY(pot, pot->neb_F.reserve(rows * D));
+  CU_TRY(pot, pot->neb_E.reserve(rows));
+  CU_TRY(pot, pot->neb_P.reserve(mov * D));
+  CU_TRY(pot, pot->neb_T.reserve(mov * D));
+  CU_TRY(pot, pot->neb_C.reserve(static_cast<size_t>(nBands)));
+  CU_TRY(pot, cudaMemcpyAsync(pot->neb_R.p, positions, rows * D * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->neb_F.p, forces, rows * D * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->neb_E.p, energies, rows * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  const int rc = eonb200_neb_forces_device(pot, nBands, nImages, nAtoms, nFreeAtoms, pot->neb_R.p, pot->neb_F.p,
+                                           pot->neb_E.p, box, prm, pot->neb_P.p, pot->neb_T.p, pot->neb_C.p);
+  if (rc) return rc;
+  CU_TRY(pot, cudaMemcpyAsync(projected, pot->neb_P.p, mov * D * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+  if (tangents)
+    CU_TRY(pot, cudaMemcpyAsync(tangents, pot->neb_T.p, mov * D * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+  if (climbing)
+    CU_TRY(pot, cudaMemcpyAsync(climbing, pot->neb_C.p, static_cast<size_t>(nBands) * sizeof(int), cudaMemcpyDeviceToHost,
+                                pot->stream));
+  CU_TRY(pot, cudaStreamSynchronize(pot->stream));
   return 0;
 }
 

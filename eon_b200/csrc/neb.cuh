@@ -1,0 +1,206 @@
+// neb.cuh -- nudged-elastic-band force projection for many bands at once.
+//
+// What NudgedElasticBand::updateForces does per movable image after the potential call
+// (client/NudgedElasticBand.cpp:551-646): minimum-image differences to both neighbours, the tangent
+// (client/NEBTangent.cpp:36-69), the spring force (client/NEBSpringForce.cpp:17-42,113-136), the projection
+// (client/NEBProjection.cpp:17-31, client/NEBForceProjection.cpp:65-112), the climbing image and
+// zeroTranslation.  One CTA per (band, image); everything is a handful of passes over 3 N doubles, so
+// the kernel is HBM / L2 bound: 5 vectors read, 2 written per image.
+#pragma once
+#include "common.cuh"
+
+namespace eonb200 {
+
+enum NebProjection { NEB_PROJ_NEB = 0, NEB_PROJ_DNEB = 1, NEB_PROJ_ELASTIC_BAND = 2 };
+
+struct NebArgs {
+  const double *pos;     // [bands][images + 2][3 N]
+  const double *frc;     // same shape: Matter forces (fixed axes zeroed); endpoint rows are not read
+  const double *energy;  // [bands][images + 2]
+  double *projected;     // [bands][images][3 N]
+  double *tangent;       // [bands][images][3 N]
+  int *climbing;         // [bands]: index of the climbing image (0 = none), may be null
+  double cell[9], inv[9];
+  double ksp, k_min, k_max;
+  int images, atoms;
+  int cell_ok, all_free, ci_active, old_tangent, projection, weighted;
+};
+
+// pbc of one atom row (include/eon/Matter.h:42-50)
+__device__ __forceinline__ void neb_mic(const NebArgs &a, double (&d)[3]) {
+  if (!a.cell_ok) return;
+  double f[3];
+  for (int k = 0; k < 3; k++) f[k] = d[0] * a.inv[k] + d[1] * a.inv[3 + k] + d[2] * a.inv[6 + k];
+  for (int k = 0; k < 3; k++) f[k] -= floor(f[k] + 0.5);
+  for (int k = 0; k < 3; k++) d[k] = f[0] * a.cell[k] + f[1] * a.cell[3 + k] + f[2] * a.cell[6 + k];
+}
+
+__device__ __forceinline__ void neb_diffs(const NebArgs &a, const double *rp, const double *rc, const double *rn, int at,
+                                          double (&dn)[3], double (&dp)[3]) {
+  for (int k = 0; k < 3; k++) {
+    dn[k] = rn[3 * at + k] - rc[3 * at + k];
+    dp[k] = rc[3 * at + k] - rp[3 * at + k];
+  }
+  neb_mic(a, dn);
+  neb_mic(a, dp);
+}
+
+// forceSpring of UniformSpring::compute (client/NEBSpringForce.cpp:24): ksp * pbc(dNext - dPrev)
+__device__ __forceinline__ void neb_spring(const NebArgs &a, const double (&dn)[3], const double (&dp)[3], double (&s)[3]) {
+  for (int k = 0; k < 3; k++) s[k] = dn[k] - dp[k];
+  neb_mic(a, s);
+  for (int k = 0; k < 3; k++) s[k] *= a.ksp;
+}
+
+__global__ void __launch_bounds__(256) k_neb_band(NebArgs a) {
+  __shared__ double red[4 * kMaxWarps];
+  const int M = a.images, N = a.atoms, D = 3 * N;
+  const int band = blockIdx.x / M, img = blockIdx.x % M + 1;
+  const double *E = a.energy + static_cast<size_t>(band) * (M + 2);
+  const size_t row = static_cast<size_t>(band) * (M + 2) + img;
+  const double *rc = a.pos + row * D, *rp = rc - D, *rn = rc + D;
+  const double *fc = a.frc + row * D;
+  double *T = a.tangent + (static_cast<size_t>(band) * M + img - 1) * D;
+  double *P = a.projected + (static_cast<size_t>(band) * M + img - 1) * D;
+
+  // highest movable image: std::max_element keeps the first of equal maxima (NudgedElasticBand.cpp:551-560)
+  int imax = 1;
+  for (int j = 2; j <= M; j++)
+    if (E[imax] < E[j]) imax = j;
+  const double e_max = E[imax];
+  const bool climbs = a.ci_active && img == imax;
+  if (a.climbing && img == 1 && threadIdx.x == 0) a.climbing[band] = a.ci_active ? imax : 0;
+
+  // tangent rule (NEBTangent.cpp:44-66): 0 = next, 1 = previous, 2 = energy-weighted mix
+  const double e = E[img], e_prev = E[img - 1], e_next = E[img + 1];
+  int rule = 2;
+  double c_next = 0.0, c_prev = 0.0;
+  if (a.old_tangent || (e_next > e && e > e_prev)) {
+    rule = 0;
+  } else if (e > e_next && e_prev > e) {
+    rule = 1;
+  } else {
+    const double dprev = e_prev - e, dnext = e_next - e;
+    const double lo = fmin(fabs(dprev), fabs(dnext)), hi = fmax(fabs(dprev), fabs(dnext));
+    c_next = dprev > dnext ? lo : hi;
+    c_prev = dprev > dnext ? hi : lo;
+  }
+
+  // pass 1: raw tangent, |dNext|^2, |dPrev|^2, |tangent|^2
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (int at = threadIdx.x; at < N; at += blockDim.x) {
+    double dn[3], dp[3];
+    neb_diffs(a, rp, rc, rn, at, dn, dp);
+    for (int k = 0; k < 3; k++) {
+      const double t = rule == 0 ? dn[k] : (rule == 1 ? dp[k] : __dadd_rn(__dmul_rn(dn[k], c_next), __dmul_rn(dp[k], c_prev)));
+      T[3 * at + k] = t;
+      acc[0] += dn[k] * dn[k];
+      acc[1] += dp[k] * dp[k];
+      acc[2] += t * t;
+    }
+  }
+  block_sum<3>(acc, red);
+  const double dist_next = sqrt(acc[0]), dist_prev = sqrt(acc[1]);
+  double t_norm = sqrt(acc[2]);
+  const bool fallback = !(t_norm > 1e-10);  // NEBTangent.cpp:21-33
+  if (fallback) t_norm = dist_next;
+  const bool scale = t_norm > 1e-10;
+  const bool want_spring = a.projection != NEB_PROJ_NEB;
+
+  // pass 2: normalise; F.t and spring.t
+  double dot[2] = {0.0, 0.0};
+  for (int at = threadIdx.x; at < N; at += blockDim.x) {
+    double dn[3], dp[3], s[3] = {0.0, 0.0, 0.0};
+    if (fallback || want_spring) neb_diffs(a, rp, rc, rn, at, dn, dp);
+    if (want_spring) neb_spring(a, dn, dp, s);
+    for (int k = 0; k < 3; k++) {
+      double t = fallback ? dn[k] : T[3 * at + k];
+      if (scale) t /= t_norm;
+      T[3 * at + k] = t;
+      dot[0] += fc[3 * at + k] * t;
+      dot[1] += s[k] * t;
+    }
+  }
+  block_sum<2>(dot, red);
+  const double f_t = dot[0], s_t = dot[1];
+
+  // doubly nudged term (NEBForceProjection.cpp:73-97)
+  double dneb_switch = 0.0, sp_fn = 0.0, f_perp_norm = 1.0;
+  if (a.projection == NEB_PROJ_DNEB) {
+    double q[3] = {0.0, 0.0, 0.0};
+    for (int at = threadIdx.x; at < N; at += blockDim.x) {
+      double dn[3], dp[3], s[3];
+      neb_diffs(a, rp, rc, rn, at, dn, dp);
+      neb_spring(a, dn, dp, s);
+      for (int k = 0; k < 3; k++) {
+        const double t = T[3 * at + k];
+        const double sp = s[k] - s_t * t, fp = fc[3 * at + k] - f_t * t;
+        q[0] += sp * sp;
+        q[1] += fp * fp;
+        q[2] += sp * fp;
+      }
+    }
+    block_sum<3>(q, red);
+    const double sp_norm = sqrt(q[0]);
+    f_perp_norm = sqrt(q[1]);
+    if (sp_norm > 1e-10 && f_perp_norm > 1e-10) {
+      sp_fn = q[2] / f_perp_norm;
+      dneb_switch = 2.0 / 3.14159265358979323846 * atan(f_perp_norm * f_perp_norm / (sp_norm * sp_norm));
+    } else {
+      f_perp_norm = 1.0;
+    }
+  }
+
+  // parallel spring coefficient (NEBSpringForce.cpp:23,35-36; spring constants :113-131)
+  double par = a.ksp * (dist_next - dist_prev);
+  if (a.weighted) {
+    const double e_ref = fmin(E[0], E[M + 1]);
+    const double range = e_max - e_ref;
+    double kk[2];
+    for (int s = 0; s < 2; s++) {
+      const int idx = img + s;  // springConstants[idx - 1] sits between images idx - 1 and idx
+      double kv = a.k_min;
+      if (!(range < 1e-10)) {
+        const double ei = fmax(E[idx], E[idx - 1]);
+        if (ei > e_ref) {
+          double al = (e_max - ei) / range;
+          al = fmax(0.0, fmin(1.0, al));
+          kv = (1.0 - al) * a.k_max + al * a.k_min;
+        }
+      }
+      kk[s] = kv;  // kk[0] = springConstants[img - 1], kk[1] = springConstants[img]
+    }
+    par = kk[1] * dist_next - kk[0] * dist_prev;
+  }
+
+  // pass 3: the projected force
+  double col[3] = {0.0, 0.0, 0.0};
+  for (int at = threadIdx.x; at < N; at += blockDim.x) {
+    double dn[3], dp[3], s[3] = {0.0, 0.0, 0.0};
+    if (want_spring) {
+      neb_diffs(a, rp, rc, rn, at, dn, dp);
+      neb_spring(a, dn, dp, s);
+    }
+    for (int k = 0; k < 3; k++) {
+      const double t = T[3 * at + k], f = fc[3 * at + k];
+      double dneb = 0.0;
+      if (a.projection == NEB_PROJ_DNEB && dneb_switch != 0.0) {
+        const double sp = s[k] - s_t * t, fpn = (f - f_t * t) / f_perp_norm;
+        dneb = (sp - sp_fn * fpn) * dneb_switch;
+      }
+      double out;
+      if (climbs) out = f - 2.0 * f_t * t + dneb;                       // NEBForceProjection.cpp:69-71
+      else if (a.projection == NEB_PROJ_ELASTIC_BAND) out = s[k] + f;   // NEBProjection.cpp:17-19
+      else out = par * t + (f - f_t * t) + dneb;                        // :21-31
+      P[3 * at + k] = out;
+      col[k] += out;
+    }
+  }
+  if (a.all_free) {  // zeroTranslation (NEBForceProjection.cpp:101-110)
+    block_sum<3>(col, red);
+    for (int at = threadIdx.x; at < N; at += blockDim.x)
+      for (int k = 0; k < 3; k++) P[3 * at + k] -= col[k] / static_cast<double>(N);
+  }
+}
+
+}  // namespace eonb200

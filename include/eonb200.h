@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONB200_ABI_VERSION 2
+#define EONB200_ABI_VERSION 3
 
 #if defined(_WIN32)
 #define EONB200_API __declspec(dllexport)
@@ -237,6 +237,42 @@ EONB200_API unsigned long long eonb200_kernel_launches(const EonB200Pot *pot);
  * out[0] = lists rebuilt, out[1] = lists reused, out[2] = row capacity K, out[3] = max row fill,
  * out[4] = ordered in-cutoff pairs visited by the last force evaluation (sum over systems). */
 EONB200_API int eonb200_nl_stats(EonB200Pot *pot, long long out[5]);
+
+/* ---- NEB band forces ----------------------------------------------------------------------
+ * Replaces the per-image loop of NudgedElasticBand::updateForces after the potential call
+ * (client/NudgedElasticBand.cpp:551-646) for many bands at once: minimum-image neighbour differences, tangent
+ * (client/NEBTangent.cpp:36-69), spring force (client/NEBSpringForce.cpp:17-42,113-136), projection
+ * (client/NEBProjection.cpp:17-45, client/NEBForceProjection.cpp:65-97), climbing image and zeroTranslation (:101-110).
+ * The Onsager-Machlup spring (NEBSpringForce.cpp:46-111) is not covered. */
+enum { EONB200_NEB_PROJECTION_NEB = 0, EONB200_NEB_PROJECTION_DNEB = 1, EONB200_NEB_PROJECTION_ELASTIC_BAND = 2 };
+
+typedef struct EonB200NebParams {
+  double spring_constant; /* neb_options.spring.constant (5.0) */
+  double k_min, k_max;    /* neb_options.spring.weighting.k_min / k_max (0.97 / 9.7), used when energy_weighted */
+  int climbing_image;     /* ci_active of the reference: the highest movable image climbs */
+  int old_tangent;        /* neb_options.climbing_image.use_old_tangent: tangent = direction to the next image */
+  int projection;         /* EONB200_NEB_PROJECTION_*: spring.doubly_nudged / spring.use_elastic_band */
+  int energy_weighted;    /* neb_options.spring.weighting.enabled (forces the plain NEB projection, as the reference) */
+} EonB200NebParams;
+
+EONB200_API void eonb200_neb_params_default(EonB200NebParams *p);
+
+/* Host buffers, all contiguous: positions / forces [nBands][nImages + 2][3 nAtoms] (both endpoints included; forces are
+ * Matter::getForces values, i.e. fixed axes already zeroed, endpoint rows unused), energies [nBands][nImages + 2], box[9]
+ * row-major cell shared by all bands (null = no periodic wrap).  Writes projected and tangents
+ * [nBands][nImages][3 nAtoms] (tangents may be null) and climbing[nBands] (may be null): index of the climbing image,
+ * 0 when climbing_image is off.  nFreeAtoms == nAtoms switches zeroTranslation on.  Returns 0 or an error code. */
+EONB200_API int eonb200_neb_forces(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms,
+                                   const double *positions, const double *forces, const double *energies,
+                                   const double *box, const EonB200NebParams *prm, double *projected, double *tangents,
+                                   int *climbing);
+
+/* Same with DEVICE pointers for everything but box and prm (bands kept resident between optimiser steps); asynchronous
+ * on the handle's stream. */
+EONB200_API int eonb200_neb_forces_device(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms,
+                                          const double *d_positions, const double *d_forces, const double *d_energies,
+                                          const double *box, const EonB200NebParams *prm, double *d_projected,
+                                          double *d_tangents, int *d_climbing);
 
 /* CUDA-event milliseconds of the last (synchronous) force_batch / force_batch_device call, split as
  * out[0] = k_prepare (staging, Verlet check, cell-list rebuilds), out[1] = the force pass kernel(s). */

@@ -1,0 +1,147 @@
+"""NEB band forces (client/NudgedElasticBand.cpp:551-646 and the helpers it dispatches to) on the device against the
+numpy oracle in oracle/neb_band.py, plus the analytic properties the reference's helper tests rely on."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from eon_b200 import B200Potential, neb as NEB
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import neb_band as ONEB  # noqa: E402
+
+
+def _random_bands(seed, B, M, N, cell, fixed_atoms=0):
+    rng = np.random.default_rng(seed)
+    L = np.diag(cell)
+    a = rng.uniform(0.0, 1.0, (B, 1, N, 3)) * L
+    b = a + rng.normal(0.0, 0.4, (B, 1, N, 3))
+    lam = np.linspace(0.0, 1.0, M + 2).reshape(1, M + 2, 1, 1)
+    R = a + lam * (b - a) + rng.normal(0.0, 0.03, (B, M + 2, N, 3))
+    R = R - np.floor(R / L) * L          # wrapped: neighbouring images differ by whole cells for some atoms
+    F = rng.normal(0.0, 0.5, (B, M + 2, N, 3))
+    F[:, :, :fixed_atoms] = 0.0
+    E = rng.normal(0.0, 1.0, (B, M + 2))
+    return R, F, E
+
+
+def _energy_shapes(E):
+    E = E.copy()
+    E[0] = np.array([0.0, 0.2, 0.5, 0.9, 0.6, 0.3, 0.1])[:E.shape[1]]        # single maximum
+    if E.shape[0] > 1:
+        E[1] = np.linspace(0.0, 1.0, E.shape[1])                              # monotonic: highest is the last movable
+    if E.shape[0] > 2:
+        E[2] = np.array([0.0, 0.4, 0.4, 0.1, 0.4, 0.4, 0.0])[:E.shape[1]]    # ties: first maximum wins, flat neighbours
+    return E
+
+
+CASES = [dict(), dict(climbing_image=1), dict(old_tangent=1), dict(projection=1), dict(projection=1, climbing_image=1),
+         dict(projection=2), dict(energy_weighted=1, climbing_image=1), dict(energy_weighted=1, projection=2),
+         dict(spring_constant=0.3, climbing_image=1)]
+
+
+@pytest.mark.parametrize("n_fixed", [0, 5])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join("%s%s" % kv for kv in c.items()) or "default")
+def test_band_forces_match_oracle(backend, case, n_fixed):
+    B, M, N = 5, 5, 23
+    cell = np.diag([9.0, 10.0, 11.0])
+    R, F, E = _random_bands(3 + n_fixed, B, M, N, cell, n_fixed)
+    E = _energy_shapes(E)
+    with B200Potential("lj", lib=backend) as pot:
+        P, T, ci = NEB.neb_forces(pot, R.reshape(B, M + 2, -1), F.reshape(B, M + 2, -1), E, cell, N - n_fixed, **case)
+    okw = dict(ksp=case.get("spring_constant", 5.0), climbing_image=bool(case.get("climbing_image")),
+               old_tangent=bool(case.get("old_tangent")), projection=case.get("projection", 0),
+               energy_weighted=bool(case.get("energy_weighted")))
+    for b in range(B):
+        P0, T0, ci0 = ONEB.band_forces(R[b], F[b], E[b], cell, N - n_fixed, **okw)
+        assert ci[b] == ci0
+        assert np.abs(T[b].reshape(M, N, 3) - T0).max() <= 1e-13
+        assert np.abs(P[b].reshape(M, N, 3) - P0).max() <= 1e-11 * max(1.0, np.abs(P0).max())
+    assert ci[0] == (3 if case.get("climbing_image") else 0)
+    if case.get("climbing_image"):
+        assert ci[1] == M and ci[2] == 1
+
+
+def test_band_force_properties(backend):
+    """Unit tangents, nudging (only the spring acts along the tangent), climbing-image inversion, zero translation."""
+    B, M, N = 3, 5, 17
+    cell = np.diag([8.0, 8.0, 8.0])
+    R, F, E = _random_bands(11, B, M, N, cell)
+    E = _energy_shapes(E)
+    D = 3 * N
+    with B200Potential("lj", lib=backend) as pot:
+        P, T, ci = NEB.neb_forces(pot, R.reshape(B, M + 2, D), F.reshape(B, M + 2, D), E, cell, N - 1, climbing_image=1)
+        Pz, _, _ = NEB.neb_forces(pot, R.reshape(B, M + 2, D), F.reshape(B, M + 2, D), E, cell, N, climbing_image=1)
+        # no cell: plain differences
+        Pn, Tn, _ = NEB.neb_forces(pot, R.reshape(B, M + 2, D), F.reshape(B, M + 2, D), E, None, N - 1)
+    assert np.allclose(np.linalg.norm(T, axis=2), 1.0, atol=1e-13)
+    Fm = F[:, 1:M + 1].reshape(B, M, D)
+    for b in range(B):
+        for i in range(M):
+            dn = ONEB.pbc(R[b, i + 2] - R[b, i + 1], cell)
+            dp = ONEB.pbc(R[b, i + 1] - R[b, i], cell)
+            along = P[b, i] @ T[b, i]
+            if ci[b] == i + 1:
+                assert along == pytest.approx(-(Fm[b, i] @ T[b, i]), abs=1e-11)
+                perp = P[b, i] - along * T[b, i]
+                assert np.allclose(perp, Fm[b, i] - (Fm[b, i] @ T[b, i]) * T[b, i], atol=1e-11)
+            else:
+                assert along == pytest.approx(5.0 * (np.linalg.norm(dn) - np.linalg.norm(dp)), abs=1e-11)
+    assert np.abs(Pz.reshape(B, M, N, 3).sum(axis=2)).max() < 1e-11          # zeroTranslation when every atom is free
+    assert np.abs(P.reshape(B, M, N, 3).sum(axis=2)).max() > 1e-3
+    for b in range(B):
+        P0, T0, _ = ONEB.band_forces(R[b], F[b], E[b], None, N - 1)
+        assert np.abs(Pn[b].reshape(M, N, 3) - P0).max() <= 1e-11 and np.abs(Tn[b].reshape(M, N, 3) - T0).max() <= 1e-13
+    assert NEB.convergence_force(P, ci).shape == (B,)
+    assert np.allclose(NEB.convergence_force(P), np.linalg.norm(P, axis=2).max(axis=1))
+    only = NEB.convergence_force(P, ci, ci_converged_only=True)
+    assert all(only[b] == pytest.approx(np.linalg.norm(P[b, ci[b] - 1])) for b in range(B))
+
+
+def test_degenerate_band_and_errors(backend):
+    N, M = 4, 3
+    R = np.tile(np.arange(3.0 * N).reshape(1, 1, -1), (1, M + 2, 1))   # every image identical: no direction at all
+    F = np.ones((1, M + 2, 3 * N))
+    E = np.zeros((1, M + 2))
+    with B200Potential("lj", lib=backend) as pot:
+        P, T, ci = NEB.neb_forces(pot, R, F, E, np.diag([50.0, 50.0, 50.0]), N - 1, climbing_image=1)
+        assert np.isfinite(P).all() and np.all(T == 0.0)               # NEBTangent.cpp:21-33: left unnormalised
+        assert np.array_equal(P, F[:, 1:M + 1]) and ci[0] == 1
+        with pytest.raises(ValueError):
+            NEB.neb_forces(pot, R[:, :2], F[:, :2], E[:, :2], None)
+        with pytest.raises(RuntimeError, match="projection"):
+            NEB.neb_forces(pot, R, F, E, None, projection=7)
+        with pytest.raises(TypeError):
+            NEB.neb_forces(pot, R, F, E, None, springiness=1.0)
+
+
+def test_lj13_band_end_to_end(backend, oracle):
+    """`band_forces`: one forceBatch over the movable images of two bands (reactant -> product of the reference's
+    neb_morse fixture, and the reverse), masked / net-force-free forces, then the band kernel; against the C oracle's
+    forces fed through the numpy band oracle."""
+    a = oracle.load_fixture("lj13.json")
+    b = oracle.load_fixture("lj13_product.json")
+    Z, cell = a["atomic_nrs"], a["cell"]
+    N, M = len(Z), 5
+    lam = np.linspace(0.0, 1.0, M + 2).reshape(-1, 1, 1)
+    band = a["positions"][None] + lam * ONEB.pbc(b["positions"] - a["positions"], cell)[None]
+    R = np.stack([band, band[::-1]])
+    opot = oracle.potential(oracle.POT_LJ)
+    with B200Potential("lj", lib=backend) as pot:
+        out = NEB.band_forces(pot, R.reshape(2, M + 2, -1), Z, cell, climbing_image=1)
+        assert pot.forceCallCounter == 2 * 2 + 2 * M
+    for k in range(2):
+        E0 = np.empty(M + 2)
+        F0 = np.zeros((M + 2, N, 3))
+        for i in range(M + 2):
+            E0[i], f = oracle.force(opot, R[k, i], Z, cell)
+            F0[i] = f - f.mean(axis=0)
+        assert np.abs(out["energies"][k] - E0).max() <= 1e-8
+        P0, T0, ci0 = ONEB.band_forces(R[k], F0, E0, cell, N, climbing_image=True)
+        assert out["climbing"][k] == ci0 and 1 <= ci0 <= M
+        assert np.abs(out["tangents"][k].reshape(M, N, 3) - T0).max() <= 1e-12
+        assert np.abs(out["projected"][k].reshape(M, N, 3) - P0).max() <= 1e-9 * max(1.0, np.abs(P0).max())
+    # the reversed band is the same path: same energies mirrored, same climbing image mirrored
+    assert np.allclose(out["energies"][0], out["energies"][1][::-1], atol=1e-10)
+    assert out["climbing"][0] == M + 1 - out["climbing"][1] or np.isclose(*[out["energies"][k][out["climbing"][k]] for k in (0, 1)])
