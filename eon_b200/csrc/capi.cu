@@ -103,6 +103,7 @@ struct EonB200Pot {
   NlStore nl;  // cache of the stateless batch slots
   DevBuf<double> neb_R, neb_F, neb_E, neb_P, neb_T;  // eonb200_neb_forces staging
   DevBuf<int> neb_C;
+  int neb_attr = 0;
   unsigned long long force_calls = 0, launches = 0;
   long long last_stats[5] = {0, 0, 0, 0, 0};
   double last_ms[2] = {0.0, 0.0};
@@ -786,7 +787,22 @@ int eonb200_neb_forces_device(EonB200Pot *pot, long nBands, long nImages, long n
   a.weighted = prm->energy_weighted ? 1 : 0;
   // elastic band / doubly nudged only without energy weighting (client/NEBProjection.cpp:33-45)
   a.projection = a.weighted ? static_cast<int>(NEB_PROJ_NEB) : prm->projection;
-  EONB200_LAUNCH(k_neb_band, static_cast<unsigned>(nBands * nImages), 256, 0, pot->stream, a);
+  const unsigned grid = static_cast<unsigned>(nBands * nImages);
+  bool staged = false;
+#ifndef EONB200_EMU  // (the emulation runs the any-size kernel)
+  const size_t stage = neb_stage_bytes(static_cast<int>(nAtoms));
+  if (stage <= static_cast<size_t>(pot->max_dyn_smem)) {
+    if (!pot->neb_attr) {
+      CU_TRY(pot, cudaFuncSetAttribute(reinterpret_cast<const void *>(k_neb_band_tma),
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, pot->max_dyn_smem));
+      pot->neb_attr = 1;
+    }
+    const size_t total = static_cast<size_t>(nBands) * (nImages + 2) * 3 * nAtoms;
+    EONB200_LAUNCH(k_neb_band_tma, grid, 256, stage, pot->stream, a, total);
+    staged = true;
+  }
+#endif
+  if (!staged) EONB200_LAUNCH(k_neb_band, grid, 256, 0, pot->stream, a);
   CU_TRY(pot, cudaGetLastError());
   pot->launches += 1;
   return 0;

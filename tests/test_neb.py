@@ -63,6 +63,24 @@ def test_band_forces_match_oracle(backend, case, n_fixed):
         assert ci[1] == M and ci[2] == 1
 
 
+@pytest.mark.parametrize("n_atoms", [256, 301, 601, 1000, 2500])
+@pytest.mark.parametrize("case", [dict(climbing_image=1), dict(projection=1, climbing_image=1)], ids=["neb", "dneb"])
+def test_band_forces_sizes(backend, case, n_atoms):
+    """Both kernels on the GPU: rows staged in shared memory by bulk copies (odd and even row lengths, so aligned and
+    shifted copies and the end-of-array fallback all occur) and, at 2500 atoms, the any-size kernel; all atoms free."""
+    B, M = 2, 3
+    cell = np.diag([28.638, 28.638, 40.125])
+    R, F, E = _random_bands(n_atoms, B, M, n_atoms, cell)
+    with B200Potential("lj", lib=backend) as pot:
+        P, T, ci = NEB.neb_forces(pot, R.reshape(B, M + 2, -1), F.reshape(B, M + 2, -1), E, cell, n_atoms, **case)
+    for b in range(B):
+        P0, T0, ci0 = ONEB.band_forces(R[b], F[b], E[b], cell, n_atoms, climbing_image=True,
+                                       projection=case.get("projection", 0))
+        assert ci[b] == ci0
+        assert np.abs(T[b].reshape(M, n_atoms, 3) - T0).max() <= 1e-13
+        assert np.abs(P[b].reshape(M, n_atoms, 3) - P0).max() <= 1e-11 * max(1.0, np.abs(P0).max())
+
+
 def test_band_force_properties(backend):
     """Unit tangents, nudging (only the spring acts along the tangent), climbing-image inversion, zero translation."""
     B, M, N = 3, 5, 17
