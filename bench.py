@@ -521,6 +521,58 @@ def run_b200(args):
         wk4.close()
         mpot.close()
 
+    # BASELINE.json configs[4] as a fourth data point: examples/neb-al bands (reactant -> product, 7 movable images of 601
+    # atoms), every movable image of every band in one forceBatch call, then the band kernel; host buffers throughout
+    c5 = None
+    if not args.no_c5:
+        from eon_b200 import neb as NEB
+        with open(os.path.join(WL.GOLDEN_DIR, "neb_al.json")) as fh:
+            d5 = json.load(fh)
+        s5 = WL.load_structure("neb_al.json")
+        N5, M5, B5 = s5.n_atoms, 7, 64
+        prod = np.array(d5["product_positions"], dtype=np.float64)
+        inv5 = np.linalg.inv(s5.cell)
+        dfrac = (prod - s5.positions) @ inv5
+        path = (dfrac - np.floor(dfrac + 0.5)) @ s5.cell
+        lam = np.linspace(0.0, 1.0, M5 + 2).reshape(1, -1, 1, 1)
+        free5 = 1.0 - s5.fixed.reshape(1, 1, N5, 3)
+        bands = np.empty((B5, M5 + 2, N5, 3))
+        for b in range(B5):
+            rng = np.random.default_rng(500 + first + b)
+            bands[b] = s5.positions[None] + lam[0] * path[None] + rng.uniform(-0.02, 0.02, (M5 + 2, N5, 3)) * free5[0]
+        bands[:, 0], bands[:, M5 + 1] = s5.positions, s5.positions + path
+        R5 = bands.reshape(B5, M5 + 2, 3 * N5)
+        npot = B200Potential("eam", device=local_rank, skin=args.skin, pin_host_buffers=1)
+        with B200Potential("eam", device=local_rank, skin=args.skin) as hpot:  # two-call host path, for comparison
+            _, Ue, _ = hpot.forceBatch(2, N5, np.ascontiguousarray(R5[0, [0, M5 + 1]]), s5.atomic_nrs, s5.cell)
+            ends = np.broadcast_to(np.asarray(Ue).reshape(1, 2), (B5, 2))
+            ref5 = NEB.band_forces(hpot, R5, s5.atomic_nrs, s5.cell, s5.fixed, endpoint_energies=ends, climbing_image=1)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                NEB.band_forces(hpot, R5, s5.atomic_nrs, s5.cell, s5.fixed, endpoint_energies=ends, climbing_image=1)
+            wall5_host = (time.perf_counter() - t0) / 3
+        out5 = None
+        for _ in range(3):
+            out5 = NEB.band_forces_resident(npot, R5, s5.atomic_nrs, s5.cell, s5.fixed, climbing_image=1)
+        dev5 = float(np.abs(out5["projected"] - ref5["projected"]).max())
+        barrier()
+        reps5 = 10
+        t0 = time.perf_counter()
+        for _ in range(reps5):
+            out5 = NEB.band_forces_resident(npot, R5, s5.atomic_nrs, s5.cell, s5.fixed, climbing_image=1)
+        wall5 = reduce_max(time.perf_counter() - t0) / reps5
+        c5 = {"workload": "examples/neb-al: 601 Al atoms (200 fixed), in-tree EAM, %d bands x %d movable images, linear "
+                          "reactant -> product paths with U(-0.02,0.02) A jitter; eonb200_neb_band_forces: positions up, one "
+                          "batched EAM launch over all images, one band-kernel launch, projected forces + energies back "
+                          "(host buffers, page-locked by the handle)" % (B5, M5),
+              "bands": int(B5 * world), "images_per_band": M5, "ms_per_band_evaluation_batch": wall5 * 1e3,
+              "ms_two_call_host_path": wall5_host * 1e3, "max_abs_dev_vs_host_path": dev5,
+              "image_force_evals_per_s": B5 * world * M5 / wall5, "atom_force_evals_per_s": B5 * world * M5 * N5 / wall5,
+              "climbing_images": [int(x) for x in np.unique(out5["climbing"])],
+              "max_projected_force": float(NEB.convergence_force(out5["projected"]).max()),
+              "barrier_eV": float(out5["energies"][0].max() - out5["energies"][0, 0])}
+        npot.close()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _, _ = cpu_force_baseline(struct, sets[0], 1.0, True)
@@ -535,7 +587,7 @@ def run_b200(args):
                 "gpu_launches": int(launches), "roofline": roofline,
                 "extra": {"wall_s_timed_region": t_wall, "value_hot_l2": units / world / (t_hot * 1e-3),
                           "value_fresh_list_every_step": units / world / (t_fresh * 1e-3),
-                          "fp64_peak_tflops_measured": fp64_peak / 1e12, "c3": c3, "c4": c4},
+                          "fp64_peak_tflops_measured": fp64_peak / 1e12, "c3": c3, "c4": c4, "c5": c5},
                 "search": search}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -558,6 +610,7 @@ def main():
     ap.add_argument("--no-search", action="store_true")
     ap.add_argument("--no-c3", action="store_true", help="skip the 4096 x 2047-atom data point")
     ap.add_argument("--no-c4", action="store_true", help="skip the akmc-pt Morse process-search data point")
+    ap.add_argument("--no-c5", action="store_true", help="skip the neb-al band-force data point")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -27,7 +27,7 @@ SYMBOLS = [
     "eonb200_walkers_displace_along_mode", "eonb200_walkers_harvest", "eonb200_walkers_last_ms",
     "eonb200_measure_fp64_peak", "eonb200_kernel_launches", "eonb200_nl_stats",
     "eonb200_last_force_ms", "eonb200_phase_clocks", "eonb200_l2_flush",
-    "eonb200_neb_params_default", "eonb200_neb_forces", "eonb200_neb_forces_device",
+    "eonb200_neb_params_default", "eonb200_neb_forces", "eonb200_neb_forces_device", "eonb200_neb_band_forces",
 ]
 
 
@@ -142,4 +142,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.eonb200_neb_forces_device.argtypes = [_vp, C.c_long, C.c_long, C.c_long, C.c_long, C.c_void_p, C.c_void_p,
                                               C.c_void_p, _dp, C.POINTER(NebParams), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.eonb200_neb_forces_device.restype = C.c_int
+    lib.eonb200_neb_band_forces.argtypes = [_vp, C.c_long, C.c_long, C.c_long, _dp, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                            _dp, C.c_int, C.POINTER(NebParams), _dp, _dp, _dp, C.POINTER(C.c_int)]
+    lib.eonb200_neb_band_forces.restype = C.c_int
     return lib

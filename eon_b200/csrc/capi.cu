@@ -102,7 +102,9 @@ struct EonB200Pot {
   std::vector<std::pair<const char *, size_t>> pinned;  // caller ranges page-locked by this handle (pin_host_buffers)
   NlStore nl;  // cache of the stateless batch slots
   DevBuf<double> neb_R, neb_F, neb_E, neb_P, neb_T;  // eonb200_neb_forces staging
-  DevBuf<int> neb_C;
+  DevBuf<int> neb_C, neb_Z;
+  DevBuf<double> neb_box, neb_mask;
+  std::vector<double> neb_hmask;
   int neb_attr = 0;
   unsigned long long force_calls = 0, launches = 0;
   long long last_stats[5] = {0, 0, 0, 0, 0};
@@ -752,10 +754,9 @@ void eonb200_neb_params_default(EonB200NebParams *p) {
   p->energy_weighted = 0;
 }
 
-int eonb200_neb_forces_device(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms,
-                              const double *d_positions, const double *d_forces, const double *d_energies,
-                              const double *box, const EonB200NebParams *prm, double *d_projected, double *d_tangents,
-                              int *d_climbing) {
+static int neb_launch(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms, const double *d_positions,
+                      const double *d_forces, const double *d_energies, const double *box, const EonB200NebParams *prm,
+                      double *d_projected, double *d_tangents, int *d_climbing, const double *d_mask, int remove_net) {
   if (!pot) return 1;
   if (nBands <= 0 || nImages <= 0 || nAtoms <= 0) return fail(pot, 2, "neb_forces: bands, images and atoms must be positive");
   if (!d_positions || !d_forces || !d_energies || !prm || !d_projected || !d_tangents)
@@ -770,6 +771,8 @@ int eonb200_neb_forces_device(EonB200Pot *pot, long nBands, long nImages, long n
   a.projected = d_projected;
   a.tangent = d_tangents;
   a.climbing = d_climbing;
+  a.mask = d_mask;
+  a.remove_net = remove_net;
   a.cell_ok = 0;
   for (int k = 0; k < 9; k++) a.cell[k] = a.inv[k] = 0.0;
   if (box) {
@@ -806,6 +809,88 @@ int eonb200_neb_forces_device(EonB200Pot *pot, long nBands, long nImages, long n
   CU_TRY(pot, cudaGetLastError());
   pot->launches += 1;
   return 0;
+}
+
+int eonb200_neb_forces_device(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms,
+                              const double *d_positions, const double *d_forces, const double *d_energies,
+                              const double *box, const EonB200NebParams *prm, double *d_projected, double *d_tangents,
+                              int *d_climbing) {
+  return neb_launch(pot, nBands, nImages, nAtoms, nFreeAtoms, d_positions, d_forces, d_energies, box, prm, d_projected,
+                    d_tangents, d_climbing, nullptr, 0);
+}
+
+int eonb200_neb_band_forces(EonB200Pot *pot, long nBands, long nImages, long nAtoms, const double *positions,
+                            const int *atomicNrs, const int *fixed, const double *box, int remove_net_force,
+                            const EonB200NebParams *prm, double *projected, double *energies, double *tangents,
+                            int *climbing) {
+  if (!pot) return 1;
+  if (nBands <= 0 || nImages <= 0 || nAtoms <= 0) return fail(pot, 2, "neb_band_forces: bands, images and atoms must be positive");
+  if (!positions || !atomicNrs || !box || !prm || !projected) return fail(pot, 2, "neb_band_forces: null argument");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  const long N = nAtoms, S = nBands * (nImages + 2);
+  const size_t D = 3 * static_cast<size_t>(N);
+  const size_t rows = static_cast<size_t>(S), mov = static_cast<size_t>(nBands) * nImages;
+  if (S > 2147483647L / 2) return fail(pot, 2, "neb_band_forces: too many images");
+  CU_TRY(pot, pot->neb_R.reserve(rows * D));
+  CU_TRY(pot, pot->neb_F.reserve(rows * D));
+  CU_TRY(pot, pot->neb_E.reserve(rows));
+  CU_TRY(pot, pot->neb_P.reserve(mov * D));
+  CU_TRY(pot, pot->neb_T.reserve(mov * D));
+  CU_TRY(pot, pot->neb_C.reserve(static_cast<size_t>(nBands)));
+  CU_TRY(pot, pot->neb_Z.reserve(static_cast<size_t>(N)));
+  CU_TRY(pot, pot->neb_box.reserve(9));
+  CU_TRY(pot, pot->neb_mask.reserve(D));
+  long n_fixed_atoms = 0;
+  bool any_fixed = false;
+  if (fixed) {
+    pot->neb_hmask.resize(D);
+    for (long i = 0; i < N; i++) {
+      bool fx = false;
+      for (int k = 0; k < 3; k++) {
+        pot->neb_hmask[3 * i + k] = fixed[3 * i + k] ? 0.0 : 1.0;
+        fx = fx || fixed[3 * i + k] != 0;
+      }
+      n_fixed_atoms += fx ? 1 : 0;
+    }
+    any_fixed = n_fixed_atoms > 0;
+  }
+  pin_range(pot, positions, rows * D * sizeof(double));
+  pin_range(pot, projected, mov * D * sizeof(double));
+  CU_TRY(pot, cudaMemcpyAsync(pot->neb_R.p, positions, rows * D * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->neb_Z.p, atomicNrs, static_cast<size_t>(N) * sizeof(int), cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(pot->neb_box.p, box, 9 * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  if (any_fixed)
+    CU_TRY(pot, cudaMemcpyAsync(pot->neb_mask.p, pot->neb_hmask.data(), D * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  ForceBatchArgs a;
+  memset(&a, 0, sizeof(a));
+  a.S = static_cast<int>(S);
+  a.N = static_cast<int>(N);
+  a.R = pot->neb_R.p;
+  a.strideR = static_cast<int>(D);
+  a.Z = pot->neb_Z.p;
+  a.strideZ = 0;  // one atomicNrs row and one cell shared by every image
+  a.box = pot->neb_box.p;
+  a.strideBox = 0;
+  a.F = pot->neb_F.p;
+  a.U = pot->neb_E.p;
+  a.force_rebuild = 0;
+  // endpoints ride along in the same launch (2 of nImages + 2 rows): positions, forces and energies keep the
+  // [band][image] layout the band kernel reads, and the endpoint energies come for free
+  auto tail = [&]() -> int {
+    const int rc = neb_launch(pot, nBands, nImages, N, N - n_fixed_atoms, pot->neb_R.p, pot->neb_F.p, pot->neb_E.p, box, prm,
+                              pot->neb_P.p, pot->neb_T.p, pot->neb_C.p, any_fixed ? pot->neb_mask.p : nullptr,
+                              (!any_fixed && remove_net_force) ? 1 : 0);
+    if (rc) return rc;
+    CU_TRY(pot, cudaMemcpyAsync(projected, pot->neb_P.p, mov * D * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+    if (energies) CU_TRY(pot, cudaMemcpyAsync(energies, pot->neb_E.p, rows * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+    if (tangents)
+      CU_TRY(pot, cudaMemcpyAsync(tangents, pot->neb_T.p, mov * D * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
+    if (climbing)
+      CU_TRY(pot, cudaMemcpyAsync(climbing, pot->neb_C.p, static_cast<size_t>(nBands) * sizeof(int), cudaMemcpyDeviceToHost,
+                                  pot->stream));
+    return 0;
+  };
+  return run_force_batch(pot, pot->nl, a, box, true, tail);
 }
 
 int eonb200_neb_forces(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms, const double *positions,

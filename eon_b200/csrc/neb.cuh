@@ -22,6 +22,9 @@ struct NebArgs {
   double *projected;     // [bands][images][3 N]
   double *tangent;       // [bands][images][3 N]
   int *climbing;         // [bands]: index of the climbing image (0 = none), may be null
+  const double *mask;    // [3 N] 1 = free axis, 0 = fixed (Matter::getForces, client/Matter.cpp:324-333); null = frc is
+                         // already masked.  Only set by eonb200_neb_band_forces, which owns the force rows.
+  int remove_net;        // subtract the mean force of each image first (client/Matter.cpp:531-536; no fixed atoms)
   double cell[9], inv[9];
   double ksp, k_min, k_max;
   int images, atoms;
@@ -109,6 +112,26 @@ __device__ __forceinline__ double neb_parallel(const NebArgs &a, const double *E
   return kk[1] * dist_next - kk[0] * dist_prev;
 }
 
+// Matter::getForces on a raw force row in place: fixed axes zeroed, or the mean force removed.  Every thread touches
+// only the atoms it owns in the later passes (atom = thread + k * blockDim).
+__device__ __forceinline__ void neb_matter_forces(const NebArgs &a, double *f, double *red) {
+  if (!a.mask && !a.remove_net) return;
+  const int N = a.atoms;
+  double c[3] = {0.0, 0.0, 0.0};
+  for (int at = threadIdx.x; at < N; at += blockDim.x)
+    for (int k = 0; k < 3; k++) {
+      double v = f[3 * at + k];
+      if (a.mask) v *= a.mask[3 * at + k];
+      f[3 * at + k] = v;
+      c[k] += v;
+    }
+  if (a.remove_net) {
+    block_sum<3>(c, red);
+    for (int at = threadIdx.x; at < N; at += blockDim.x)
+      for (int k = 0; k < 3; k++) f[3 * at + k] -= c[k] / static_cast<double>(N);
+  }
+}
+
 __global__ void __launch_bounds__(256) k_neb_band(NebArgs a) {
   __shared__ double red[4 * kMaxWarps];
   const int M = a.images, N = a.atoms, D = 3 * N;
@@ -120,6 +143,7 @@ __global__ void __launch_bounds__(256) k_neb_band(NebArgs a) {
   double *T = a.tangent + (static_cast<size_t>(band) * M + img - 1) * D;
   double *P = a.projected + (static_cast<size_t>(band) * M + img - 1) * D;
 
+  neb_matter_forces(a, const_cast<double *>(fc), red);
   const NebImage im = neb_image(a, E, img);
   const int rule = im.rule;
   const double c_next = im.c_next, c_prev = im.c_prev;
@@ -271,6 +295,7 @@ __global__ void __launch_bounds__(256) k_neb_band_tma(NebArgs a, size_t total_do
     __syncthreads();
   }
   double *rp = spos + ppad, *rc = rp + D, *rn = rc + D, *fc = sfrc + fpad;
+  neb_matter_forces(a, fc, red);
 
   // pass 1: differences in place (rn <- dNext, rp <- dPrev), raw tangent into rc
   double acc[3] = {0.0, 0.0, 0.0};

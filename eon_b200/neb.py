@@ -92,6 +92,35 @@ def band_forces(pot, positions, atomic_nrs, box, fixed=None, endpoint_energies=N
     return {"projected": P, "tangents": T, "climbing": ci, "energies": E, "forces": F[:, 1:M + 1]}
 
 
+def band_forces_resident(pot, positions, atomic_nrs, box, fixed=None, remove_net_force: bool = True, prm=None,
+                         want_tangents: bool = False, **kw):
+    """`band_forces` as ONE library call (``eonb200_neb_band_forces``): positions up once, all images of all bands in
+    one batched potential launch (endpoints included, so their energies need no separate call), masking and band
+    algebra on the device, only projected forces, energies and climbing images back."""
+    R = np.ascontiguousarray(positions, dtype=np.float64)
+    if R.ndim == 2:
+        R = R[None]
+    B, M2, D = R.shape
+    M, N = M2 - 2, D // 3
+    if M < 1:
+        raise ValueError("a band needs at least one movable image")
+    if prm is None:
+        prm = neb_params(pot._lib, **kw)
+    Z = np.ascontiguousarray(atomic_nrs, dtype=np.int32).reshape(N)
+    cell = np.ascontiguousarray(box, dtype=np.float64).reshape(9)
+    fx = None if fixed is None else np.ascontiguousarray(fixed, dtype=np.int32).reshape(D)
+    P = np.empty((B, M, D))
+    E = np.empty((B, M2))
+    T = np.empty((B, M, D)) if want_tangents else None
+    ci = np.zeros(B, dtype=np.int32)
+    ip = C.POINTER(C.c_int)
+    pot._check(pot._lib.eonb200_neb_band_forces(pot._h, B, M, N, _dp(R), Z.ctypes.data_as(ip),
+                                                None if fx is None else fx.ctypes.data_as(ip), _dp(cell),
+                                                1 if remove_net_force else 0, C.byref(prm), _dp(P), _dp(E),
+                                                None if T is None else _dp(T), ci.ctypes.data_as(ip)))
+    return {"projected": P, "tangents": T, "climbing": ci, "energies": E}
+
+
 def convergence_force(projected, climbing=None, metric: str = "norm", fixed=None, ci_converged_only: bool = False):
     """``NudgedElasticBand::convergenceForce`` per band (client/NudgedElasticBand.cpp:433-466)."""
     P = np.asarray(projected, dtype=float)

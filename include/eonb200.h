@@ -267,6 +267,19 @@ EONB200_API int eonb200_neb_forces(EonB200Pot *pot, long nBands, long nImages, l
                                    const double *box, const EonB200NebParams *prm, double *projected, double *tangents,
                                    int *climbing);
 
+/* One NEB force evaluation of many bands in a single call: positions [nBands][nImages + 2][3 nAtoms] go to the device
+ * once, every image (the two endpoints ride along, which also yields their energies) is evaluated by the handle's
+ * potential in ONE batched launch, Matter::getForces is applied in the band kernel (fixed[3 nAtoms] axes zeroed, or --
+ * when nothing is fixed and remove_net_force is set -- the mean force removed; client/Matter.cpp:324-333,531-536), and
+ * only the results come back: projected [nBands][nImages][3 nAtoms], energies [nBands][nImages + 2] (nullable),
+ * tangents (nullable), climbing[nBands] (nullable).  atomicNrs[nAtoms] and box[9] are shared by all images; fixed may
+ * be null.  Replaces the forceBatch call site AND the per-image loop of NudgedElasticBand::updateForces
+ * (client/NudgedElasticBand.cpp:475-521,584-643).  The force-call counter advances by nBands * (nImages + 2). */
+EONB200_API int eonb200_neb_band_forces(EonB200Pot *pot, long nBands, long nImages, long nAtoms, const double *positions,
+                                        const int *atomicNrs, const int *fixed, const double *box, int remove_net_force,
+                                        const EonB200NebParams *prm, double *projected, double *energies,
+                                        double *tangents, int *climbing);
+
 /* Same with DEVICE pointers for everything but box and prm (bands kept resident between optimiser steps); asynchronous
  * on the handle's stream. */
 EONB200_API int eonb200_neb_forces_device(EonB200Pot *pot, long nBands, long nImages, long nAtoms, long nFreeAtoms,

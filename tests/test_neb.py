@@ -163,3 +163,38 @@ def test_lj13_band_end_to_end(backend, oracle):
     # the reversed band is the same path: same energies mirrored, same climbing image mirrored
     assert np.allclose(out["energies"][0], out["energies"][1][::-1], atol=1e-10)
     assert out["climbing"][0] == M + 1 - out["climbing"][1] or np.isclose(*[out["energies"][k][out["climbing"][k]] for k in (0, 1)])
+
+
+@pytest.mark.parametrize("system", ["lj13", "morse_pt"])
+def test_resident_band_evaluation_matches_host_path(backend, oracle, system):
+    """``eonb200_neb_band_forces`` (one call: all images evaluated and projected on the device) against
+    `band_forces` (forceBatch + host masking + band kernel): all-free LJ13 (mean force removed, zeroTranslation) and the
+    Morse slab with fixed atoms (axes masked in the kernel)."""
+    M, B = 4, 3
+    if system == "lj13":
+        a, b = oracle.load_fixture("lj13.json"), oracle.load_fixture("lj13_product.json")
+        R0, R1, fixed, kind = a["positions"], b["positions"], None, "lj"
+    else:
+        a = oracle.load_fixture("morse_pt_saddle.json")
+        R0, fixed, kind = a["positions"], a["fixed"], "morse_pt"
+        R1 = R0 + (a["displacement_positions"] - R0) * 2.0
+    Z, cell = a["atomic_nrs"], a["cell"]
+    N = len(Z)
+    lam = np.linspace(0.0, 1.0, M + 2).reshape(1, -1, 1, 1)
+    rng = np.random.default_rng(2)
+    free = 1.0 if fixed is None else (1 - fixed).reshape(1, 1, N, 3)
+    R = R0[None, None] + lam * ONEB.pbc(R1 - R0, cell)[None, None] + rng.normal(0.0, 0.01, (B, M + 2, N, 3)) * free
+    R = R.reshape(B, M + 2, -1)
+    for case in (dict(climbing_image=1), dict(projection=1)):
+        with B200Potential(kind, lib=backend) as pot:
+            ref = NEB.band_forces(pot, R, Z, cell, fixed, **case)
+        with B200Potential(kind, lib=backend) as pot:
+            out = NEB.band_forces_resident(pot, R, Z, cell, fixed, want_tangents=True, **case)
+            assert pot.forceCallCounter == B * (M + 2)
+            again = NEB.band_forces_resident(pot, R, Z, cell, fixed, **case)  # cached neighbour lists, no tangents
+        assert np.array_equal(out["climbing"], ref["climbing"])
+        assert np.abs(out["energies"] - ref["energies"]).max() <= 1e-9
+        assert np.abs(out["tangents"] - ref["tangents"]).max() <= 1e-12
+        scale = max(1.0, np.abs(ref["projected"]).max())
+        assert np.abs(out["projected"] - ref["projected"]).max() <= 1e-10 * scale
+        assert np.abs(again["projected"] - out["projected"]).max() <= 1e-10 * scale and again["tangents"] is None
