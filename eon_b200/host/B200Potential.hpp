@@ -59,6 +59,9 @@ public:
     bind(force, "eonb200_force");
     bind(force_batch, "eonb200_force_batch");
     bind(force_calls, "eonb200_force_calls");
+    bind(neb_params_default, "eonb200_neb_params_default");
+    bind(neb_forces, "eonb200_neb_forces");
+    bind(neb_band_forces, "eonb200_neb_band_forces");
   }
 
   decltype(&eonb200_abi_version) abi_version{nullptr};
@@ -69,6 +72,9 @@ public:
   decltype(&eonb200_force) force{nullptr};
   decltype(&eonb200_force_batch) force_batch{nullptr};
   decltype(&eonb200_force_calls) force_calls{nullptr};
+  decltype(&eonb200_neb_params_default) neb_params_default{nullptr};
+  decltype(&eonb200_neb_forces) neb_forces{nullptr};
+  decltype(&eonb200_neb_band_forces) neb_band_forces{nullptr};
 
 private:
   template <typename F>
@@ -130,6 +136,35 @@ public:
   [[nodiscard]] bool isThreadSafe() const noexcept override { return false; }
   [[nodiscard]] bool isSharedInstanceThreadSafe() const noexcept override { return false; }
   [[nodiscard]] bool needsPerImageInstance() const noexcept override { return false; }
+
+  // ---- beyond eonc::Potential: the NEB band algebra (client/NudgedElasticBand.cpp:551-646) ----------------------
+  static EonB200NebParams nebDefaults() {
+    EonB200NebParams p;
+    B200Loader::instance().neb_params_default(&p);
+    return p;
+  }
+  // Tangent, springs, projection, climbing image of nBands bands from positions / Matter forces / energies
+  // ([nBands][nImages + 2][3 nAtoms], [nBands][nImages + 2]) the caller already holds.
+  void nebForces(long nBands, long nImages, long nAtoms, long nFreeAtoms, const double *positions, const double *forces,
+                 const double *energies, const double *box, const EonB200NebParams &prm, double *projected,
+                 double *tangents, int *climbing) {
+    check(B200Loader::instance().neb_forces(m_handle, nBands, nImages, nAtoms, nFreeAtoms, positions, forces, energies,
+                                            box, &prm, projected, tangents, climbing));
+  }
+  // The whole updateForces step in one call: potential on every image, Matter::getForces masking, band algebra.
+  // Counts one force call per image like forceBatch does (endpoints included: they are re-evaluated).
+  void nebBandForces(long nBands, long nImages, long nAtoms, const double *positions, const int *atomicNrs,
+                     const int *fixed, const double *box, bool removeNetForce, const EonB200NebParams &prm,
+                     double *projected, double *energies, double *tangents, int *climbing) {
+    check(B200Loader::instance().neb_band_forces(m_handle, nBands, nImages, nAtoms, positions, atomicNrs, fixed, box,
+                                                 removeNetForce ? 1 : 0, &prm, projected, energies, tangents, climbing));
+    for (long i = 0; i < nBands * (nImages + 2); i++) {
+      forceCallCounter++;
+#ifndef EONB200_HOST_STUB
+      PotRegistry::get().on_force_call(ptype);
+#endif
+    }
+  }
 
   [[nodiscard]] EonB200Pot *handle() const noexcept { return m_handle; }
 

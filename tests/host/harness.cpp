@@ -1,12 +1,15 @@
 // tests/host/harness.cpp -- TEST INFRASTRUCTURE: drives eon_b200/host/B200Potential.hpp the way eonclient does.
 //
-//   harness <lib> <kind> <nSystems> <nAtoms> < input > output
+//   harness <lib> <kind> <nSystems> <nAtoms> [neb] < input > output
 // input (text): for every system 3N positions, then N atomic numbers, then 9 box values.
 // It calls forceBatch with arrays of per-system pointers exactly like client/ImprovedDimer.cpp:176 /
 // client/NudgedElasticBand.cpp:515, then force() on system 0 like client/Matter.cpp:523, and prints
-// energies and forces with %.17g.  Exit code 3 = potential could not be created (no GPU).
+// energies and forces with %.17g.  With "neb" the systems are the images of one band (both endpoints included) and
+// nebBandForces replaces the two calls: prints the climbing image, the energies and the projected forces.
+// Exit code 3 = potential could not be created (no GPU).
 #include "B200Potential.hpp"
 
+#include <algorithm>
 #include <cstdio>
 #include <memory>
 #include <vector>
@@ -44,6 +47,20 @@ int main(int argc, char **argv) {
     pB[s] = B[s].data();
   }
   std::vector<double> E(S), V(S, -1.0);
+  if (argc > 5 && std::string(argv[5]) == "neb") {
+    auto *bp = static_cast<eonc::B200Potential *>(pot.get());
+    std::vector<double> band(S * 3 * N), proj((S - 2) * 3 * N, -777.0);
+    for (long s = 0; s < S; s++) std::copy(R[s].begin(), R[s].end(), band.begin() + s * 3 * N);
+    EonB200NebParams prm = eonc::B200Potential::nebDefaults();
+    prm.climbing_image = 1;
+    int ci = -1;
+    bp->nebBandForces(1, S - 2, N, band.data(), Z[0].data(), nullptr, B[0].data(), true, prm, proj.data(), E.data(),
+                      nullptr, &ci);
+    printf("neb %d calls %zu\n", ci, pot->forceCallCounter.load());
+    for (double e : E) printf("%.17g\n", e);
+    for (double f : proj) printf("%.17g\n", f);
+    return 0;
+  }
   try {
     pot->forceBatch(S, N, pR.data(), pZ.data(), pF.data(), E.data(), V.data(), pB.data());
   } catch (int code) {

@@ -18,14 +18,14 @@ def build_harness():
     assert out.returncode == 0, out.stdout
 
 
-def run(kind, systems):
+def run(kind, systems, *extra):
     S, N = len(systems), len(systems[0][1])
     text = []
     for R, Z, box in systems:
         text.append(" ".join(repr(float(x)) for x in np.asarray(R).reshape(-1)))
         text.append(" ".join(str(int(z)) for z in Z))
         text.append(" ".join(repr(float(x)) for x in np.asarray(box).reshape(-1)))
-    return subprocess.run([HARNESS, LIB, str(kind), str(S), str(N)], input="\n".join(text) + "\n", text=True,
+    return subprocess.run([HARNESS, LIB, str(kind), str(S), str(N)] + list(extra), input="\n".join(text) + "\n", text=True,
                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
 
 
@@ -67,3 +67,23 @@ def test_shim_rethrows_14324():
     build_harness()
     out = run(3, [(np.random.default_rng(0).uniform(0, 5, (4, 3)), [13, 13, 29, 13], np.eye(3) * 10)])
     assert out.returncode == 0 and out.stdout.strip() == "thrown 14324"
+
+
+@pytest.mark.gpu
+def test_shim_neb_band_forces(oracle):
+    """`B200Potential::nebBandForces` (one call for the whole updateForces step) against the Python wrapper."""
+    from eon_b200 import B200Potential, neb as NEB
+    build_harness()
+    a, b = oracle.load_fixture("lj13.json"), oracle.load_fixture("lj13_product.json")
+    M, N = 5, len(a["atomic_nrs"])
+    lam = np.linspace(0.0, 1.0, M + 2).reshape(-1, 1, 1)
+    band = a["positions"][None] + lam * (b["positions"] - a["positions"])[None]
+    out = run(0, [(band[i], a["atomic_nrs"], a["cell"]) for i in range(M + 2)], "neb")
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.split("\n")
+    with B200Potential("lj") as pot:
+        ref = NEB.band_forces_resident(pot, band.reshape(1, M + 2, -1), a["atomic_nrs"], a["cell"], climbing_image=1)
+    assert lines[0] == "neb %d calls %d" % (ref["climbing"][0], M + 2)
+    vals = np.array([float(x) for x in lines[1:] if x])
+    assert np.array_equal(vals[:M + 2], ref["energies"][0])
+    assert np.array_equal(vals[M + 2:], ref["projected"].reshape(-1))
