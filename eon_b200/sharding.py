@@ -63,3 +63,25 @@ def harvest(local: Harvest, dst: int = 0, group=None) -> Optional[Harvest]:
     if rank != dst:
         return None
     return concat_harvests(gathered)
+
+
+def gather_bands(local: dict, dst: int = 0, group=None) -> Optional[dict]:
+    """The same end-of-run exchange for NEB bands: every rank holds the result dictionary of its own bands
+    (`eon_b200.neb.band_forces_resident`: arrays with the band index first); rank `dst` gets them concatenated in band
+    order, the others None.  A band never spans ranks (its images are coupled, client/NudgedElasticBand.cpp:581-592), so
+    this is the only communication."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    gathered = [None] * world if rank == dst else None
+    dist.gather_object(local, gathered, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = {}
+    for key in gathered[0]:
+        vals = [g[key] for g in gathered]
+        out[key] = None if any(v is None for v in vals) else np.concatenate(vals, axis=0)
+    return out

@@ -92,3 +92,55 @@ def test_reference_arm_runs_on_rank0_only():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps",
                           "1", "--warmup", "0"], env=env, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def _band_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, HERE)
+    import emu_lib
+    import oracle_lib
+    from eon_b200 import B200Potential, neb as NEB
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        a, b = oracle_lib.load_fixture("lj13.json"), oracle_lib.load_fixture("lj13_product.json")
+        B, M = 5, 3
+        lam = np.linspace(0.0, 1.0, M + 2).reshape(1, -1, 1, 1)
+        R = a["positions"][None, None] + lam * (b["positions"] - a["positions"])[None, None] \
+            + np.random.default_rng(9).normal(0.0, 0.02, (B, M + 2, len(a["atomic_nrs"]), 3))
+        R = R.reshape(B, M + 2, -1)
+        lo, hi = sharding.shard_range(B, rank, world)
+        with B200Potential("lj", lib=emu_lib.lib()) as pot:
+            mine = NEB.band_forces_resident(pot, R[lo:hi], a["atomic_nrs"], a["cell"], climbing_image=1)
+            got = sharding.gather_bands(mine, dst=0)
+            if rank == 0:
+                ref = NEB.band_forces_resident(pot, R, a["atomic_nrs"], a["cell"], climbing_image=1)
+                ok = all(np.array_equal(got[k], ref[k]) for k in ("projected", "energies", "climbing")) \
+                    and got["tangents"] is None and got["projected"].shape[0] == B
+                q.put(("rank0", bool(ok), hi - lo))
+            else:
+                q.put(("other", got is None, hi - lo))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bands_shard_over_two_gloo_ranks():
+    """NEB bands shard like walkers: each rank evaluates its own bands (emulation backend here), one gather at the end."""
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_band_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    out = dict((o[0], o[1:]) for o in out)
+    assert out["rank0"][0] is True and out["other"][0] is True
+    assert out["rank0"][1] + out["other"][1] == 5
