@@ -81,6 +81,27 @@ def test_band_forces_sizes(backend, case, n_atoms):
         assert np.abs(P[b].reshape(M, n_atoms, 3) - P0).max() <= 1e-11 * max(1.0, np.abs(P0).max())
 
 
+def test_band_forces_triclinic_cell(backend):
+    """General (sheared) cell: the full fractional-coordinate minimum image instead of the orthorhombic shortcut."""
+    B, M, N = 2, 4, 19
+    cell = np.array([[9.0, 0.0, 0.0], [2.5, 8.0, 0.0], [-1.0, 1.5, 10.0]])
+    rng = np.random.default_rng(21)
+    frac = rng.uniform(0.0, 1.0, (B, 1, N, 3)) + np.linspace(0.0, 1.0, M + 2).reshape(1, -1, 1, 1) * rng.normal(0, 0.05, (B, 1, N, 3))
+    frac -= np.floor(frac)                      # wrapped per image: neighbouring images may sit a whole cell apart
+    R = frac @ cell
+    F = rng.normal(0.0, 0.5, (B, M + 2, N, 3))
+    E = rng.normal(0.0, 1.0, (B, M + 2))
+    for case in (dict(climbing_image=1), dict(projection=1), dict(projection=2)):
+        with B200Potential("lj", lib=backend) as pot:
+            P, T, ci = NEB.neb_forces(pot, R.reshape(B, M + 2, -1), F.reshape(B, M + 2, -1), E, cell, N - 1, **case)
+        for b in range(B):
+            P0, T0, ci0 = ONEB.band_forces(R[b], F[b], E[b], cell, N - 1, climbing_image=bool(case.get("climbing_image")),
+                                           projection=case.get("projection", 0))
+            assert ci[b] == ci0
+            assert np.abs(T[b].reshape(M, N, 3) - T0).max() <= 1e-12
+            assert np.abs(P[b].reshape(M, N, 3) - P0).max() <= 1e-10 * max(1.0, np.abs(P0).max())
+
+
 def test_band_force_properties(backend):
     """Unit tangents, nudging (only the spring acts along the tangent), climbing-image inversion, zero translation."""
     B, M, N = 3, 5, 17
