@@ -15,7 +15,7 @@ MINMODE_DIMER, MINMODE_LANCZOS = 0, 1
 ROT_SD, ROT_CG, ROT_LBFGS = 0, 1, 2
 METRIC_NORM, METRIC_MAX_ATOM, METRIC_MAX_COMPONENT = 0, 1, 2
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 #: every symbol include/eonb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -53,7 +53,7 @@ class Config(C.Structure):
                 ("n_eam_rows", C.c_int), ("eam_rows", C.POINTER(EamRow)),
                 ("eam_conservative", C.c_int), ("skin", C.c_double), ("threads_per_walker", C.c_int),
                 ("tiles_override", C.c_int), ("lpa_override", C.c_int),
-                ("pin_host_buffers", C.c_int)]
+                ("pin_host_buffers", C.c_int), ("eam_pair_mode", C.c_int)]
 
 
 class SearchParams(C.Structure):

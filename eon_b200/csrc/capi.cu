@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <string>
@@ -70,6 +71,12 @@ struct NlStore {
   DevBuf<double> rbuild, pairA, pairB, dfd, upart;
   DevBuf<double4> pos4;
   DevBuf<unsigned char> rowid;
+  // owner / receiver lists of the Newton's-third-law EAM kernel (types.cuh: NlBatch::own_*)
+  DevBuf<int> recv_code, roff, hl_hdr, lane_atom, atom_lane;
+  DevBuf<int2> cls2, own_cs;
+  DevBuf<double2> own_ab;
+  int n3 = 0;          // lists allocated
+  int slots_seen = 0;  // most receiver slots any walker of this store needed (sizes the launch's shared memory)
   long S = 0, N = 0;
   int K = 0, Np = 0;
 };
@@ -318,6 +325,41 @@ void pick_fused(const EonB200Pot *pot, long S, long N, int *T_out, int *threads_
 #endif
 }
 
+// Newton's-third-law EAM kernel: one lane per atom up to 448 atoms (two CTAs per SM), more atoms per lane beyond.
+int pick_n3_threads(const EonB200Pot *pot, long N) {
+#ifdef EONB200_EMU
+  (void)pot;
+  (void)N;
+  return 1;
+#else
+  long t;
+  if (pot->cfg.threads_per_walker > 0)
+    t = (pot->cfg.threads_per_walker + 31) / 32 * 32;
+  else if (N <= 448)
+    t = std::max<long>(64, (N + 31) / 32 * 32);
+  else
+    t = std::min<long>(1024, (N + 1) / 2 + 31) / 32 * 32;
+  return static_cast<int>(std::min<long>(std::max<long>(t, 32), 1024));
+#endif
+}
+
+bool use_n3(const EonB200Pot *pot, long N) {
+  return pot->cfg.kind == EONB200_POT_EAM && pot->cfg.eam_pair_mode != 1 &&
+         static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0)) + 8 * 8 * N <= pot->max_dyn_smem && pot->cfg.skin > 0.0;
+}
+
+// Receiver slots the next launch reserves shared memory for: what the lists built so far needed plus a margin, or --
+// before the first build -- an estimate from the row capacity; never more than the SM has.
+int pick_slot_cap(const EonB200Pot *pot, const NlStore &nl, long N) {
+  long want = nl.slots_seen > 0 ? nl.slots_seen + nl.slots_seen / 16 + 64 : N * nl.K / 3;
+  const long room = (pot->max_dyn_smem - static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0))) / 8 - 16;
+  want = std::min(want, room);
+  // two CTAs per SM when that is within reach
+  const long two = ((227 * 1024) / 2 - 1024 - static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0))) / 8 - 16;
+  if (nl.slots_seen > 0 && nl.slots_seen <= two) want = std::min(want, two);
+  return static_cast<int>(std::max<long>(want, 0) / 16 * 16);
+}
+
 int pick_max_cells(long N) { return static_cast<int>(std::min<long>(std::max<long>(64, N), 4096)); }
 
 // Row capacity guess from the mean density; truncated builds are detected and regrown.
@@ -329,10 +371,10 @@ int guess_K(double rc, long N, const double *box) {
   long K = static_cast<long>(std::ceil(1.5 * expect)) + 16;
   K = std::min<long>(K, std::max<long>(N - 1, 16) + 32);
   K = (K + 7) / 8 * 8;
-  return static_cast<int>(std::max<long>(K, 8));
+  return static_cast<int>(std::max<long>(K, 16));  // (the half-list EAM kernel requests its first 16 rows unconditionally)
 }
 
-int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K) {
+int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K, bool n3_lists = false) {
   const int Np = static_cast<int>((N + 31) / 32 * 32);
   CU_TRY(pot, nl.nbr.reserve(static_cast<size_t>(S) * K * Np));
   CU_TRY(pot, nl.cnt.reserve(static_cast<size_t>(S) * Np));
@@ -353,6 +395,24 @@ int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K) {
     CU_TRY(pot, nl.cnt2.reserve(static_cast<size_t>(S) * Np));
     nl.scratch_stride = static_cast<int>(fused_scratch_ints(static_cast<int>(N), pick_max_cells(N)));
     CU_TRY(pot, nl.cellscratch.reserve(static_cast<size_t>(S) * nl.scratch_stride));
+    nl.n3 = 0;
+    nl.slots_seen = 0;
+    if (n3_lists && use_n3(pot, N)) {
+      nl.n3 = 1;
+      const size_t cells = static_cast<size_t>(S) * K * Np;
+      CU_TRY(pot, nl.own_cs.reserve(cells));
+      CU_TRY(pot, nl.recv_code.reserve(cells));
+      CU_TRY(pot, nl.own_ab.reserve(cells));
+      CU_TRY(pot, nl.cls2.reserve(static_cast<size_t>(S) * Np));
+      CU_TRY(pot, nl.roff.reserve(static_cast<size_t>(S) * (Np + 1)));
+      CU_TRY(pot, nl.lane_atom.reserve(static_cast<size_t>(S) * Np));
+      CU_TRY(pot, nl.atom_lane.reserve(static_cast<size_t>(S) * Np));
+      CU_TRY(pot, cudaMemsetAsync(nl.lane_atom.p, 0, sizeof(int) * S * Np, pot->stream));
+      CU_TRY(pot, nl.hl_hdr.reserve(static_cast<size_t>(S) * 8));
+      CU_TRY(pot, cudaMemsetAsync(nl.hl_hdr.p, 0, sizeof(int) * 8 * S, pot->stream));
+      CU_TRY(pot, cudaMemsetAsync(nl.cls2.p, 0, sizeof(int2) * S * Np, pot->stream));
+      CU_TRY(pot, cudaMemsetAsync(nl.roff.p, 0, sizeof(int) * S * (Np + 1), pot->stream));
+    }
   }
   CU_TRY(pot, cudaMemsetAsync(nl.state.p, 0, sizeof(int) * S, pot->stream));
   CU_TRY(pot, cudaMemsetAsync(nl.done.p, 0, sizeof(int) * S, pot->stream));
@@ -388,6 +448,15 @@ NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
   b.flags = nl.flags.p;
   b.upart = nl.upart.p;
   b.done = nl.done.p;
+  b.own_cs = nl.n3 ? nl.own_cs.p : nullptr;
+  b.recv_code = nl.n3 ? nl.recv_code.p : nullptr;
+  b.own_ab = nl.n3 ? nl.own_ab.p : nullptr;
+  b.cls2 = nl.n3 ? nl.cls2.p : nullptr;
+  b.roff = nl.n3 ? nl.roff.p : nullptr;
+  b.lane_atom = nl.n3 ? nl.lane_atom.p : nullptr;
+  b.atom_lane = nl.n3 ? nl.atom_lane.p : nullptr;
+  b.hl_hdr = nl.n3 ? nl.hl_hdr.p : nullptr;
+  b.slot_cap = 0;
   return b;
 }
 
@@ -439,7 +508,7 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
   if (nl.S < S || nl.N != N || nl.K == 0) {
     double unit[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     const int K = std::max(nl.N == N ? nl.K : 0, guess_K(pot->hp.rc_list, N, h_box0 ? h_box0 : unit));
-    int rc = nl_alloc(pot, nl, S, N, K);
+    int rc = nl_alloc(pot, nl, S, N, K, true);
     if (rc) return rc;
   }
   a.maxCells = pick_max_cells(N);
@@ -453,7 +522,22 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
   // EAM: one cluster of T CTAs per walker
   int fused_T = 1, fused_threads = 1;
   size_t fused_smem = 0;
-  if (eam) {
+  const bool n3 = eam && use_n3(pot, N) && nl.n3;
+  int slot_cap = 0;
+  if (n3) {
+    fused_T = 1;
+    fused_threads = pick_n3_threads(pot, N);
+    a.tiles = 1;
+    a.lpa = 1;
+    a.kmax = nl.K;
+    a.clocks = nullptr;
+    if (pot->clocks_on) {
+      pot->clocks_ctas = S;
+      CU_TRY(pot, pot->d_clocks.reserve(static_cast<size_t>(pot->clocks_ctas) * 16));
+      CU_TRY(pot, cudaMemsetAsync(pot->d_clocks.p, 0, sizeof(long long) * pot->clocks_ctas * 16, pot->stream));
+      a.clocks = pot->d_clocks.p;
+    }
+  } else if (eam) {
     pick_fused(pot, S, N, &fused_T, &fused_threads);
     fused_smem = smem_bytes_fused(static_cast<int>(N));
     if (static_cast<long>(fused_smem) > pot->max_dyn_smem)
@@ -482,8 +566,34 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
     CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
     NlBatch view = nl_view(pot, nl);
+    if (n3) {
+      slot_cap = pick_slot_cap(pot, nl, N);
+      fused_smem = smem_bytes_n3(static_cast<int>(N), slot_cap);
+      view.slot_cap = slot_cap;
+    }
     CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
-    if (eam) {
+    if (n3) {
+      const dim3 grid(1u, static_cast<unsigned>(S));
+#ifdef EONB200_EMU
+      EONB200_LAUNCH(k_eam_n3, grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+#else
+      static const int n3_minb = getenv("EONB200_N3_MINB") ? atoi(getenv("EONB200_N3_MINB")) : 0;  // development aid
+      const bool two = n3_minb != 1 && 2 * (fused_smem + 1024) <= 227 * 1024;
+      if (n3_minb == 2 && fused_threads <= 224 && two)
+        EONB200_LAUNCH((k_eam_n3_t<224, 2>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+      else if (n3_minb != 1 && fused_threads <= 224 && 4 * (fused_smem + 1024) <= 227 * 1024)
+        EONB200_LAUNCH((k_eam_n3_t<224, 4>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+      else if (fused_threads <= 448 && two)
+        EONB200_LAUNCH((k_eam_n3_t<448, 2>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+      else if (fused_threads <= 512 && two)
+        EONB200_LAUNCH((k_eam_n3_t<512, 2>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+      else if (fused_threads <= 512)
+        EONB200_LAUNCH((k_eam_n3_t<512, 1>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+      else
+        EONB200_LAUNCH((k_eam_n3_t<1024, 1>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+#endif
+      pot->launches += 1;
+    } else if (eam) {
       const dim3 grid(static_cast<unsigned>(fused_T), static_cast<unsigned>(S));
 #ifdef EONB200_EMU
       EONB200_LAUNCH_CLUSTER(k_eam_fused, grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
@@ -535,6 +645,7 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     pot->last_stats[2] = nl.K;
     pot->last_stats[3] = need;
     pot->last_stats[4] = static_cast<long long>(pot->h_stats.p[2]);
+    if (n3) nl.slots_seen = std::max(nl.slots_seen, static_cast<int>(pot->h_stats.p[3]));
     if (need <= nl.K) {
       nl.rowmax_seen = std::max(nl.rowmax_seen, need);
       return 0;
@@ -544,7 +655,7 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     pot->force_calls -= static_cast<unsigned long long>(S);
     const int K = (static_cast<int>(need * 1.2) + 8 + 7) / 8 * 8;
     nl.K = 0;
-    rc = nl_alloc(pot, nl, S, N, K);
+    rc = nl_alloc(pot, nl, S, N, K, true);
     if (rc) return rc;
     a.force_rebuild = 1;
   }
@@ -631,6 +742,7 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
       return bail("eonb200_create: cannot allocate device memory");
     }
     pot->hp.exp_tab = pot->d_exp_tab.p;
+    for (int j = 0; j < 16; j++) pot->hp.exp_t16[j] = static_cast<double>(exp2l(static_cast<long double>(j) / 16.0L));
   }
   bool ok = cudaStreamCreate(&pot->stream) == cudaSuccess;
   for (int k = 0; k < 3 && ok; k++) ok = cudaEventCreate(&pot->ev[k]) == cudaSuccess;
@@ -666,6 +778,18 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_fused_t<512, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<224, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<224, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<448, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<512, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<1024, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
 #endif
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_pair), cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -33,6 +33,7 @@ constexpr double kSafeEps = 1e-300;  // include/eon/SafeMath.h:19
 #define EONB200_LIKELY(x) (__builtin_expect(!!(x), 1))
 
 #ifdef EONB200_EMU
+#define __grid_constant__
 #define EONB200_NOINLINE __attribute__((noinline))
 #else
 #define EONB200_NOINLINE __noinline__
@@ -295,6 +296,62 @@ __device__ __forceinline__ int ld_cg(const int *p) {
 #endif
 }
 __device__ __forceinline__ double ld_cg(const double *p) {
+#ifndef EONB200_EMU
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+// ---- shared-memory FP64 accumulation (half-list EAM kernel: both atoms of a pair receive its contribution) -------
+// sm_100a has no native shared FP64 add: the instruction is a load / DADD / compare-and-swap loop.  add3 keeps the
+// three loops of a force vector in flight together (three loads, three adds, three CAS) and retries a component only
+// when its CAS lost a race, which is rare: the lanes of a warp push to distinct atoms nearly always.
+__device__ __forceinline__ void smem_add_f64(double *p, double v) {
+#ifdef EONB200_EMU
+  *p += v;
+#else
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void smem_add3_f64(double *p, double x, double y, double z) {
+#ifdef EONB200_EMU
+  p[0] += x;
+  p[1] += y;
+  p[2] += z;
+#else
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  unsigned long long o0, o1, o2, r0, r1, r2;
+  asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(o0) : "r"(a) : "memory");
+  asm volatile("ld.volatile.shared.b64 %0, [%1+8];" : "=l"(o1) : "r"(a) : "memory");
+  asm volatile("ld.volatile.shared.b64 %0, [%1+16];" : "=l"(o2) : "r"(a) : "memory");
+  const unsigned long long n0 = static_cast<unsigned long long>(__double_as_longlong(__longlong_as_double(static_cast<long long>(o0)) + x));
+  const unsigned long long n1 = static_cast<unsigned long long>(__double_as_longlong(__longlong_as_double(static_cast<long long>(o1)) + y));
+  const unsigned long long n2 = static_cast<unsigned long long>(__double_as_longlong(__longlong_as_double(static_cast<long long>(o2)) + z));
+  asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(r0) : "r"(a), "l"(o0), "l"(n0) : "memory");
+  asm volatile("atom.shared.cas.b64 %0, [%1+8], %2, %3;" : "=l"(r1) : "r"(a), "l"(o1), "l"(n1) : "memory");
+  asm volatile("atom.shared.cas.b64 %0, [%1+16], %2, %3;" : "=l"(r2) : "r"(a), "l"(o2), "l"(n2) : "memory");
+  if (r0 != o0) asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(a), "d"(x) : "memory");
+  if (r1 != o1) asm volatile("red.shared.add.f64 [%0+8], %1;" ::"r"(a), "d"(y) : "memory");
+  if (r2 != o2) asm volatile("red.shared.add.f64 [%0+16], %1;" ::"r"(a), "d"(z) : "memory");
+#endif
+}
+// Barrier + CTA-wide OR of a predicate (one barrier instruction).
+__device__ __forceinline__ int cta_any(int p) {
+#ifdef EONB200_EMU
+  return p;
+#else
+  return __syncthreads_or(p);
+#endif
+}
+__device__ __forceinline__ int2 ld_cg(const int2 *p) {
+#ifndef EONB200_EMU
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ double2 ld_cg(const double2 *p) {
 #ifndef EONB200_EMU
   return __ldcg(p);
 #else

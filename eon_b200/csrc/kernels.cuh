@@ -630,6 +630,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_eam_fused_t(const PotParams *__r
 }
 #endif
 
+}  // namespace eonb200
+#include "eam_n3.cuh"
+namespace eonb200 {
+
 // Neighbour lists only (eonb200_neighbors): build with the caller's cutoff, skin 0.
 __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_neighbors(NlBatch nl, NlParams np, int S, int N, const double *R,
                                                                     const double *box, int maxCells, const double *exp_tab) {

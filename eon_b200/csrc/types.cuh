@@ -33,6 +33,7 @@ struct PotParams {
   int eam_fast_ok;        // every EAM row (or the Morse parameters) keeps its exp arguments inside exp_tab_fast's
                           // range (set by the host)
   const double *exp_tab;  // [128] 2^(j/128), device memory (table of the exp used by the pair loops)
+  double exp_t16[16];     // 2^(j/16): the one-line table of exp_t16 (Newton's-third-law EAM kernel)
   EamRowDev rows[kMaxEamRows];
 };
 
@@ -80,6 +81,19 @@ struct NlBatch {
   int *flags;       // [S] bit 0: more than one element, bit 1: element without a row
   double *upart;    // [S][kMaxTiles][4] energy / pair-count partials per tile and pass
   int *done;        // [S] tiles finished (last one sums the partials in tile order)
+  // owner / receiver lists of the Newton's-third-law EAM kernel (eam_n3.cuh).  Every unordered pair of the sure-in
+  // and uncertain classes is OWNED by one of its atoms (parity rule): the owner evaluates it and hands the partner's
+  // share over through a slot of shared memory.  Slot-major like nbr (lanes = atoms read consecutive words).
+  int2 *own_cs;     // [S][K][Np] pairs atom i owns, sure-in first, then uncertain: x = code (j | image << 20), y = the
+                    //            partner's receiver slot for this pair (index into the CTA's slot buffer)
+  int *recv_code;   // [S][K][Np] codes of the pairs atom i receives, in slot order
+  int2 *cls2;       // [S][Np]    x = owned sure-in | owned uncertain << 16, y = received (sure-in + uncertain)
+  int *lane_atom;   // [S][Np]    atom of lane position t (atoms ranked by owned pairs); the lists above are stored by lane
+  int *atom_lane;   // [S][Np]    its inverse
+  int *roff;        // [S][Np + 1] first slot of lane position t (exclusive scan of the received counts); [N] = slots in use
+  double2 *own_ab;  // [S][K][Np] (g'(r)/r, -(+-phi'(r)/r)) of the owned pairs, written by the density pass
+  int *hl_hdr;      // [S][8]     [0] slots in use, [1] 1 = lists valid, [2] list rows in use (multiple of 4)
+  int slot_cap;     // receiver slots the launch has shared memory for
 };
 
 // One system as seen by its CTA.
@@ -107,6 +121,14 @@ struct SysView {
   int *flags;
   double *upart;
   int *done;
+  int2 *own_cs;
+  int *recv_code;
+  int2 *cls2;
+  int *lane_atom, *atom_lane;
+  int *roff;
+  double2 *own_ab;
+  int *hl_hdr;
+  int slot_cap;
 };
 
 __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, const double *R, const int *Z,
@@ -137,6 +159,16 @@ __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, con
   v.flags = nl.flags ? nl.flags + s : nullptr;
   v.upart = nl.upart ? nl.upart + static_cast<size_t>(s) * kMaxTiles * 4 : nullptr;
   v.done = nl.done ? nl.done + s : nullptr;
+  const size_t kn = static_cast<size_t>(s) * nl.K * nl.Np;
+  v.own_cs = nl.own_cs ? nl.own_cs + kn : nullptr;
+  v.recv_code = nl.recv_code ? nl.recv_code + kn : nullptr;
+  v.own_ab = nl.own_ab ? nl.own_ab + kn : nullptr;
+  v.cls2 = nl.cls2 ? nl.cls2 + static_cast<size_t>(s) * nl.Np : nullptr;
+  v.roff = nl.roff ? nl.roff + static_cast<size_t>(s) * (nl.Np + 1) : nullptr;
+  v.lane_atom = nl.lane_atom ? nl.lane_atom + static_cast<size_t>(s) * nl.Np : nullptr;
+  v.atom_lane = nl.atom_lane ? nl.atom_lane + static_cast<size_t>(s) * nl.Np : nullptr;
+  v.hl_hdr = nl.hl_hdr ? nl.hl_hdr + static_cast<size_t>(s) * 8 : nullptr;
+  v.slot_cap = nl.slot_cap;
   return v;
 }
 
@@ -176,6 +208,13 @@ struct Smem {
   float4 *sh27f;     // [27] single-precision copy (fused kernel pre-filter)
   float4 *posf;      // [N]   fused kernel: single-precision copy of the positions (pre-filter)
   double *clu;       // [2 * 8] fused kernel: energy / pair-count partials of the CTAs of a cluster (rank 0 sums them)
+  double *rho;       // (unused)
+  double *facc;      // (unused)
+  // Newton's-third-law EAM kernel (eam_n3.cuh)
+  double2 *pxy;      // [N + 1] (x, y) of the prepared positions: a 16-byte stride spreads a gather over all banks
+  double2 *pzw;      // [N + 1] (z, F'(rho))
+  double *t16;       // [16] 2^(j/16), one 128-byte line: any lookup of a warp is conflict free
+  double *slots;     // [slot_cap] receiver slots: the partner's share of a pair (g, then the force scalar)
   int maxCells;
 };
 
@@ -234,6 +273,11 @@ __device__ inline Smem carve_smem_tile(unsigned char *base, int N) {
   s.stage = nullptr;
   s.clu = nullptr;
   s.posf = nullptr;
+  s.rho = nullptr;
+  s.facc = nullptr;
+  s.pxy = s.pzw = nullptr;
+  s.t16 = nullptr;
+  s.slots = nullptr;
   s.cell_of = s.wrapc = s.order = s.cell_start = s.cell_fill = nullptr;
   s.maxCells = 0;
   return s;
@@ -261,6 +305,11 @@ __host__ __device__ inline size_t fused_scratch_ints(int N, int maxCells) {
 
 __device__ inline Smem carve_smem_fused(unsigned char *base, int N, int maxCells, int *scratch) {
   Smem s;
+  s.rho = nullptr;
+  s.facc = nullptr;
+  s.pxy = s.pzw = nullptr;
+  s.t16 = nullptr;
+  s.slots = nullptr;
   size_t o = 0;
   s.pos = reinterpret_cast<double4 *>(base + o);
   o += align_up(sizeof(double4) * (N + 1) + 32, 128);
@@ -292,6 +341,26 @@ __device__ inline Smem carve_smem_fused(unsigned char *base, int N, int maxCells
   s.cell_start = scratch ? scratch + 3 * Np : nullptr;
   s.cell_fill = scratch ? scratch + 3 * Np + Cp : nullptr;
   s.maxCells = maxCells;
+  return s;
+}
+
+// Newton's-third-law EAM kernel: the fused kernel's layout (its cold paths and its ordered-pair lane functions run
+// unchanged) followed by the split position arrays, the exp table line and the receiver slots.
+__host__ __device__ inline size_t smem_bytes_n3(int N, int slot_cap) {
+  return align_up(smem_bytes_fused(N), 128) + 2 * align_up(sizeof(double2) * (static_cast<size_t>(N) + 1), 128) + 128 +
+         align_up(sizeof(double) * static_cast<size_t>(slot_cap), 128);
+}
+
+__device__ inline Smem carve_smem_n3(unsigned char *base, int N, int maxCells, int *scratch) {
+  Smem s = carve_smem_fused(base, N, maxCells, scratch);
+  size_t o = align_up(smem_bytes_fused(N), 128);
+  s.pxy = reinterpret_cast<double2 *>(base + o);
+  o += align_up(sizeof(double2) * (static_cast<size_t>(N) + 1), 128);
+  s.pzw = reinterpret_cast<double2 *>(base + o);
+  o += align_up(sizeof(double2) * (static_cast<size_t>(N) + 1), 128);
+  s.t16 = reinterpret_cast<double *>(base + o);
+  o += 128;
+  s.slots = reinterpret_cast<double *>(base + o);
   return s;
 }
 
@@ -336,6 +405,11 @@ __device__ inline Smem carve_smem(unsigned char *base, int N, int maxCells, bool
   s.shz = s.shy + 16;
   s.sh27 = reinterpret_cast<double4 *>(s.shz + 16);
   s.clu = nullptr;
+  s.rho = nullptr;
+  s.facc = nullptr;
+  s.pxy = s.pzw = nullptr;
+  s.t16 = nullptr;
+  s.slots = nullptr;
   s.maxCells = maxCells;
   return s;
 }

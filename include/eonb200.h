@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONB200_ABI_VERSION 3
+#define EONB200_ABI_VERSION 4
 
 #if defined(_WIN32)
 #define EONB200_API __declspec(dllexport)
@@ -73,6 +73,11 @@ typedef struct EonB200Config {
                              (cudaHostRegister, cached per handle, released at destroy) and copy straight from / to
                              them instead of staging through the handle's own pinned buffers.  The caller must keep
                              such buffers allocated until eonb200_destroy.  0 (default): always stage.          */
+  int eam_pair_mode;      /* EAM force_batch kernel.  0 (default): every unordered pair evaluated once (Newton's third
+                             law; both atoms accumulate in shared memory, so results agree run to run to rounding,
+                             ~1e-16 relative).  1: every ordered pair evaluated from its own atom's row, fixed summation
+                             order (bit-reproducible; about twice the arithmetic).  Systems with several elements or a
+                             box narrower than 2 (r_cut + skin) + skin always take the ordered-pair general code.        */
 } EonB200Config;
 
 typedef struct EonB200Pot EonB200Pot; /* opaque */

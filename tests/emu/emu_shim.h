@@ -106,6 +106,11 @@ inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v)
   *p += v;
   return o;
 }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
+  unsigned long long o = *p;
+  if (v > o) *p = v;
+  return o;
+}
 inline int atomicMax(int *p, int v) {
   int o = *p;
   if (v > o) *p = v;
@@ -119,6 +124,14 @@ struct float4 {
   float x, y, z, w;
 };
 inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+struct int2 {
+  int x, y;
+};
+inline int2 make_int2(int x, int y) { return int2{x, y}; }
+struct double2 {
+  double x, y;
+};
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 using std::max;
 using std::min;
 

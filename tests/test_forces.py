@@ -184,12 +184,18 @@ def test_even_and_odd_atom_counts(backend, oracle):
                 assert_parity(F[s], U[s], F0, U0)
 
 
-@pytest.mark.parametrize("kw", [dict(tiles_override=1, threads_per_walker=64),   # several atoms per thread, one CTA
-                                dict(tiles_override=2, threads_per_walker=32),   # ... in a two-CTA cluster
-                                dict(tiles_override=4), dict(tiles_override=8)])  # one atom per thread, wide clusters
+@pytest.mark.parametrize("kw", [
+    # ordered-pair kernel (eam_pair_mode=1): cluster sizes and atoms per thread
+    dict(eam_pair_mode=1, tiles_override=1, threads_per_walker=64),   # several atoms per thread, one CTA
+    dict(eam_pair_mode=1, tiles_override=2, threads_per_walker=32),   # ... in a two-CTA cluster
+    dict(eam_pair_mode=1, tiles_override=4), dict(eam_pair_mode=1, tiles_override=8),  # one atom per thread, wide clusters
+    # half-list kernel (default): CTA sizes below, at and above the atom count (the half list is laid out per size)
+    dict(threads_per_walker=64), dict(threads_per_walker=224), dict(), dict(threads_per_walker=512),
+    dict(threads_per_walker=1024)])
 def test_fused_eam_launch_shapes(backend, oracle, kw):
-    """Every shape of the fused EAM kernel (cluster size, atoms per thread) gives the oracle's forces, with a fresh
-    list, a reused list and a list rebuilt inside the kernel after a large displacement."""
+    """Every shape of the two EAM kernels gives the oracle's forces, with a fresh list, a reused list, a list whose
+    atoms drifted beyond skin / 4 (every candidate screened again) and a list rebuilt inside the kernel after a large
+    displacement."""
     from eon_b200 import workloads as WL
     s = WL.load_structure("akmc_al.json")
     opot = oracle.potential(oracle.POT_EAM)
@@ -205,10 +211,15 @@ def test_fused_eam_launch_shapes(backend, oracle, kw):
 
 
 def test_caller_owned_pinned_buffers(backend, oracle):
-    """pin_host_buffers + out=: the page-locked direct path returns what the staged path returns, bit for bit."""
+    """pin_host_buffers + out=: the page-locked direct path returns what the staged path returns."""
     from eon_b200 import workloads as WL
     s = WL.load_structure("akmc_al.json")
     R = np.ascontiguousarray(WL.jitter(s.positions, 5, 0.05, seed=3).reshape(5, -1))
+
+    def same(a, b):  # the half-list kernel's shared-memory accumulation order is free: equal to rounding
+        a, b = np.asarray(a).reshape(-1), np.asarray(b).reshape(-1)
+        return np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+
     with B200Potential("eam", lib=backend) as pot:
         F0, U0, _ = pot.forceBatch(5, s.n_atoms, R, s.atomic_nrs, s.cell.reshape(9))
     out = np.full((5, 3 * s.n_atoms), np.nan)
@@ -216,12 +227,12 @@ def test_caller_owned_pinned_buffers(backend, oracle):
         for _ in range(2):  # second call: ranges already registered
             F1, U1, _ = pot.forceBatch(5, s.n_atoms, R, s.atomic_nrs, s.cell.reshape(9), out=out)
             assert F1.base is out or np.shares_memory(F1, out)
-            assert np.array_equal(F1.reshape(5, -1), F0.reshape(5, -1)) and np.array_equal(U1, U0)
+            assert same(F1, F0) and same(U1, U0)
         # per-system topologies and boxes still work next to the shared-row shortcut
         Zs = np.tile(s.atomic_nrs, (5, 1))
         Bs = np.tile(s.cell.reshape(9), (5, 1))
         F2, U2, _ = pot.forceBatch(5, s.n_atoms, R, Zs, Bs)
-        assert np.array_equal(F2.reshape(5, -1), F0.reshape(5, -1)) and np.array_equal(U2, U0)
+        assert same(F2, F0) and same(U2, U0)
     with pytest.raises(ValueError):
         with B200Potential("eam", lib=backend) as pot:
             pot.forceBatch(5, s.n_atoms, R, s.atomic_nrs, s.cell.reshape(9), out=np.zeros(7))
