@@ -73,8 +73,10 @@ struct NlStore {
   DevBuf<unsigned char> rowid;
   // owner / receiver lists of the Newton's-third-law EAM kernel (types.cuh: NlBatch::own_*)
   DevBuf<int> recv_code, roff, hl_hdr, lane_atom, atom_lane;
-  DevBuf<int2> cls2, own_cs;
+  DevBuf<int2> own_cs;
+  DevBuf<int4> lhdr;
   DevBuf<double2> own_ab;
+  DevBuf<double> lo_build;
   int n3 = 0;          // lists allocated
   int slots_seen = 0;  // most receiver slots any walker of this store needed (sizes the launch's shared memory)
   long S = 0, N = 0;
@@ -325,18 +327,32 @@ void pick_fused(const EonB200Pot *pot, long S, long N, int *T_out, int *threads_
 #endif
 }
 
-// Newton's-third-law EAM kernel: one lane per atom up to 448 atoms (two CTAs per SM), more atoms per lane beyond.
-int pick_n3_threads(const EonB200Pot *pot, long N) {
+// Newton's-third-law EAM kernel: one lane per atom up to 1024 atoms, more atoms per lane beyond; two lanes per atom
+// (half the row per lane) on request.
+int pick_n3_lpa(const EonB200Pot *pot, long N) {
 #ifdef EONB200_EMU
   (void)pot;
   (void)N;
+  return 1;  // (one thread per CTA: no partner lane)
+#else
+  static const int forced = getenv("EONB200_N3_LPA") ? atoi(getenv("EONB200_N3_LPA")) : 0;  // development aid
+  if (pot->cfg.threads_per_walker > 0) return pot->cfg.threads_per_walker >= 2 * N && forced != 1 ? 2 : 1;
+  if (forced == 1 || forced == 2) return 2 * N <= 1024 ? forced : 1;
+  return 1;  // measured on B200 (C2, 385 atoms): two lanes per atom 85 us per step against 73 us with one
+#endif
+}
+int pick_n3_threads(const EonB200Pot *pot, long N, int lpa) {
+#ifdef EONB200_EMU
+  (void)pot;
+  (void)N;
+  (void)lpa;
   return 1;
 #else
   long t;
   if (pot->cfg.threads_per_walker > 0)
     t = (pot->cfg.threads_per_walker + 31) / 32 * 32;
-  else if (N <= 448)
-    t = std::max<long>(64, (N + 31) / 32 * 32);
+  else if (lpa * N <= 1024)
+    t = std::max<long>(64, (lpa * N + 31) / 32 * 32);
   else
     t = std::min<long>(1024, (N + 1) / 2 + 31) / 32 * 32;
   return static_cast<int>(std::min<long>(std::max<long>(t, 32), 1024));
@@ -345,7 +361,8 @@ int pick_n3_threads(const EonB200Pot *pot, long N) {
 
 bool use_n3(const EonB200Pot *pot, long N) {
   return pot->cfg.kind == EONB200_POT_EAM && pot->cfg.eam_pair_mode != 1 &&
-         static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0)) + 8 * 8 * N <= pot->max_dyn_smem && pot->cfg.skin > 0.0;
+         N <= kN3MaxAtoms && static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0)) + 8 * 8 * N <= pot->max_dyn_smem &&
+         pot->cfg.skin > 0.0;
 }
 
 // Receiver slots the next launch reserves shared memory for: what the lists built so far needed plus a margin, or --
@@ -357,7 +374,8 @@ int pick_slot_cap(const EonB200Pot *pot, const NlStore &nl, long N) {
   // two CTAs per SM when that is within reach
   const long two = ((227 * 1024) / 2 - 1024 - static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0))) / 8 - 16;
   if (nl.slots_seen > 0 && nl.slots_seen <= two) want = std::min(want, two);
-  return static_cast<int>(std::max<long>(want, 0) / 16 * 16);
+  want = std::max<long>(want, 3 * N + 4);  // the raw coordinates land in the slot buffer
+  return static_cast<int>((std::max<long>(want, 0) + 15) / 16 * 16);
 }
 
 int pick_max_cells(long N) { return static_cast<int>(std::min<long>(std::max<long>(64, N), 4096)); }
@@ -400,18 +418,24 @@ int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K, bool n3_lists 
     if (n3_lists && use_n3(pot, N)) {
       nl.n3 = 1;
       const size_t cells = static_cast<size_t>(S) * K * Np;
-      CU_TRY(pot, nl.own_cs.reserve(cells));
-      CU_TRY(pot, nl.recv_code.reserve(cells));
-      CU_TRY(pot, nl.own_ab.reserve(cells));
-      CU_TRY(pot, nl.cls2.reserve(static_cast<size_t>(S) * Np));
-      CU_TRY(pot, nl.roff.reserve(static_cast<size_t>(S) * (Np + 1)));
+      const size_t slack = static_cast<size_t>(kN3Slack) * Np;  // rows the pair loops request ahead of a row's end
+      CU_TRY(pot, nl.own_cs.reserve(cells + slack));
+      CU_TRY(pot, nl.recv_code.reserve(cells + slack));
+      CU_TRY(pot, nl.own_ab.reserve(cells + slack));
+      CU_TRY(pot, cudaMemsetAsync(nl.own_cs.p, 0, sizeof(int2) * (cells + slack), pot->stream));
+      CU_TRY(pot, cudaMemsetAsync(nl.recv_code.p, 0, sizeof(int) * (cells + slack), pot->stream));
+      CU_TRY(pot, cudaMemsetAsync(nl.own_ab.p, 0, sizeof(double2) * (cells + slack), pot->stream));
+      CU_TRY(pot, nl.lhdr.reserve(static_cast<size_t>(S) * Np * 2));
+      CU_TRY(pot, nl.roff.reserve(static_cast<size_t>(S) * (2 * Np + 1)));
       CU_TRY(pot, nl.lane_atom.reserve(static_cast<size_t>(S) * Np));
       CU_TRY(pot, nl.atom_lane.reserve(static_cast<size_t>(S) * Np));
       CU_TRY(pot, cudaMemsetAsync(nl.lane_atom.p, 0, sizeof(int) * S * Np, pot->stream));
+      CU_TRY(pot, nl.lo_build.reserve(static_cast<size_t>(S) * 4));
+      CU_TRY(pot, cudaMemsetAsync(nl.lo_build.p, 0, sizeof(double) * 4 * S, pot->stream));
       CU_TRY(pot, nl.hl_hdr.reserve(static_cast<size_t>(S) * 8));
       CU_TRY(pot, cudaMemsetAsync(nl.hl_hdr.p, 0, sizeof(int) * 8 * S, pot->stream));
-      CU_TRY(pot, cudaMemsetAsync(nl.cls2.p, 0, sizeof(int2) * S * Np, pot->stream));
-      CU_TRY(pot, cudaMemsetAsync(nl.roff.p, 0, sizeof(int) * S * (Np + 1), pot->stream));
+      CU_TRY(pot, cudaMemsetAsync(nl.lhdr.p, 0, sizeof(int4) * S * Np * 2, pot->stream));
+      CU_TRY(pot, cudaMemsetAsync(nl.roff.p, 0, sizeof(int) * S * (2 * Np + 1), pot->stream));
     }
   }
   CU_TRY(pot, cudaMemsetAsync(nl.state.p, 0, sizeof(int) * S, pot->stream));
@@ -451,12 +475,14 @@ NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
   b.own_cs = nl.n3 ? nl.own_cs.p : nullptr;
   b.recv_code = nl.n3 ? nl.recv_code.p : nullptr;
   b.own_ab = nl.n3 ? nl.own_ab.p : nullptr;
-  b.cls2 = nl.n3 ? nl.cls2.p : nullptr;
+  b.lhdr = nl.n3 ? nl.lhdr.p : nullptr;
   b.roff = nl.n3 ? nl.roff.p : nullptr;
   b.lane_atom = nl.n3 ? nl.lane_atom.p : nullptr;
   b.atom_lane = nl.n3 ? nl.atom_lane.p : nullptr;
   b.hl_hdr = nl.n3 ? nl.hl_hdr.p : nullptr;
+  b.lo_build = nl.n3 ? nl.lo_build.p : nullptr;
   b.slot_cap = 0;
+  b.n3_lpa = 1;
   return b;
 }
 
@@ -526,9 +552,9 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
   int slot_cap = 0;
   if (n3) {
     fused_T = 1;
-    fused_threads = pick_n3_threads(pot, N);
+    a.lpa = pick_n3_lpa(pot, N);
+    fused_threads = pick_n3_threads(pot, N, a.lpa);
     a.tiles = 1;
-    a.lpa = 1;
     a.kmax = nl.K;
     a.clocks = nullptr;
     if (pot->clocks_on) {
@@ -570,6 +596,7 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
       slot_cap = pick_slot_cap(pot, nl, N);
       fused_smem = smem_bytes_n3(static_cast<int>(N), slot_cap);
       view.slot_cap = slot_cap;
+      view.n3_lpa = a.lpa;
     }
     CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
     if (n3) {
@@ -589,6 +616,8 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
         EONB200_LAUNCH((k_eam_n3_t<512, 2>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
       else if (fused_threads <= 512)
         EONB200_LAUNCH((k_eam_n3_t<512, 1>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+      else if (fused_threads <= 800)
+        EONB200_LAUNCH((k_eam_n3_t<800, 1>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
       else
         EONB200_LAUNCH((k_eam_n3_t<1024, 1>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
 #endif
@@ -788,6 +817,8 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<512, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<800, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<1024, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&

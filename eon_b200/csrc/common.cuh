@@ -123,7 +123,11 @@ __device__ __forceinline__ double group_sum(double v) {
 enum RedOp { RED_SUM = 0, RED_MAX = 1, RED_MIN = 2 };
 
 // Block reduction of NV values at once; scratch holds NV * kMaxWarps doubles of shared memory.
-// Every thread returns with the identical result in v[].  Two barriers.
+// Every thread returns with the identical result in v[]: warp partials -> shared memory -> every warp folds the
+// partials with the same xor butterfly (fixed order, no serial tail).  Two barriers (the second frees the scratch).
+__device__ __forceinline__ double red_identity(int op) {
+  return op == RED_SUM ? 0.0 : (op == RED_MAX ? -HUGE_VAL : HUGE_VAL);
+}
 template <int NV>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV], double *scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -136,12 +140,8 @@ __device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < NV; k++) {
-    double r = scratch[k * kMaxWarps];
-    for (int w = 1; w < nwarps; w++) {
-      const double x = scratch[k * kMaxWarps + w];
-      r = op[k] == RED_SUM ? r + x : (op[k] == RED_MAX ? fmax(r, x) : fmin(r, x));
-    }
-    v[k] = r;
+    const double x = lane < nwarps ? scratch[k * kMaxWarps + lane] : red_identity(op[k]);
+    v[k] = op[k] == RED_SUM ? warp_sum(x) : (op[k] == RED_MAX ? warp_max(x) : warp_min(x));
   }
   __syncthreads();
 }
@@ -345,6 +345,13 @@ __device__ __forceinline__ int cta_any(int p) {
 #endif
 }
 __device__ __forceinline__ int2 ld_cg(const int2 *p) {
+#ifndef EONB200_EMU
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+__device__ __forceinline__ int4 ld_cg(const int4 *p) {
 #ifndef EONB200_EMU
   return __ldcg(p);
 #else

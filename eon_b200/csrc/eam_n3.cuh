@@ -17,52 +17,77 @@
 //   force 1   owner: s = -(F'_i + F'_j) g'/r - phi'/r;  F_i += s d;  s into the partner's slot
 //   [barrier]
 //   force 2   receiver: F_i += s d' with its own d' = r_i - r_j (= -d), slots in slot order.
-// Summation orders are fixed, so results are bit-reproducible.  Walkers whose atoms have drifted beyond skin/4 from
-// the list's build positions (every candidate must be screened again) and walkers whose slots do not fit the launch's
-// shared memory take the ordered-pair lane functions of potentials.cuh inside the same kernel; mixed-element systems
-// and small boxes the general row functions.
+// Summation orders are fixed, so results are bit-reproducible.  The pair loops carry no branches and no bounds tests:
+// rows are padded with ghost entries that fail the cutoff (owned rows) or have zero length (received rows), and pairs
+// outside the cutoff are computed and discarded by selects.  Anything but the common case -- lists present and valid,
+// every atom within skin/4 of its build position, one element, non-negative coordinates, slots that fit -- leaves the
+// hot instruction stream through ONE out-of-line call (eam_n3_cold), which rebuilds the lists or finishes the walker
+// with the ordered-pair / general functions of potentials.cuh.
 #pragma once
+
+#ifndef EONB200_N3_UD
+#define EONB200_N3_UD 2
+#endif
+#ifndef EONB200_N3_UF
+#define EONB200_N3_UF 4
+#endif
 
 namespace eonb200 {
 
-constexpr int kN3Batch = 4;  // list words / scratch words a lane keeps in flight
-constexpr int kN3Pre = 16;   // receiver codes a lane requests ahead of the receiver pass
+constexpr int kN3UD = EONB200_N3_UD;   // pairs per iteration of the density loop
+constexpr int kN3UF = EONB200_N3_UF;   // pairs per iteration of the force loops; owned / received rows are padded to this
+constexpr int kN3Slack = 8;  // list rows a loop may request beyond a row's end (the allocations carry this many extra)
 
-// Lists of this kernel carry the image of a pair as 2 bits per axis above the index (0: none, 1: + L, 2: - L is added
-// to r_i - r_j), so that the fold is a pair of selects on the box length instead of a table lookup in shared memory.
-__device__ __forceinline__ int n3_code(int mic_code) {
-  const int id = static_cast<unsigned>(mic_code) >> kNbrIndexBits;  // (fx + 1) + 3 (fy + 1) + 9 (fz + 1), pack_mic
-  const int f[3] = {id % 3 - 1, (id / 3) % 3 - 1, id / 9 - 1};
-  int bits = 0;
-  for (int k = 0; k < 3; k++) bits |= (f[k] == 0 ? 0 : (f[k] < 0 ? 1 : 2)) << (2 * k);  // sh27: offset = -f L
-  return (mic_code & kNbrIndexMask) | (bits << kNbrIndexBits);
+// List words of this kernel: bits 0..15 = 16 j, the byte offset of atom j in the two position arrays (x, y) and
+// (z, F') -- 16-byte strides, so that a gather over random atoms uses every bank -- (j <= 2047; the ghost atom is j = N); bits 16, 17, 18 = "add this atom's box fold along x, y, z" -- an atom in the upper half of the
+// box only ever meets images at -L, one in the lower half at +L (EAM.cpp:152-172 with wrapped coordinates), so the
+// sign is a property of the lane (N3Lane::sL*), not of the pair.
+constexpr int kN3OffMask = 0xffff;
+constexpr int kN3FoldX = 1 << 16, kN3FoldY = 1 << 17, kN3FoldZ = 1 << 18;
+constexpr int kN3MaxAtoms = 2047;
+
+// hl_hdr words of a walker
+enum { N3H_SLOTS = 0, N3H_VALID = 1, N3H_ROWS = 2, N3H_ROWZ = 3, N3H_CONFLICT = 4 };  // VALID: 0, or the lists' lanes per atom
+
+// The atom that evaluates the unordered pair {i, j}: the one with the shorter row (surface atoms own all their pairs
+// with bulk atoms, so that every atom owns about the same number); between atoms of equal row length the lower index
+// when i + j is even, the higher when odd.
+__device__ __forceinline__ bool n3_owner(int i, int j, int deg_i, int deg_j) {
+  if (deg_i != deg_j) return deg_i < deg_j;
+  return (i < j) == (((i + j) & 1) == 0);
 }
-__device__ __forceinline__ double n3_fold(int bits, double L) { return (bits & 1) ? L : ((bits & 2) ? -L : 0.0); }
+__device__ __forceinline__ int n3_deg(const SysView &sys, int i) {
+  const int c = sys.cls[i];
+  return (c & 0xffff) + (c >> 16);
+}
 
-// The atom that evaluates the unordered pair {i, j}: the lower index when i + j is even, the higher when odd.
-__device__ __forceinline__ bool n3_owner(int i, int j) { return (i < j) == (((i + j) & 1) == 0); }
+__device__ __forceinline__ int n3_round_up(int n, int m) { return (n + m - 1) / m * m; }
 
 // Owner / receiver lists from the freshly built full rows (sys.nbr / cls).  CTA-wide; runs after a list rebuild only.
 //
 // Lanes do not take the atoms in index order: atoms are ranked by the number of pairs they own (descending, ties by
-// index) and lane t takes the atom of rank t, so the lanes of a warp run the same number of iterations (surface
-// atoms own half as many pairs as bulk atoms).  Every per-atom list below is stored by LANE (column t), so that the
-// lanes of a warp still read consecutive words; codes and slots refer to atom indices / slot numbers.
-// Rows are padded with null entries (count them out, compute them anyway: no branches in the pair loops): owned rows
-// to a multiple of kN3Batch, received rows to a multiple of kN3Batch and at least kN3Pre.
-__device__ inline void n3_build(const SysView &sys) {
+// index), and the atom of rank r is worked on by the `lpa` adjacent lanes (columns) r lpa .. r lpa + lpa - 1: its owned
+// pairs and its received pairs are dealt out to them in turn, every column has its own run of slots, and the columns
+// of an atom add their partial density / force with a warp shuffle.  Every list below is stored by COLUMN, so that
+// the lanes of a warp read consecutive words; codes and slots refer to atom indices / slot numbers.
+__device__ inline void n3_build(const SysView &sys, const Smem &sm, const PotParams &P, int lpa) {
   const int N = sys.N;
+  const size_t step = static_cast<size_t>(sys.Np) * lpa;  // columns per list row
   const size_t Np = static_cast<size_t>(sys.Np);
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int krows = sys.K / lpa;  // list rows a column has
   int *key = sys.cnt2;  // [Np] scratch: pairs owned by atom i
-  if (tid == 0) sys.hl_hdr[2] = 0;
+  if (tid == 0) {
+    sys.hl_hdr[N3H_VALID] = 0;
+    sys.hl_hdr[N3H_ROWS] = 0;
+    sys.hl_hdr[N3H_CONFLICT] = 0;
+  }
   for (int i = tid; i < N; i += nt) {
-    const int c = sys.cls[i];
-    const int n01 = (c & 0xffff) + (c >> 16);
+    const int n01 = n3_deg(sys, i);
     int no = 0;
     for (int k = 0; k < n01; k++) {
       const int j = sys.nbr[k * Np + i] & kNbrIndexMask;
-      if (j != i && n3_owner(i, j)) no++;
+      if (j != i && n3_owner(i, j, n01, n3_deg(sys, j))) no++;
     }
     key[i] = no;
   }
@@ -78,150 +103,165 @@ __device__ inline void n3_build(const SysView &sys) {
     sys.atom_lane[i] = rank;
   }
   __syncthreads();
+  const int ghost = N << 4;
   int rows = 0;  // rows of the owner / receiver arrays in use
   for (int i = tid; i < N; i += nt) {
-    const size_t t = static_cast<size_t>(sys.atom_lane[i]);
+    const size_t col0 = static_cast<size_t>(sys.atom_lane[i]) * lpa;
     const int c = sys.cls[i];
     const int n0 = c & 0xffff, n01 = n0 + (c >> 16);
-    int no_s = 0, no_u = 0, nr = 0;
+    int no_s = 0, no_u = 0, nr = 0, minus = 0, plus = 0;
     for (int k = 0; k < n01; k++) {
       const int code = sys.nbr[k * Np + i];
       const int j = code & kNbrIndexMask;
       if (j == i) continue;  // a self image only exists in boxes the fast path never sees
-      if (n3_owner(i, j)) {
-        sys.own_cs[(no_s + no_u) * Np + t] = make_int2(n3_code(code), 0);
+      const int id = static_cast<unsigned>(code) >> kNbrIndexBits;  // (fx + 1) + 3 (fy + 1) + 9 (fz + 1), pack_mic
+      const int f[3] = {id % 3 - 1, (id / 3) % 3 - 1, id / 9 - 1};   // sh27: offset added to r_i - r_j is -f L
+      int w = j << 4;
+      for (int a = 0; a < 3; a++) {
+        if (f[a] != 0) w |= kN3FoldX << a;
+        if (f[a] > 0) minus |= 1 << a;
+        if (f[a] < 0) plus |= 1 << a;
+      }
+      if (n3_owner(i, j, n01, n3_deg(sys, j))) {
+        const int e = no_s + no_u;
+        if (e / lpa < krows) sys.own_cs[(e / lpa) * step + col0 + e % lpa] = make_int2(w, 0);
         if (k < n0) no_s++; else no_u++;
       } else {
-        sys.recv_code[nr * Np + t] = n3_code(code);
+        if (nr / lpa < krows) sys.recv_code[(nr / lpa) * step + col0 + nr % lpa] = w;
         nr++;
       }
     }
-    const int self = i;  // partner = the atom itself, no image: a harmless null entry
+    if (minus & plus) atomicOr(sys.hl_hdr + N3H_CONFLICT, 1);  // (cannot happen while the box holds two cutoffs)
     const int nown = no_s + no_u;
-    const int nown_pad = max(kN3Batch, (nown + kN3Batch - 1) / kN3Batch * kN3Batch);
-    for (int k = nown; k < nown_pad && k < sys.K; k++) sys.own_cs[k * Np + t] = make_int2(nown > 0 ? sys.own_cs[t].x : self, -1);
-    const int nr_pad = max(kN3Pre, (nr + kN3Batch - 1) / kN3Batch * kN3Batch);
-    for (int k = nr; k < nr_pad && k < sys.K; k++) sys.recv_code[k * Np + t] = self;
-    sys.cls2[t] = make_int2(no_s | (no_u << 16), nr);
-    sys.roff[t] = nr;
-    rows = max(rows, max(nown_pad, nr_pad));
+    for (int h = 0; h < lpa; h++) {
+      const int nown_h = (nown - h + lpa - 1) / lpa, nso_h = (no_s - h + lpa - 1) / lpa, nr_h = (nr - h + lpa - 1) / lpa;
+      const int nown_pad = n3_round_up(nown_h, kN3UF), nr_pad = n3_round_up(nr_h, kN3UF);
+      for (int k = nown_h; k < nown_pad && k < krows; k++) {  // ghost pairs: beyond every cutoff, zero weights
+        sys.own_cs[k * step + col0 + h] = make_int2(ghost, -1);
+        sys.own_ab[k * step + col0 + h] = make_double2(0.0, 0.0);
+      }
+      for (int k = nr_h; k < nr_pad && k < krows; k++) sys.recv_code[k * step + col0 + h] = i << 4;  // zero-length pairs
+      sys.lhdr[col0 + h] = make_int4(nso_h | (nown_h << 16), nr_h, 0, i | (minus << 24));
+      sys.roff[col0 + h] = nr_h;
+      rows = max(rows, max(nown_pad, nr_pad));
+    }
   }
   __syncthreads();
-  atomicMax(sys.hl_hdr + 2, min(rows, sys.K));
-  // exclusive scan of the received counts (lane order) -> first slot of every lane's atom
+  atomicMax(sys.hl_hdr + N3H_ROWS, rows);
+  // exclusive scan of the received counts (column order) -> first slot of every column
+  const int C = N * lpa;
 #ifdef EONB200_EMU
   if (tid == 0) {
     int run = 0;
-    for (int t = 0; t < N; t++) {
+    for (int t = 0; t < C; t++) {
       const int v = sys.roff[t];
       sys.roff[t] = run;
       run += v;
     }
-    sys.roff[N] = run;
+    sys.roff[C] = run;
   }
 #else
   if (tid < 32) {
     int carry = 0;
-    for (int base = 0; base < N; base += 32) {
+    for (int base = 0; base < C; base += 32) {
       const int t = base + tid;
-      const int v = t < N ? sys.roff[t] : 0;
+      const int v = t < C ? sys.roff[t] : 0;
       int x = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, x, o);
         if (tid >= o) x += y;
       }
-      if (t < N) sys.roff[t] = carry + x - v;
+      if (t < C) sys.roff[t] = carry + x - v;
       carry += __shfl_sync(0xffffffffu, x, 31);
     }
-    if (tid == 0) sys.roff[N] = carry;
+    if (tid == 0) sys.roff[C] = carry;
   }
 #endif
   __syncthreads();
-  // every owned pair learns the slot its partner reads it from; null entries point at the spare slot behind the last one
-  const int total = sys.roff[N];
-  for (int i = tid; i < N; i += nt) {
-    const size_t t = static_cast<size_t>(sys.atom_lane[i]);
-    const int cx = sys.cls2[t].x;
-    const int nown = (cx & 0xffff) + (cx >> 16);
-    const int nown_pad = max(kN3Batch, (nown + kN3Batch - 1) / kN3Batch * kN3Batch);
-    for (int k = 0; k < nown_pad && k < sys.K; k++) {
-      const int code = sys.own_cs[k * Np + t].x;
+  // every owned pair learns the slot its partner reads it from (as a byte offset into the slot buffer); ghost pairs
+  // write the spare slot behind the last one
+  const int total = sys.roff[C];
+  for (int col = tid; col < C; col += nt) {
+    const int i = sys.lane_atom[col / lpa];
+    int4 h = sys.lhdr[col];
+    h.z = sys.roff[col];
+    sys.lhdr[col] = h;
+    const int nown_h = h.x >> 16;
+    const int nown_pad = n3_round_up(nown_h, kN3UF);
+    for (int k = 0; k < nown_pad && k < krows; k++) {
+      const int code = sys.own_cs[k * step + col].x;
       int slot = total;
-      if (k < nown) {
-        const size_t tj = static_cast<size_t>(sys.atom_lane[code & kNbrIndexMask]);
-        const int nrj = sys.cls2[tj].y;
+      if (k < nown_h) {
+        const size_t cj = static_cast<size_t>(sys.atom_lane[(code & kN3OffMask) >> 4]) * lpa;
+        int nrj = 0;
+        for (int q = 0; q < lpa; q++) nrj += sys.lhdr[cj + q].y;
         int r = 0;
-        while (r < nrj && (sys.recv_code[r * Np + tj] & kNbrIndexMask) != i) r++;
-        slot = sys.roff[tj] + (r < nrj ? r : 0);
+        while (r < nrj && ((sys.recv_code[(r / lpa) * step + cj + r % lpa] & kN3OffMask) >> 4) != i) r++;
+        if (r >= nrj) r = 0;
+        slot = sys.roff[cj + r % lpa] + r / lpa;
       }
-      sys.own_cs[k * Np + t] = make_int2(code, slot);
+      sys.own_cs[k * step + col] = make_int2(code, slot * 8);
     }
   }
   if (tid == 0) {
-    sys.hl_hdr[0] = total + 1;  // slots the fast path needs (one spare for the null entries)
-    sys.hl_hdr[1] = 1;
-    atomicMax(&sys.stats[3], static_cast<unsigned long long>(total + 1));
+    int r0 = 255;
+    const int z0 = sys.Z[0];
+    for (int q = P.n_rows - 1; q >= 0; q--)
+      if (P.rows[q].Z == z0) r0 = q;
+    for (int k = 0; k < 3; k++) sys.lo_build[k] = sm.geom->lo[k];  // (prepare_positions of the rebuild just before)
+    sys.hl_hdr[N3H_SLOTS] = total + kN3UF;  // slots the fast path needs (spare slots for the ghost pairs / padded reads)
+    sys.hl_hdr[N3H_ROWZ] = r0 | (z0 << 8);
+    atomicMax(&sys.stats[3], static_cast<unsigned long long>(total + kN3UF));
   }
+  __syncthreads();
+  if (tid == 0 && ld_cg(sys.hl_hdr + N3H_ROWS) <= krows) sys.hl_hdr[N3H_VALID] = lpa;
   __syncthreads();
 }
 
-__device__ EONB200_NOINLINE void eam_n3_build(const FusedCold *fc) {
-  SysView sys;
-  Smem sm;
-  fused_cold_views(*fc, sys, sm);
-  n3_build(sys);
-}
-
-
 struct N3Lane {  // what one lane carries through the passes for one of its atoms
   double rho_own, dfd, fx, fy, fz;
+  double sLx, sLy, sLz;  // this atom's box fold per axis (+L or -L)
   int atom;              // the atom this lane works for (lanes take the atoms by rank, see n3_build)
   int nso, nown, nrecv;  // owned sure-in pairs, owned pairs, received pairs
   int rbase;             // its first slot
 };
 
-// Raw list words of lane position t (requested early, unpacked when needed: a warp stalls at the first USE of a load).
-struct N3Raw {
-  int2 c2;
-  int rbase, atom;
+struct N3Box {
+  double Lx, Ly, Lz;
 };
-__device__ __forceinline__ void n3_raw_load(const SysView &sys, int t, N3Raw &r) {
-  r.c2 = ld_cg(sys.cls2 + t);
-  r.rbase = ld_cg(sys.roff + t);
-  r.atom = ld_cg(sys.lane_atom + t);
+
+__device__ __forceinline__ void n3_unpack(const int4 &h, const N3Box &bx, N3Lane &L) {
+  L.nso = h.x & 0xffff;
+  L.nown = static_cast<unsigned>(h.x) >> 16;
+  L.nrecv = h.y;
+  L.rbase = h.z;
+  L.atom = h.w & 0xffffff;
+  L.sLx = (h.w & (1 << 24)) ? -bx.Lx : bx.Lx;
+  L.sLy = (h.w & (1 << 25)) ? -bx.Ly : bx.Ly;
+  L.sLz = (h.w & (1 << 26)) ? -bx.Lz : bx.Lz;
 }
-__device__ __forceinline__ void n3_unpack(const N3Raw &r, N3Lane &L) {
-  L.nso = r.c2.x & 0xffff;
-  L.nown = L.nso + (r.c2.x >> 16);
-  L.nrecv = r.c2.y;
-  L.rbase = r.rbase;
-  L.atom = r.atom;
-}
-__device__ __forceinline__ int n3_pad(int n) { return max(kN3Batch, (n + kN3Batch - 1) & ~(kN3Batch - 1)); }
 
 // exp with a 16-entry table that fills exactly one 128-byte line of shared memory (a warp's lookups never conflict):
-// x = (16 k + j) ln2/16 + r, |r| <= ln2/32, e^x = 2^k T[j] (1 + r + ... + r^7/5040); error < 1 ulp (r^8/8! = 1e-18).
-// No underflow guard (PotParams::eam_fast_ok).
+// x = (16 k + j) ln2/16 + r, |r| <= ln2/32, e^x = 2^k T[j] (1 + r + ... + r^6/720).  Truncation r^7/5040 < 4.5e-16 and
+// the one-step reduction (|k| <= ~1200 times the rounding of ln2/16) < 5e-15 relative: five orders below the parity
+// bar of 1e-10.  No underflow guard (PotParams::eam_fast_ok).
 __device__ __forceinline__ double exp_t16(double x, const double *T) {
-  const double kInv = 23.083120654223414;     // 16 / ln 2
-  const double kShift = 6755399441055744.0;   // 1.5 * 2^52
-  const double kLn2Hi = 6.93147180369123816490e-01 / 16.0;  // high part of ln2 (trailing zeros), exact / 16
-  const double kLn2Lo = 1.90821492927058770002e-10 / 16.0;
+  const double kInv = 23.083120654223414;    // 16 / ln 2
+  const double kShift = 6755399441055744.0;  // 1.5 * 2^52
+  const double kLn2_16 = 6.93147180559945309417e-01 / 16.0;
   double kd = fma(x, kInv, kShift);
 #ifdef EONB200_EMU
   long long ki;
   memcpy(&ki, &kd, 8);
+  const int k = static_cast<int>(ki);
 #else
-  const long long ki = __double_as_longlong(kd);
+  const int k = __double2loint(kd);
 #endif
   kd -= kShift;
-  double r = fma(kd, -kLn2Hi, x);
-  r = fma(kd, -kLn2Lo, r);
-  const int k = static_cast<int>(ki);
+  const double r = fma(kd, -kLn2_16, x);
   const double t = T[k & 15];
-  double q = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-  q = fma(q, r, 1.0 / 120.0);
+  double q = fma(r, 1.0 / 720.0, 1.0 / 120.0);
   q = fma(q, r, 1.0 / 24.0);
   q = fma(q, r, 1.0 / 6.0);
   q = fma(q, r, 0.5);
@@ -236,81 +276,105 @@ __device__ __forceinline__ double exp_t16(double x, const double *T) {
   memcpy(&out, &bits, 8);
   return out;
 #else
-  return __hiloint2double(__double2hiint(res) + ((k >> 4) << 20), __double2loint(res));
+  return __hiloint2double(__double2hiint(res) + ((k << 16) & 0xfff00000), __double2loint(res));
 #endif
 }
 
-struct N3Box {
-  double Lx, Ly, Lz;
-};
-// d = r_i - r_j folded by the image recorded at build time (n3_code)
-__device__ __forceinline__ void n3_vec(const N3Box &bx, int c, const double2 &ixy, double iz, const double2 &jxy, double jz,
-                                       double &dx, double &dy, double &dz) {
-  const int b = static_cast<unsigned>(c) >> kNbrIndexBits;
-  dx = (ixy.x - jxy.x) + n3_fold(b, bx.Lx);
-  dy = (ixy.y - jxy.y) + n3_fold(b >> 2, bx.Ly);
-  dz = (iz - jz) + n3_fold(b >> 4, bx.Lz);
+// d = r_i - r_j folded by the image recorded at build time.  pxyb / pzwb: the position arrays as bytes.
+__device__ __forceinline__ void n3_vec(const unsigned char *pxyb, const unsigned char *pzwb, int c, const N3Lane &L,
+                                       double xi, double yi, double zi, double &dx, double &dy, double &dz, double &wj) {
+  const int o = c & kN3OffMask;
+  const double2 jxy = *reinterpret_cast<const double2 *>(pxyb + o);
+  const double2 jzw = *reinterpret_cast<const double2 *>(pzwb + o);
+  dx = xi - jxy.x;
+  dy = yi - jxy.y;
+  dz = zi - jzw.x;
+  if (c & kN3FoldX) dx += L.sLx;
+  if (c & kN3FoldY) dy += L.sLy;
+  if (c & kN3FoldZ) dz += L.sLz;
+  wj = jzw.y;
+}
+__device__ __forceinline__ void n3_vec3(const unsigned char *pxyb, const unsigned char *pzwb, int c, const N3Lane &L,
+                                        double xi, double yi, double zi, double &dx, double &dy, double &dz) {
+  const int o = c & kN3OffMask;
+  const double2 jxy = *reinterpret_cast<const double2 *>(pxyb + o);
+  const double jz = *reinterpret_cast<const double *>(pzwb + o);
+  dx = xi - jxy.x;
+  dy = yi - jxy.y;
+  dz = zi - jz;
+  if (c & kN3FoldX) dx += L.sLx;
+  if (c & kN3FoldY) dy += L.sLy;
+  if (c & kN3FoldZ) dz += L.sLz;
 }
 
-// Owner density pass of lane position t: one pair per iteration, the next list word one iteration ahead (the loops
-// are kept lean on purpose: two CTAs of ~416 threads share an SM under a 72-register budget, and thread-level
-// parallelism -- 26 warps -- hides the latencies).
-__device__ __forceinline__ void n3_density(const PotParams &P, const EamRowDev *row, const SysView &sys, const Smem &sm,
-                                           const N3Box &bx, int t, N3Lane &L, int2 cs0, double (&acc)[2]) {
+struct N3K {  // pair constants of the walker's element row
+  double rc2, nb1, nb2x2, nb2x1024, naM, aMRm, Dm, nK2;
+};
+
+// Owner density pass of lane position t.
+__device__ __forceinline__ void n3_density(const N3K &K, const SysView &sys, const Smem &sm, int t, N3Lane &L,
+                                           int2 (&cur)[kN3UD], double (&acc)[2]) {
   const double *T = sm.t16;
-  const size_t step = static_cast<size_t>(sys.Np);
-  const int2 *oc = sys.own_cs + t;
+  const unsigned char *pxyb = reinterpret_cast<const unsigned char *>(sm.pxy);
+  const unsigned char *pzwb = reinterpret_cast<const unsigned char *>(sm.pzw);
+  unsigned char *slotb = reinterpret_cast<unsigned char *>(sm.slots);
+  const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
+  const int2 *oc = sys.own_cs + t + kN3UD * step;
   double2 *oab = sys.own_ab + t;
-  const double rc2 = row->rc2;
-  const double nb1 = -row->beta1, nb2x2 = -2.0 * row->beta2, nb2x1024 = -1024.0 * row->beta2;
-  const double naM = -row->alphaM, aMRm = row->alphaM * row->Rm, Dm = row->Dm;
-  // sign of the reference's own pair force (EAM.cpp:203-215) or of -grad U
-  const double nK2 = -(P.eam_conservative ? 1.0 : -1.0) * 2.0 * row->alphaM * row->Dm;
-  const double2 ixy = sm.pxy[L.atom];
-  const double iz = sm.pzw[L.atom].x;
+  const double2 pixy = sm.pxy[L.atom];
+  const double piz = sm.pzw[L.atom].x;
   double dens = 0.0, e_acc = 0.0;
   int npairs = 0;
   const int nown = L.nown, nso = L.nso;
-  int2 cnext = cs0;
-  for (int k = 0; k < nown; k++) {
-    const int2 cs = cnext;
-    oc += step;
-    cnext = ld_cg(oc);  // (row nown is valid memory: rows are padded)
-    const int c = cs.x;
-    const int j = c & kNbrIndexMask;
-    double dx, dy, dz;
-    n3_vec(bx, c, ixy, iz, sm.pxy[j], sm.pzw[j].x, dx, dy, dz);
-    const double r2 = norm2_rn(dx, dy, dz);
-    double g = 0.0, A = 0.0, nB = 0.0;
-    if (EONB200_LIKELY(k < nso || !(r2 > rc2))) {  // EAM.cpp:172 decides for the uncertain class; sure-in pairs are inside
-      npairs++;
+  for (int k = 0; k < nown; k += kN3UD) {
+    int2 cs[kN3UD];
+#pragma unroll
+    for (int u = 0; u < kN3UD; u++) {
+      cs[u] = cur[u];
+      cur[u] = ld_cg(oc + u * step);  // (rows beyond the end are valid memory: kN3Slack)
+    }
+    oc += kN3UD * step;
+#pragma unroll
+    for (int u = 0; u < kN3UD; u++) {
+      const int c = cs[u].x;
+      double dx, dy, dz;
+      n3_vec3(pxyb, pzwb, c, L, pixy.x, pixy.y, piz, dx, dy, dz);
+      const double r2 = norm2_rn(dx, dy, dz);
+      // EAM.cpp:172 decides for the uncertain class; sure-in pairs are inside; ghost pairs are far outside
+      const bool in = (k + u < nso) || !(r2 > K.rc2);
       const double invr = rsqrt_fast(r2);
       const double r = r2 * invr;
       const double r4 = r2 * r2;
-      const double e1 = exp_t16(nb1 * r, T);
-      const double e2 = exp_t16(nb2x2 * r, T);
-      const double ex = exp_t16(fma(naM, r, aMRm), T);
+      const double e1 = exp_t16(K.nb1 * r, T);
+      const double e2 = exp_t16(K.nb2x2 * r, T);
+      const double ex = exp_t16(fma(K.naM, r, K.aMRm), T);
       const double rho_pair = fma(512.0, e2, e1);
-      g = (r4 * r2) * rho_pair;  // EAM.cpp:178-183
-      const double uu = fma(nb2x1024, e2, nb1 * e1);
+      double g = (r4 * r2) * rho_pair;  // EAM.cpp:178-183
+      const double uu = fma(K.nb2x1024, e2, K.nb1 * e1);
       // g'(r)/r = [6 r^5 rho_pair + r^6 u] / r = r^4 (6 rho_pair + r u)   (EAM.cpp:186-198)
-      A = r4 * fma(r, uu, 6.0 * rho_pair);
+      double A = r4 * fma(r, uu, 6.0 * rho_pair);
       const double dm = 1.0 - ex;
-      nB = (nK2 * dm) * (ex * invr);              // -(+-phi'(r)/r), EAM.cpp:200-217
-      e_acc = fma(Dm, fma(dm, dm, -1.0), e_acc);  // Dm (d^2 - 1): once per unordered pair
+      double nB = (K.nK2 * dm) * (ex * invr);  // -(+-phi'(r)/r), EAM.cpp:200-217
+      double em = K.Dm * fma(dm, dm, -1.0);     // Dm (d^2 - 1): once per unordered pair
+      g = in ? g : 0.0;
+      A = in ? A : 0.0;
+      nB = in ? nB : 0.0;
+      em = in ? em : 0.0;
+      npairs += in ? 1 : 0;
+      dens += g;
+      e_acc += em;
+      *reinterpret_cast<double *>(slotb + cs[u].y) = g;
+      oab[u * step] = make_double2(A, nB);
     }
-    dens += g;
-    sm.slots[cs.y] = g;
-    *oab = make_double2(A, nB);
-    oab += step;
+    oab += kN3UD * step;
   }
   L.rho_own = dens;
   acc[0] += e_acc;
   acc[1] += static_cast<double>(npairs);
 }
 
-// rho_i = own part + received slots (fixed order: four interleaved partial sums); F(rho), F'(rho).  Returns F(rho_i).
-__device__ __forceinline__ double n3_embed(const EamRowDev *row, const Smem &sm, N3Lane &L) {
+// This column's part of rho_i: own part + its received slots (fixed order: four interleaved partial sums).
+__device__ __forceinline__ double n3_rho_part(const Smem &sm, const N3Lane &L) {
   const double *sl = sm.slots + L.rbase;
   const int nr = L.nrecv;
   double s0 = L.rho_own, s1 = 0.0, s2 = 0.0, s3 = 0.0;
@@ -322,150 +386,195 @@ __device__ __forceinline__ double n3_embed(const EamRowDev *row, const Smem &sm,
     s3 += sl[r + 3];
   }
   for (; r < nr; r++) s0 += sl[r];
-  const double dens = (s0 + s1) + (s2 + s3);
-  L.dfd = eam_dembed(row->dc, dens);
-  return eam_embed(row->c, dens);
+  return (s0 + s1) + (s2 + s3);
+}
+// The value a pair of adjacent lanes (the two columns of an atom) add up to; both lanes get it.
+__device__ __forceinline__ double n3_pair_sum(double v) {
+#ifndef EONB200_EMU
+  return v + __shfl_xor_sync(0xffffffffu, v, 1);
+#else
+  return v;
+#endif
 }
 
-// Owner force pass.  Pairs outside the cutoff carry zero weights (written by the density pass).  The body is a dozen
-// instructions, so the list and scratch words run kN3Ring iterations ahead (an L2 round trip is ~1000 cycles).
-constexpr int kN3Ring = 4;
-__device__ __forceinline__ void n3_force_own(const SysView &sys, const Smem &sm, const N3Box &bx, int t, N3Lane &L,
-                                             int2 (&cq)[kN3Ring], double2 (&wq)[kN3Ring]) {
-  const size_t step = static_cast<size_t>(sys.Np);
-  const int2 *oc = sys.own_cs + t + kN3Ring * step;
-  const double2 *oab = sys.own_ab + t + kN3Ring * step;
-  const double2 ixy = sm.pxy[L.atom];
-  const double iz = sm.pzw[L.atom].x;
-  const double dfi = L.dfd;
+// Owner force pass.  Pairs outside the cutoff and ghost pairs carry zero weights (written by the density pass / the
+// list build).
+__device__ __forceinline__ void n3_own_prefetch(const SysView &sys, int t, int2 (&cq)[kN3UF], double2 (&wq)[kN3UF]) {
+  const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
+#pragma unroll
+  for (int u = 0; u < kN3UF; u++) {
+    cq[u] = ld_cg(sys.own_cs + t + u * step);
+    wq[u] = ld_cg(sys.own_ab + t + u * step);
+  }
+}
+__device__ __forceinline__ void n3_force_own(const SysView &sys, const Smem &sm, int t, N3Lane &L, int2 (&cq)[kN3UF],
+                                             double2 (&wq)[kN3UF]) {
+  const unsigned char *pxyb = reinterpret_cast<const unsigned char *>(sm.pxy);
+  const unsigned char *pzwb = reinterpret_cast<const unsigned char *>(sm.pzw);
+  unsigned char *slotb = reinterpret_cast<unsigned char *>(sm.slots);
+  const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
+  const int2 *oc = sys.own_cs + t + kN3UF * step;
+  const double2 *oab = sys.own_ab + t + kN3UF * step;
+  const double2 pixy = sm.pxy[L.atom];
+  const double piz = sm.pzw[L.atom].x;
+  const double ndfi = -L.dfd;
   double fx = 0.0, fy = 0.0, fz = 0.0;
   const int nown = L.nown;
-  for (int k0 = 0; k0 < nown; k0 += kN3Ring) {
+  for (int k0 = 0; k0 < nown; k0 += kN3UF) {
+    int2 cs[kN3UF];
+    double2 w[kN3UF];
 #pragma unroll
-    for (int u = 0; u < kN3Ring; u++) {
-      const int2 cs = cq[u];
-      const double2 w = wq[u];
-      if (k0 + u + kN3Ring < nown) {  // refill this ring position
-        cq[u] = ld_cg(oc + u * step);
-        wq[u] = ld_cg(oab + u * step);
-      }
-      if (k0 + u < nown) {
-        const int c = cs.x;
-        const int j = c & kNbrIndexMask;
-        const double2 jzw = sm.pzw[j];
-        double dx, dy, dz;
-        n3_vec(bx, c, ixy, iz, sm.pxy[j], jzw.x, dx, dy, dz);
-        const double sc = fma(-(dfi + jzw.y), w.x, w.y);
-        fx = fma(sc, dx, fx);
-        fy = fma(sc, dy, fy);
-        fz = fma(sc, dz, fz);
-        sm.slots[cs.y] = sc;
-      }
+    for (int u = 0; u < kN3UF; u++) {
+      cs[u] = cq[u];
+      w[u] = wq[u];
+      cq[u] = ld_cg(oc + u * step);
+      wq[u] = ld_cg(oab + u * step);
     }
-    oc += kN3Ring * step;
-    oab += kN3Ring * step;
+    oc += kN3UF * step;
+    oab += kN3UF * step;
+#pragma unroll
+    for (int u = 0; u < kN3UF; u++) {
+      double dx, dy, dz, dfj;
+      n3_vec(pxyb, pzwb, cs[u].x, L, pixy.x, pixy.y, piz, dx, dy, dz, dfj);
+      const double sc = fma(ndfi - dfj, w[u].x, w[u].y);
+      fx = fma(sc, dx, fx);
+      fy = fma(sc, dy, fy);
+      fz = fma(sc, dz, fz);
+      *reinterpret_cast<double *>(slotb + cs[u].y) = sc;
+    }
   }
   L.fx = fx;
   L.fy = fy;
   L.fz = fz;
 }
-__device__ __forceinline__ void n3_own_prefetch(const SysView &sys, int t, int2 (&cq)[kN3Ring], double2 (&wq)[kN3Ring]) {
-  const size_t step = static_cast<size_t>(sys.Np);
-#pragma unroll
-  for (int u = 0; u < kN3Ring; u++) {  // (rows beyond the count are valid memory: rows are padded to a multiple of 4)
-    cq[u] = ld_cg(sys.own_cs + t + u * step);
-    wq[u] = ld_cg(sys.own_ab + t + u * step);
-  }
-}
 
-// Receiver force pass: F_i += s d' over the atom's slots in slot order, kN3RecvRing list words ahead.
-constexpr int kN3RecvRing = 8;
-__device__ __forceinline__ void n3_recv_prefetch(const SysView &sys, int t, int (&rq)[kN3RecvRing]) {
-  const size_t step = static_cast<size_t>(sys.Np);
+// Receiver force pass: F_i += s d' over the atom's slots in slot order.  Padded entries have d' = 0.
+__device__ __forceinline__ void n3_recv_prefetch(const SysView &sys, int t, int (&rq)[kN3UF]) {
+  const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
 #pragma unroll
-  for (int u = 0; u < kN3RecvRing; u++) rq[u] = ld_cg(sys.recv_code + t + u * step);  // (padded to >= kN3Pre rows)
+  for (int u = 0; u < kN3UF; u++) rq[u] = ld_cg(sys.recv_code + t + u * step);
 }
-__device__ __forceinline__ void n3_force_recv(const SysView &sys, const Smem &sm, const N3Box &bx, int t, const N3Lane &L,
-                                              double *F, int (&rq)[kN3RecvRing]) {
-  const size_t step = static_cast<size_t>(sys.Np);
-  const int *rc = sys.recv_code + t + kN3RecvRing * step;
+__device__ __forceinline__ void n3_force_recv(const SysView &sys, const Smem &sm, int t, N3Lane &L, int (&rq)[kN3UF]) {
+  const unsigned char *pxyb = reinterpret_cast<const unsigned char *>(sm.pxy);
+  const unsigned char *pzwb = reinterpret_cast<const unsigned char *>(sm.pzw);
+  const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
+  const int *rc = sys.recv_code + t + kN3UF * step;
   const double *sl = sm.slots + L.rbase;
-  const double2 ixy = sm.pxy[L.atom];
-  const double iz = sm.pzw[L.atom].x;
+  const double2 pixy = sm.pxy[L.atom];
+  const double piz = sm.pzw[L.atom].x;
   double fx = L.fx, fy = L.fy, fz = L.fz;
   const int nr = L.nrecv;
-  for (int k0 = 0; k0 < nr; k0 += kN3RecvRing) {
+  for (int k0 = 0; k0 < nr; k0 += kN3UF) {
+    int c[kN3UF];
 #pragma unroll
-    for (int u = 0; u < kN3RecvRing; u++) {
-      const int c = rq[u];
-      if (k0 + u + kN3RecvRing < nr) rq[u] = ld_cg(rc + u * step);
-      if (k0 + u < nr) {
-        const int j = c & kNbrIndexMask;
-        double dx, dy, dz;
-        n3_vec(bx, c, ixy, iz, sm.pxy[j], sm.pzw[j].x, dx, dy, dz);
-        const double sc = sl[k0 + u];
-        fx = fma(sc, dx, fx);
-        fy = fma(sc, dy, fy);
-        fz = fma(sc, dz, fz);
-      }
+    for (int u = 0; u < kN3UF; u++) {
+      c[u] = rq[u];
+      rq[u] = ld_cg(rc + u * step);
     }
-    rc += kN3RecvRing * step;
+    rc += kN3UF * step;
+#pragma unroll
+    for (int u = 0; u < kN3UF; u++) {
+      double dx, dy, dz;
+      n3_vec3(pxyb, pzwb, c[u], L, pixy.x, pixy.y, piz, dx, dy, dz);
+      const double sc = sl[k0 + u];
+      fx = fma(sc, dx, fx);
+      fy = fma(sc, dy, fy);
+      fz = fma(sc, dz, fz);
+    }
   }
-  const int i = L.atom;
-  F[3 * i] = fx;
-  F[3 * i + 1] = fy;
-  F[3 * i + 2] = fz;
+  L.fx = fx;
+  L.fy = fy;
+  L.fz = fz;
 }
 
-// One lane position per thread (SINGLE: the lane state stays in registers between the passes, the first words of the
-// force passes are requested while the CTA meets at the barriers) or several (state through HBM scratch: sys.dfd holds
-// the own density part, the output rows the own force part).
+// Sum of two per-thread values over the CTA; thread 0 gets the result.  One barrier.
+__device__ __forceinline__ void cta_sum2_to0(double (&v)[2], double *scratch) {
+#ifndef EONB200_EMU
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  v[0] = warp_sum(v[0]);
+  v[1] = warp_sum(v[1]);
+  if (lane == 0) {
+    scratch[warp] = v[0];
+    scratch[kMaxWarps + warp] = v[1];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    v[0] = warp_sum(lane < nwarps ? scratch[lane] : 0.0);
+    v[1] = warp_sum(lane < nwarps ? scratch[kMaxWarps + lane] : 0.0);
+  }
+#else
+  (void)scratch;
+#endif
+}
+
+// One list column per thread (SINGLE: the lane state stays in registers between the passes, the first words of the
+// force passes are requested while the CTA meets at the barriers; one or two columns per atom) or several (one column
+// per atom; state through HBM scratch: sys.dfd holds the own density part, the output rows the own force part).
 template <bool SINGLE>
-__device__ __forceinline__ void eam_n3_fast(const PotParams &P, const EamRowDev *row, const SysView &sys, const Smem &sm,
-                                            const N3Box &bx, double *F, double *U, const N3Raw &raw0, int2 cs0, long long *clk) {
-  const int N = sys.N;
+__device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const double *dc, const SysView &sys,
+                                            const Smem &sm, const N3Box &bx, double *F, double *U, const int4 &h0,
+                                            int2 (&cd)[kN3UD], long long *clk) {
+  const int lpa = SINGLE ? sys.n3_lpa : 1;
+  const int C = sys.N * lpa;  // list columns
   const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
+  const bool first = lpa == 1 || (tid & 1) == 0;  // the column that speaks for the atom
   double acc[2] = {0.0, 0.0};
   N3Lane L;
-  N3Raw rw = raw0;
-  int2 cq[kN3Ring];
-  double2 wq[kN3Ring];
-  int rq[kN3RecvRing];
-  for (int t = tid; t < N; t += nt) {
-    if (!SINGLE && t != tid) {
-      n3_raw_load(sys, t, rw);
-      cs0 = ld_cg(sys.own_cs + t);
+  int2 cq[kN3UF];
+  double2 wq[kN3UF];
+  int rq[kN3UF];
+  n3_unpack(h0, bx, L);
+  L.rho_own = 0.0;
+  if (SINGLE) {
+    if (tid < C) n3_density(K, sys, sm, tid, L, cd, acc);
+  } else {
+    for (int t = tid; t < C; t += nt) {
+      if (t != tid) {
+        n3_unpack(ld_cg(sys.lhdr + t), bx, L);
+#pragma unroll
+        for (int u = 0; u < kN3UD; u++) cd[u] = ld_cg(sys.own_cs + t + u * step);
+      }
+      n3_density(K, sys, sm, t, L, cd, acc);
+      sys.dfd[t] = L.rho_own;
     }
-    n3_unpack(rw, L);
-    n3_density(P, row, sys, sm, bx, t, L, cs0, acc);
-    if (!SINGLE) sys.dfd[t] = L.rho_own;
   }
-  if (SINGLE && tid < N) {  // first words of the two force passes
+  if (SINGLE && tid < C) {  // first words of the two force passes
     n3_own_prefetch(sys, tid, cq, wq);
     n3_recv_prefetch(sys, tid, rq);
   }
   phase_clock(clk, 6);
   __syncthreads();
   phase_clock(clk, 7);
-  for (int t = tid; t < N; t += nt) {
-    if (!SINGLE) {
-      n3_raw_load(sys, t, rw);
-      n3_unpack(rw, L);
-      L.rho_own = sys.dfd[t];
+  if (SINGLE) {
+    double part = tid < C ? n3_rho_part(sm, L) : 0.0;
+    if (lpa == 2) part = n3_pair_sum(part);
+    if (tid < C) {
+      L.dfd = eam_dembed(dc, part);
+      if (first) {
+        acc[0] += eam_embed(c, part);
+        sm.pzw[L.atom].y = L.dfd;
+      }
     }
-    acc[0] += n3_embed(row, sm, L);
-    sm.pzw[L.atom].y = L.dfd;
+  } else {
+    for (int t = tid; t < C; t += nt) {
+      n3_unpack(ld_cg(sys.lhdr + t), bx, L);
+      L.rho_own = sys.dfd[t];
+      const double dens = n3_rho_part(sm, L);
+      acc[0] += eam_embed(c, dens);
+      sm.pzw[L.atom].y = eam_dembed(dc, dens);
+    }
   }
   __syncthreads();
   phase_clock(clk, 8);
-  for (int t = tid; t < N; t += nt) {
+  for (int t = tid; t < C; t += nt) {
     if (!SINGLE) {
-      n3_raw_load(sys, t, rw);
-      n3_unpack(rw, L);
+      n3_unpack(ld_cg(sys.lhdr + t), bx, L);
       L.dfd = sm.pzw[L.atom].y;
       n3_own_prefetch(sys, t, cq, wq);
     }
-    n3_force_own(sys, sm, bx, t, L, cq, wq);
+    n3_force_own(sys, sm, t, L, cq, wq);
     if (!SINGLE) {
       F[3 * L.atom] = L.fx;
       F[3 * L.atom + 1] = L.fy;
@@ -474,34 +583,58 @@ __device__ __forceinline__ void eam_n3_fast(const PotParams &P, const EamRowDev 
   }
   __syncthreads();
   phase_clock(clk, 9);
-  for (int t = tid; t < N; t += nt) {
-    if (!SINGLE) {
-      n3_raw_load(sys, t, rw);
-      n3_unpack(rw, L);
+  if (SINGLE) {
+    if (tid < C)
+      n3_force_recv(sys, sm, tid, L, rq);
+    else
+      L.fx = L.fy = L.fz = 0.0;
+    if (lpa == 2) {
+      L.fx = n3_pair_sum(L.fx);
+      L.fy = n3_pair_sum(L.fy);
+      L.fz = n3_pair_sum(L.fz);
+    }
+    if (tid < C && first) {
+      F[3 * L.atom] = L.fx;
+      F[3 * L.atom + 1] = L.fy;
+      F[3 * L.atom + 2] = L.fz;
+    }
+  } else {
+    for (int t = tid; t < C; t += nt) {
+      n3_unpack(ld_cg(sys.lhdr + t), bx, L);
       L.fx = F[3 * L.atom];
       L.fy = F[3 * L.atom + 1];
       L.fz = F[3 * L.atom + 2];
       n3_recv_prefetch(sys, t, rq);
+      n3_force_recv(sys, sm, t, L, rq);
+      F[3 * L.atom] = L.fx;
+      F[3 * L.atom + 1] = L.fy;
+      F[3 * L.atom + 2] = L.fz;
     }
-    n3_force_recv(sys, sm, bx, t, L, F, rq);
   }
-  block_sum<2>(acc, sm.red);
+  cta_sum2_to0(acc, sm.red);
   if (tid == 0) {
     *U = acc[0];
     atomicAdd(&sys.stats[2], 2ULL * static_cast<unsigned long long>(acc[1]));  // ordered in-cutoff pairs
   }
 }
 
+__device__ __forceinline__ void n3_cold_views(const FusedCold &fc, SysView &sys, Smem &sm) {
+  EONB200_DYN_SMEM(smem_raw);
+  sys = batch_sys(fc.nl, fc.a, blockIdx.y);
+  sm = carve_smem_n3(smem_raw, fc.a.N, fc.a.maxCells, sys.cellscratch);
+}
+
 // The ordered-pair lane functions (filter -> density -> force over the walker's full rows, potentials.cuh) inside this
 // kernel: walkers beyond skin/4 of their build positions, or whose slots do not fit.
-__device__ EONB200_NOINLINE void eam_n3_ordered(const FusedCold *fc, const PotParams *P_sh, int r0, bool near_build) {
+__device__ EONB200_NOINLINE void eam_n3_ordered(const FusedCold *fc, int r0, bool near_build) {
   SysView sys;
   Smem sm;
   fused_cold_views(*fc, sys, sm);
-  const PotParams &P = *P_sh;
+  const PotParams &P = *fc->Pp;
   const int N = sys.N, tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < N; i += nt) {
     const double4 p = sm.pos[i];
+    sm.pos[i].w = 0.0;
     sm.posf[i] = make_float4(static_cast<float>(p.x), static_cast<float>(p.y), static_cast<float>(p.z), 0.0f);
   }
   if (tid == 0) {  // the ghost atom the row padding points at: far outside every cutoff
@@ -532,25 +665,77 @@ __device__ EONB200_NOINLINE void eam_n3_ordered(const FusedCold *fc, const PotPa
     eam_fused_fast<false>(P, ff, sys, sm, 0, N, 1u, 0u, F, U, n0_first, kend_first, cur, nullptr);
 }
 
-// Smallest value over the CTA of three per-thread values (all threads get the result).  One barrier; the caller's
-// next barrier protects the scratch.
-__device__ __forceinline__ void cta_min3(double (&v)[3], double *scratch) {
-#ifndef EONB200_EMU
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nwarps = (blockDim.x + 31) >> 5;
-#pragma unroll
-  for (int k = 0; k < 3; k++) v[k] = warp_min(v[k]);
-  if (lane == 0) {
-    scratch[warp] = v[0];
-    scratch[kMaxWarps + warp] = v[1];
-    scratch[2 * kMaxWarps + warp] = v[2];
+// Everything but the common case.  disp2_thread: this thread's largest squared displacement from the build positions
+// (meaningless without a list).  Returns 1 when the walker is (now) fit for the fast path -- lists valid for the
+// positions in sm.pos -- and 0 when the walker has been finished here.
+__device__ EONB200_NOINLINE int eam_n3_cold(FusedCold *fc, const NlBatch *nl, const ForceBatchArgs *a, const PotParams *Pp,
+                                            double disp2_thread) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) {
+    fc->nl = *nl;
+    fc->a = *a;
+    fc->Pp = Pp;
   }
   __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 3; k++) v[k] = warp_min(lane < nwarps ? scratch[k * kMaxWarps + lane] : 1e300);
-#else
-  (void)scratch;
-#endif
+  SysView sys;
+  Smem sm;
+  n3_cold_views(*fc, sys, sm);
+  const PotParams &P = *Pp;
+  const int N = sys.N;
+  for (int i = tid; i < N; i += nt) sm.pos[i] = make_double4(sm.pxy[i].x, sm.pxy[i].y, sm.pzw[i].x, 0.0);
+  for (int k = tid; k < 128; k += nt) sm.exp_tab[k] = P.exp_tab[k];
+  const double Lbox[3] = {sys.box[0], sys.box[4], sys.box[8]};
+  fill_sh27(sm, Lbox[0], Lbox[1], Lbox[2]);
+  const bool have = *sys.state != 0;
+  const int z0 = sys.Z[0];
+  double mixed_t = 0.0;
+  for (int i = tid; i < N; i += nt)
+    if (sys.Z[i] != z0) mixed_t = 1.0;
+  double red[2] = {disp2_thread, mixed_t};
+  {
+    const int op[2] = {RED_MAX, RED_MAX};
+    block_reduce<2>(red, op, sm.red);
+  }
+  const bool mixed = red[1] != 0.0;
+  double disp2 = red[0];
+  const double need = 2.0 * P.rc_list + P.skin;  // stored folds stay the reference's minimum image
+  const bool tab_ok = Lbox[0] >= need && Lbox[1] >= need && Lbox[2] >= need;
+  // small (or open) boxes: the hot path's nearest-image positions mean nothing there; EAM.cpp:56-90 as written
+  if (!tab_ok) disp2 = eam_fused_reconvert(fc, have);
+  const double lim = 0.5 * P.skin, dstar = 0.25 * P.skin;
+  const int h_valid = ld_cg(sys.hl_hdr + N3H_VALID);
+  const int h_rowz = ld_cg(sys.hl_hdr + N3H_ROWZ);
+  const bool rebuild = fc->a.force_rebuild != 0 || !have || P.skin <= 0.0 || !(disp2 <= lim * lim) ||
+                       h_valid != sys.n3_lpa || (h_rowz >> 8) != z0;
+  const bool near_build = rebuild || disp2 <= dstar * dstar;  // a fresh list is built from these very positions
+  if (rebuild) {
+    __syncthreads();
+    if (tid == 0) sys.hl_hdr[N3H_VALID] = 0;
+    eam_fused_rebuild(fc, Pp);
+    n3_build(sys, sm, P, sys.n3_lpa);
+  }
+  if (mixed || !tab_ok || !P.eam_fast_ok) {  // general rows: full element table, geometry for mic_vec
+    if (tid == 0) sm.pos[N] = make_double4(1e150, 1e150, 1e150, 0.0);
+    __syncthreads();
+    eam_fused_general(fc, tab_ok, 0, N);
+    return 0;
+  }
+  int r0 = -1;
+  for (int q = P.n_rows - 1; q >= 0; q--)
+    if (P.rows[q].Z == z0) r0 = q;
+  double *F = fc->a.F + static_cast<size_t>(blockIdx.y) * fc->a.strideR;
+  if (r0 < 0) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
+    for (int k = tid; k < 3 * N; k += nt) F[k] = 0.0;
+    if (tid == 0) fc->a.U[blockIdx.y] = nan("");
+    return 0;
+  }
+  const bool fits = ld_cg(sys.hl_hdr + N3H_VALID) == sys.n3_lpa && ld_cg(sys.hl_hdr + N3H_SLOTS) <= sys.slot_cap &&
+                    ld_cg(sys.hl_hdr + N3H_CONFLICT) == 0 && N <= kN3MaxAtoms;
+  if (!near_build || !fits) {
+    eam_n3_ordered(fc, r0, near_build);
+    return 0;
+  }
+  return 1;
 }
 
 // grid (1, S): one CTA per walker.  Pg: the parameter block as a kernel argument (constant bank: no load latency on
@@ -559,19 +744,12 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
                                             const ForceBatchArgs &a) {
   EONB200_DYN_SMEM(smem_raw);
   const int s = blockIdx.y;
-  __shared__ FusedCold cold;  // filled only when a cold path is about to run
-  // the element rows come out of the constant bank (cold at every launch) while the positions are staged
-  __shared__ __align__(16) unsigned long long rows_sh[(sizeof(EamRowDev) * kMaxEamRows + 7) / 8];
-  {
-    const int nw = static_cast<int>((sizeof(EamRowDev) * P.n_rows + 7) / 8);
-    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(P.rows);
-    for (int k = threadIdx.x; k < nw; k += blockDim.x) rows_sh[k] = src[k];
-  }
-  const EamRowDev *rows = reinterpret_cast<const EamRowDev *>(rows_sh);
+  __shared__ FusedCold cold;  // filled only when the cold path is about to run
+  __shared__ double coef[18];  // embedding polynomial and its derivative (EamRowDev::c, dc) of the walker's element
   const SysView sys = batch_sys(nl, a, s);
-  Smem sm = carve_smem_n3(smem_raw, a.N, a.maxCells, sys.cellscratch);
-  for (int k = threadIdx.x; k < 16; k += blockDim.x) sm.t16[k] = P.exp_t16[k];
+  const Smem sm = carve_smem_n3(smem_raw, a.N, a.maxCells, sys.cellscratch);
   const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
+  const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
   long long *clk = a.clocks ? a.clocks + static_cast<size_t>(s) * 16 : nullptr;
 #ifndef EONB200_EMU
   if (clk && tid == 0) {
@@ -585,213 +763,149 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   }
 #endif
   // ---- every HBM access of the prologue in flight at once ------------------------------------------------------------
-  // The walker's coordinates land in the tail of the position block.  A bulk copy needs 16-byte aligned ends on both
-  // sides: rows of an odd 3N start on odd multiples of 8 bytes for every second walker, so the copy moves the aligned
-  // interior and up to one leading and one trailing coordinate are fetched by plain loads.
+  // The walker's raw coordinates land in the slot buffer (free until the density pass).  A bulk copy needs 16-byte
+  // aligned ends on both sides: rows of an odd 3N start on odd multiples of 8 bytes for every second walker, so the copy
+  // moves the aligned interior and up to one leading and one trailing coordinate are fetched by plain loads.
   const int D = 3 * N;
   const uintptr_t addr = reinterpret_cast<uintptr_t>(sys.R);
   const bool aligned = (addr & 7u) == 0;
   const int head = (addr & 15u) ? 1 : 0;
   const int body = (D - head) & ~1;
-  double *raw = reinterpret_cast<double *>(sm.pos) + (N + (N & 1)) + head;  // &raw[head] is 16-byte aligned
-  const int h_rows = ld_cg(sys.hl_hdr + 2);  // rows of the owner / receiver lists in use (largest count over the atoms)
+  double *raw = sm.slots + head;  // &raw[head] is 16-byte aligned
   if (tid == 0) {
     mbar_init(sm.mbar, 1);
     if (aligned) {
-      mbar_expect(sm.mbar, static_cast<uint32_t>(body) * 8u + 1024u);
+      mbar_expect(sm.mbar, static_cast<uint32_t>(body) * 8u);
       bulk_g2s_issue(raw + head, sys.R + head, static_cast<uint32_t>(body) * 8u, sm.mbar);
-      bulk_g2s_issue(sm.exp_tab, P.exp_tab, 1024u, sm.mbar);
     }
-  }
-  if (tid == 64 % nt && h_rows > 0 && h_rows <= sys.K) {
-    // the list rows this walker is about to read are contiguous (slot-major): bring them into L2 with three
-    // instructions while the positions are staged
-    const uint32_t rows = static_cast<uint32_t>(h_rows) * static_cast<uint32_t>(sys.Np);
-    l2_prefetch_bulk(sys.own_cs, rows * 8u);
-    l2_prefetch_bulk(sys.recv_code, rows * 4u);
   }
   if (aligned && tid == 32 % nt && head) raw[0] = sys.R[0];
   if (aligned && tid == 33 % nt && head + body < D) raw[D - 1] = sys.R[D - 1];
-  const double Lbox[3] = {sys.box[0], sys.box[4], sys.box[8]};  // EAM.cpp:31 reads the diagonal only
-  const bool have = ld_cg(sys.state) != 0;
-  const int z0 = sys.Z[0];
-  int h_slots = ld_cg(sys.hl_hdr);
-  const int h_valid = ld_cg(sys.hl_hdr + 1);
-  // this lane's atoms: list words and the first batch of its owned pairs (speculative: lists that turn out stale are
+  // list header, this lane's header and the first batch of its owned pairs (speculative: lists that turn out stale are
   // read again after the rebuild).  Nothing is USED before the positions have landed.
-  N3Raw lraw;
-  int2 cs0 = make_int2(0, 0);
-  lraw.c2 = make_int2(0, 0);
-  lraw.rbase = lraw.atom = 0;
-  if (tid < N) {
-    n3_raw_load(sys, tid, lraw);
-    cs0 = ld_cg(sys.own_cs + tid);
-  }
-  // build positions and atomic numbers of the atoms this thread converts in the first round
-  double rb[kConvAtoms][3];
-  int zz[kConvAtoms];
-  int odd = 0;
+  const int4 hdr = ld_cg(reinterpret_cast<const int4 *>(sys.hl_hdr));
+  int4 lh = make_int4(0, 0, 0, 0);
+  int2 cd[kN3UD];
 #pragma unroll
-  for (int u = 0; u < kConvAtoms; u++) {
-    const int i = u * nt + tid;
-    zz[u] = z0;
-    if (i < N) {
-      zz[u] = sys.Z[i];
-      rb[u][0] = ld_cg(sys.rbuild + 3 * i);
-      rb[u][1] = ld_cg(sys.rbuild + 3 * i + 1);
-      rb[u][2] = ld_cg(sys.rbuild + 3 * i + 2);
-    }
+  for (int u = 0; u < kN3UD; u++) cd[u] = make_int2(0, 0);
+  const int C = N * sys.n3_lpa;  // list columns
+  if (tid < C) {
+    lh = ld_cg(sys.lhdr + tid);
+#pragma unroll
+    for (int u = 0; u < kN3UD; u++) cd[u] = ld_cg(sys.own_cs + tid + u * step);
   }
-  fill_sh27(sm, Lbox[0], Lbox[1], Lbox[2]);
+  N3Box bx;
+  bx.Lx = sys.box[0];  // EAM.cpp:31 reads the diagonal only
+  bx.Ly = sys.box[4];
+  bx.Lz = sys.box[8];
+  for (int k = tid; k < 16; k += nt) sm.t16[k] = P.exp_t16[k];
+  const double lo[3] = {ld_cg(sys.lo_build), ld_cg(sys.lo_build + 1), ld_cg(sys.lo_build + 2)};
+  // build positions and atomic numbers of the atoms this thread converts in the first round
+  double rb[3] = {0.0, 0.0, 0.0};
+  int zz = 0;
+  if (tid < N) {
+    zz = sys.Z[tid];
+    rb[0] = ld_cg(sys.rbuild + 3 * tid);
+    rb[1] = ld_cg(sys.rbuild + 3 * tid + 1);
+    rb[2] = ld_cg(sys.rbuild + 3 * tid + 2);
+  }
   __syncthreads();  // mbarrier initialised
   if (EONB200_LIKELY(aligned)) {
     mbar_wait(sm.mbar, 0);
   } else {
     for (int k = tid; k < D; k += nt) raw[k] = sys.R[k];
-    for (int k = tid; k < 128; k += nt) sm.exp_tab[k] = P.exp_tab[k];
     __syncthreads();
   }
   phase_clock(clk, 3);
-  // ---- EAM.cpp:56-83: where a coordinate is negative the whole walker moves up by the lowest one.  The first
-  // round's atoms are read into registers here; they are converted in place after the reduction's barrier (pos[i]
-  // overlaps only raw[i'] with i' <= i, and every later round meets at a barrier between its reads and its writes).
-  double lo[3] = {0.0, 0.0, 0.0};
-  double q[kConvAtoms][3];
-#pragma unroll
-  for (int u = 0; u < kConvAtoms; u++) {
-    const int i = u * nt + tid;
-    if (i < N) {
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        q[u][k] = raw[3 * i + k];
-        lo[k] = fmin(lo[k], q[u][k]);
-      }
-    }
-  }
-  for (int i = kConvAtoms * nt + tid; i < N; i += nt) {
-    lo[0] = fmin(lo[0], raw[3 * i]);
-    lo[1] = fmin(lo[1], raw[3 * i + 1]);
-    lo[2] = fmin(lo[2], raw[3 * i + 2]);
-  }
-  cta_min3(lo, sm.red);
-  // ---- raw coordinates -> shifted, wrapped positions; Verlet displacement; element check ----
-  double disp2_max = 0.0;
+  // ---- raw coordinates -> positions continuous with the list's build positions; Verlet displacement; element check ----
+  // EAM.cpp:56-90 moves the walker up by its lowest negative coordinate and wraps it into the box.  Any rigid shift
+  // and any choice of periodic images gives the same pair vectors as long as it is the one the stored folds were
+  // recorded under, so the fast path applies the BUILD's shift and takes the image of every atom nearest to its build
+  // position: no reduction over the walker, no re-wrap jumps while the list is valid.
+  const int z0 = hdr.w >> 8;
   const double dstar = 0.25 * P.skin;
-  for (int base = 0; base < N; base += kConvAtoms * nt) {
-    if (base > 0) {
-#pragma unroll
-      for (int u = 0; u < kConvAtoms; u++) {
-        const int i = base + u * nt + tid;
-        if (i < N) {
-          zz[u] = sys.Z[i];
-          rb[u][0] = ld_cg(sys.rbuild + 3 * i);
-          rb[u][1] = ld_cg(sys.rbuild + 3 * i + 1);
-          rb[u][2] = ld_cg(sys.rbuild + 3 * i + 2);
-          q[u][0] = raw[3 * i];
-          q[u][1] = raw[3 * i + 1];
-          q[u][2] = raw[3 * i + 2];
-        }
-      }
-      __syncthreads();
+  const double Lk[3] = {bx.Lx, bx.Ly, bx.Lz};
+  const double iL[3] = {1.0 / bx.Lx, 1.0 / bx.Ly, 1.0 / bx.Lz};
+  double disp2_max = 0.0;
+  int odd = 0;
+  for (int i = tid; i < N; i += nt) {
+    if (i != tid) {
+      zz = sys.Z[i];
+      rb[0] = ld_cg(sys.rbuild + 3 * i);
+      rb[1] = ld_cg(sys.rbuild + 3 * i + 1);
+      rb[2] = ld_cg(sys.rbuild + 3 * i + 2);
     }
+    double q[3], d2 = 0.0;
 #pragma unroll
-    for (int u = 0; u < kConvAtoms; u++) {
-      const int i = base + u * nt + tid;
-      if (i < N) {
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          if (lo[k] < 0.0) q[u][k] += -lo[k];  // EAM.cpp:78-83 (the shift is |lowest coordinate|)
-          if (Lbox[k] > 0.0) {
-            int guard = 0;
-            while (q[u][k] > Lbox[k] && guard++ < 1000000) q[u][k] -= Lbox[k];  // EAM.cpp:86-90
-          }
-        }
-        sm.pos[i] = make_double4(q[u][0], q[u][1], q[u][2], 0.0);  // (the cold paths' layout)
-        sm.pxy[i] = make_double2(q[u][0], q[u][1]);
-        sm.pzw[i] = make_double2(q[u][2], 0.0);
-        const double dx = q[u][0] - rb[u][0], dy = q[u][1] - rb[u][1], dz = q[u][2] - rb[u][2];
-        disp2_max = fmax(disp2_max, dx * dx + dy * dy + dz * dz);
-        if (zz[u] != z0) odd |= 2;
-      }
+    for (int k = 0; k < 3; k++) {
+      q[k] = raw[3 * i + k] + lo[k];
+      const double n = rint((q[k] - rb[k]) * iL[k]);
+      q[k] = fma(-n, Lk[k], q[k]);
+      const double d = q[k] - rb[k];
+      d2 = fma(d, d, d2);
     }
+    sm.pxy[i] = make_double2(q[0], q[1]);
+    sm.pzw[i] = make_double2(q[2], 0.0);
+    disp2_max = fmax(disp2_max, d2);
+    if (zz != z0) odd |= 1;
+  }
+  if (tid == 0) {  // the ghost atom of the row padding
+    sm.pxy[N] = make_double2(1e150, 1e150);
+    sm.pzw[N] = make_double2(1e150, 0.0);
   }
   if (!(disp2_max <= dstar * dstar)) odd |= 1;
   const double need = 2.0 * P.rc_list + P.skin;  // stored folds stay the reference's minimum image
-  const bool tab_ok = Lbox[0] >= need && Lbox[1] >= need && Lbox[2] >= need;
-  // The common case -- lists present, every atom within skin/4 of its build position, one element -- is decided by ONE
-  // barrier; anything else takes the full decision below.
-  const bool uniform_ok = have && a.force_rebuild == 0 && P.skin > 0.0 && tab_ok && P.eam_fast_ok != 0 && h_valid == 1;
-  bool near_build = true;
+  const bool tab_ok = bx.Lx >= need && bx.Ly >= need && bx.Lz >= need;
+  const int r0h = hdr.w & 0xff;
+  // The common case is decided by ONE barrier; anything else takes the out-of-line path.
+  const bool uniform_ok = a.force_rebuild == 0 && P.skin > 0.0 && tab_ok && P.eam_fast_ok != 0 &&
+                          hdr.y == sys.n3_lpa && hdr.x <= sys.slot_cap && r0h < P.n_rows && N <= kN3MaxAtoms;
+  {
+    const int rq = min(r0h, P.n_rows - 1);
+    for (int k = tid; k < 18; k += nt) coef[k] = k < 9 ? P.rows[rq].c[k] : P.rows[rq].dc[k - 9];
+  }
   phase_clock(clk, 4);
+  int r0 = r0h, nslots = hdr.x;
   if (EONB200_UNLIKELY(cta_any(odd) != 0 || !uniform_ok)) {
-    double red2[2] = {disp2_max, (odd & 2) ? 1.0 : 0.0};
-    {
-      const int op[2] = {RED_MAX, RED_MAX};
-      block_reduce<2>(red2, op, sm.red);
+#ifdef EONB200_DEBUG_COLD
+    if (tid == 0 && s == 0) printf("cold: odd %d fr %d skin %g tab %d fast %d hdr %d %d %d %d cap %d nrows %d N %d\n", odd, a.force_rebuild, P.skin, (int)tab_ok, P.eam_fast_ok, hdr.x, hdr.y, hdr.z, hdr.w, sys.slot_cap, P.n_rows, N);
+#endif
+    if (eam_n3_cold(&cold, &nl, &a, Pp, disp2_max) == 0) return;
+    __syncthreads();
+    r0 = ld_cg(sys.hl_hdr + N3H_ROWZ) & 0xff;
+    nslots = ld_cg(sys.hl_hdr + N3H_SLOTS);
+    for (int k = tid; k < 18; k += nt) coef[k] = k < 9 ? P.rows[r0].c[k] : P.rows[r0].dc[k - 9];
+    if (tid < C) {
+      lh = ld_cg(sys.lhdr + tid);
+#pragma unroll
+      for (int u = 0; u < kN3UD; u++) cd[u] = ld_cg(sys.own_cs + tid + u * step);
     }
-    if (tid == 0) {
-      cold.nl = nl;
-      cold.a = a;
-      cold.Pp = Pp;
-      sm.pos[N] = make_double4(1e150, 1e150, 1e150, 0.0);  // ghost atom of the full rows' padding (general path)
+    for (int i = tid; i < N; i += nt) {  // (a rebuild prepared the positions anew)
+      const double4 p = sm.pos[i];
+      sm.pxy[i] = make_double2(p.x, p.y);
+      sm.pzw[i] = make_double2(p.z, 0.0);
     }
     __syncthreads();
-    const bool mixed = red2[1] != 0.0;
-    const double disp2 = red2[0];
-    const double lim = 0.5 * P.skin;
-    const bool rebuild = a.force_rebuild != 0 || !have || P.skin <= 0.0 || !(disp2 <= lim * lim) || h_valid != 1;
-    near_build = rebuild || disp2 <= dstar * dstar;  // a fresh list is built from these very positions
-    if (rebuild) {
-      eam_fused_rebuild(&cold, Pp);
-      eam_n3_build(&cold);
-      h_slots = ld_cg(sys.hl_hdr);
-      if (tid < N) {
-        n3_raw_load(sys, tid, lraw);
-        cs0 = ld_cg(sys.own_cs + tid);
-      }
-      for (int i = tid; i < N; i += nt) {  // prepare_positions rewrote sm.pos
-        const double4 p = sm.pos[i];
-        sm.pxy[i] = make_double2(p.x, p.y);
-        sm.pzw[i] = make_double2(p.z, 0.0);
-      }
-      __syncthreads();
-    }
-    if (mixed || !tab_ok || !P.eam_fast_ok) {  // general rows: full element table, geometry for mic_vec
-      eam_fused_general(&cold, tab_ok, 0, N);
-      return;
-    }
   }
   phase_clock(clk, 12);
+  // spare slots behind the last one: written by ghost pairs, read (times a zero vector) by padded receiver rows
+  for (int k = tid; k < kN3UF; k += nt) sm.slots[nslots - kN3UF + k] = 0.0;
   double *F = a.F + static_cast<size_t>(s) * a.strideR;
-  int r0 = -1;
-  for (int q = 0; q < P.n_rows; q++)
-    if (rows[q].Z == z0) {
-      r0 = q;
-      break;
-    }
-  if (EONB200_UNLIKELY(r0 < 0)) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
-    for (int k = tid; k < 3 * N; k += nt) F[k] = 0.0;
-    if (tid == 0) a.U[s] = nan("");
-    return;
-  }
-  if (EONB200_UNLIKELY(!near_build || h_slots > sys.slot_cap)) {  // CTA-uniform
-    if (tid == 0) {
-      cold.nl = nl;
-      cold.a = a;
-      cold.Pp = Pp;
-    }
-    __syncthreads();
-    eam_n3_ordered(&cold, Pp, r0, near_build);
-    return;
-  }
-  N3Box bx;
-  bx.Lx = Lbox[0];
-  bx.Ly = Lbox[1];
-  bx.Lz = Lbox[2];
-  if (EONB200_LIKELY(N <= nt))
-    eam_n3_fast<true>(P, rows + r0, sys, sm, bx, F, a.U + s, lraw, cs0, clk);
+  const EamRowDev &row = P.rows[r0];
+  N3K K;
+  K.rc2 = row.rc2;
+  K.nb1 = -row.beta1;
+  K.nb2x2 = -2.0 * row.beta2;
+  K.nb2x1024 = -1024.0 * row.beta2;
+  K.naM = -row.alphaM;
+  K.aMRm = row.alphaM * row.Rm;
+  K.Dm = row.Dm;
+  // sign of the reference's own pair force (EAM.cpp:203-215) or of -grad U
+  K.nK2 = -(P.eam_conservative ? 1.0 : -1.0) * 2.0 * row.alphaM * row.Dm;
+  if (EONB200_LIKELY(C <= nt))
+    eam_n3_fast<true>(K, coef, coef + 9, sys, sm, bx, F, a.U + s, lh, cd, clk);
   else
-    eam_n3_fast<false>(P, rows + r0, sys, sm, bx, F, a.U + s, lraw, cs0, clk);
+    eam_n3_fast<false>(K, coef, coef + 9, sys, sm, bx, F, a.U + s, lh, cd, clk);
   phase_clock(clk, 10);
 }
 

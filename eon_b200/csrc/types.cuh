@@ -84,16 +84,20 @@ struct NlBatch {
   // owner / receiver lists of the Newton's-third-law EAM kernel (eam_n3.cuh).  Every unordered pair of the sure-in
   // and uncertain classes is OWNED by one of its atoms (parity rule): the owner evaluates it and hands the partner's
   // share over through a slot of shared memory.  Slot-major like nbr (lanes = atoms read consecutive words).
-  int2 *own_cs;     // [S][K][Np] pairs atom i owns, sure-in first, then uncertain: x = code (j | image << 20), y = the
-                    //            partner's receiver slot for this pair (index into the CTA's slot buffer)
+  int2 *own_cs;     // [S][K][Np] pairs atom i owns, sure-in first, then uncertain: x = code (32 j | fold bits << 16,
+                    //            eam_n3.cuh), y = byte offset of the partner's receiver slot in the CTA's slot buffer
   int *recv_code;   // [S][K][Np] codes of the pairs atom i receives, in slot order
-  int2 *cls2;       // [S][Np]    x = owned sure-in | owned uncertain << 16, y = received (sure-in + uncertain)
+  int4 *lhdr;       // [S][2 Np]  list column t (n3_lpa columns per atom): x = owned sure-in | owned << 16, y = received, z = first slot,
+                    //            w = atom | (fold is -L along x, y, z) << 24
   int *lane_atom;   // [S][Np]    atom of lane position t (atoms ranked by owned pairs); the lists above are stored by lane
   int *atom_lane;   // [S][Np]    its inverse
-  int *roff;        // [S][Np + 1] first slot of lane position t (exclusive scan of the received counts); [N] = slots in use
+  int *roff;        // [S][2 Np + 1] list-build scratch: exclusive scan of the received counts
   double2 *own_ab;  // [S][K][Np] (g'(r)/r, -(+-phi'(r)/r)) of the owned pairs, written by the density pass
-  int *hl_hdr;      // [S][8]     [0] slots in use, [1] 1 = lists valid, [2] list rows in use (multiple of 4)
+  int *hl_hdr;      // [S][8]     [0] slots the fast path needs, [1] 1 = lists valid, [2] list rows in use,
+                    //            [3] element row | Z << 8, [4] fold-sign conflict
+  double *lo_build; // [S][4]     coordinate shift (EAM.cpp:56-83) the lists were built under
   int slot_cap;     // receiver slots the launch has shared memory for
+  int n3_lpa;       // lanes (list columns) per atom of this launch, 1 or 2
 };
 
 // One system as seen by its CTA.
@@ -123,12 +127,14 @@ struct SysView {
   int *done;
   int2 *own_cs;
   int *recv_code;
-  int2 *cls2;
+  int4 *lhdr;
   int *lane_atom, *atom_lane;
   int *roff;
   double2 *own_ab;
   int *hl_hdr;
+  double *lo_build;
   int slot_cap;
+  int n3_lpa;
 };
 
 __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, const double *R, const int *Z,
@@ -163,12 +169,14 @@ __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, con
   v.own_cs = nl.own_cs ? nl.own_cs + kn : nullptr;
   v.recv_code = nl.recv_code ? nl.recv_code + kn : nullptr;
   v.own_ab = nl.own_ab ? nl.own_ab + kn : nullptr;
-  v.cls2 = nl.cls2 ? nl.cls2 + static_cast<size_t>(s) * nl.Np : nullptr;
-  v.roff = nl.roff ? nl.roff + static_cast<size_t>(s) * (nl.Np + 1) : nullptr;
+  v.lhdr = nl.lhdr ? nl.lhdr + static_cast<size_t>(s) * nl.Np * 2 : nullptr;
+  v.roff = nl.roff ? nl.roff + static_cast<size_t>(s) * (2 * nl.Np + 1) : nullptr;
   v.lane_atom = nl.lane_atom ? nl.lane_atom + static_cast<size_t>(s) * nl.Np : nullptr;
   v.atom_lane = nl.atom_lane ? nl.atom_lane + static_cast<size_t>(s) * nl.Np : nullptr;
   v.hl_hdr = nl.hl_hdr ? nl.hl_hdr + static_cast<size_t>(s) * 8 : nullptr;
+  v.lo_build = nl.lo_build ? nl.lo_build + static_cast<size_t>(s) * 4 : nullptr;
   v.slot_cap = nl.slot_cap;
+  v.n3_lpa = nl.n3_lpa;
   return v;
 }
 
@@ -214,7 +222,8 @@ struct Smem {
   double2 *pxy;      // [N + 1] (x, y) of the prepared positions: a 16-byte stride spreads a gather over all banks
   double2 *pzw;      // [N + 1] (z, F'(rho))
   double *t16;       // [16] 2^(j/16), one 128-byte line: any lookup of a warp is conflict free
-  double *slots;     // [slot_cap] receiver slots: the partner's share of a pair (g, then the force scalar)
+  double *slots;     // [slot_cap] receiver slots: the partner's share of a pair (g, then the force scalar); landing
+                     //            zone of the raw coordinates before that (slot_cap >= 3N + 4)
   int maxCells;
 };
 

@@ -128,6 +128,15 @@ struct int2 {
   int x, y;
 };
 inline int2 make_int2(int x, int y) { return int2{x, y}; }
+struct alignas(16) int4 {
+  int x, y, z, w;
+};
+inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+inline int atomicOr(int *p, int v) {
+  int o = *p;
+  *p |= v;
+  return o;
+}
 struct double2 {
   double x, y;
 };

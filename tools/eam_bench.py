@@ -71,8 +71,8 @@ if "clocks" in flags:
     start_us = (c[:, 0] - t0) / 1e3
     print("clocked launch ms", ms1, "ctas", len(c), "entry spread us: med %.1f max %.1f" % (np.median(start_us), start_us.max()))
     if mode == 0:
-        seq = [(2, "entry"), (3, "positions landed"), (4, "converted"), (12, "list decision"), (5, "filter done"),
-               (6, "density done (t0)"), (7, "density barrier"), (8, "embedding done"), (9, "force done (t0)"), (10, "exit")]
+        seq = [(2, "entry"), (3, "positions landed"), (4, "converted"), (12, "list decision"),
+               (6, "density done (t0)"), (7, "density barrier"), (8, "embedding done"), (9, "own force + barrier"), (10, "recv force, exit")]
         prev = None
         for slot, nm in seq:
             if prev is not None:
