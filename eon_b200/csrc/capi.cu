@@ -68,7 +68,7 @@ struct NlStore {
   DevBuf<int> nbr, cnt, state, flags, done, nbr2, cnt2, cls, cellscratch;
   int scratch_stride = 0;
   int rowmax_seen = 0;  // largest row fill any build of this store reported (rows worth prefetching)
-  DevBuf<double> rbuild, pairA, pairB, dfd, upart;
+  DevBuf<double> rbuild, pairA, pairB, dfd, upart, box_build;
   DevBuf<double4> pos4;
   DevBuf<unsigned char> rowid;
   // owner / receiver lists of the Newton's-third-law EAM kernel (types.cuh: NlBatch::own_*)
@@ -378,6 +378,20 @@ int pick_slot_cap(const EonB200Pot *pot, const NlStore &nl, long N) {
   return static_cast<int>((std::max<long>(want, 0) + 15) / 16 * 16);
 }
 
+// Argument checks shared by the entry points that take host atomic numbers: the packed neighbour codes hold
+// kNbrIndexMask atoms, and an EAM element without a parameter row is the reference's 14324 (EAM.cpp:116-123).
+int check_system(EonB200Pot *pot, long N, const int *Z, const char *who) {
+  if (N > kNbrIndexMask) return fail(pot, 2, "%s: more than %d atoms per system", who, kNbrIndexMask);
+  if (pot->cfg.kind == EONB200_POT_EAM && Z) {
+    for (long i = 0; i < N; i++) {
+      bool found = false;
+      for (const auto &r : pot->rows) found = found || r.Z == Z[i];
+      if (!found) return fail(pot, 14324, "EAM: no parameter row for atomic number %d", Z[i]);
+    }
+  }
+  return 0;
+}
+
 int pick_max_cells(long N) { return static_cast<int>(std::min<long>(std::max<long>(64, N), 4096)); }
 
 // Row capacity guess from the mean density; truncated builds are detected and regrown.
@@ -438,6 +452,7 @@ int nl_alloc(EonB200Pot *pot, NlStore &nl, long S, long N, int K, bool n3_lists 
       CU_TRY(pot, cudaMemsetAsync(nl.roff.p, 0, sizeof(int) * S * (2 * Np + 1), pot->stream));
     }
   }
+  CU_TRY(pot, nl.box_build.reserve(static_cast<size_t>(S) * 9));
   CU_TRY(pot, cudaMemsetAsync(nl.state.p, 0, sizeof(int) * S, pot->stream));
   CU_TRY(pot, cudaMemsetAsync(nl.done.p, 0, sizeof(int) * S, pot->stream));
   CU_TRY(pot, cudaMemsetAsync(nl.flags.p, 0, sizeof(int) * S, pot->stream));
@@ -472,6 +487,7 @@ NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
   b.flags = nl.flags.p;
   b.upart = nl.upart.p;
   b.done = nl.done.p;
+  b.box_build = nl.box_build.p;
   b.own_cs = nl.n3 ? nl.own_cs.p : nullptr;
   b.recv_code = nl.n3 ? nl.recv_code.p : nullptr;
   b.own_ab = nl.n3 ? nl.own_ab.p : nullptr;
@@ -981,6 +997,10 @@ int eonb200_neb_band_forces(EonB200Pot *pot, long nBands, long nImages, long nAt
   if (!pot) return 1;
   if (nBands <= 0 || nImages <= 0 || nAtoms <= 0) return fail(pot, 2, "neb_band_forces: bands, images and atoms must be positive");
   if (!positions || !atomicNrs || !box || !prm || !projected) return fail(pot, 2, "neb_band_forces: null argument");
+  {
+    const int rc = check_system(pot, nAtoms, atomicNrs, "neb_band_forces");
+    if (rc) return rc;
+  }
   CU_TRY(pot, cudaSetDevice(pot->device));
   const long N = nAtoms, S = nBands * (nImages + 2);
   const size_t D = 3 * static_cast<size_t>(N);
@@ -999,15 +1019,15 @@ int eonb200_neb_band_forces(EonB200Pot *pot, long nBands, long nImages, long nAt
   bool any_fixed = false;
   if (fixed) {
     pot->neb_hmask.resize(D);
-    for (long i = 0; i < N; i++) {
-      bool fx = false;
+    for (long i = 0; i < N; i++) {  // Matter::getFixed(i): all three axes; the mask itself is per axis
+      bool all_fx = true;
       for (int k = 0; k < 3; k++) {
         pot->neb_hmask[3 * i + k] = fixed[3 * i + k] ? 0.0 : 1.0;
-        fx = fx || fixed[3 * i + k] != 0;
+        all_fx = all_fx && fixed[3 * i + k] != 0;
+        any_fixed = any_fixed || fixed[3 * i + k] != 0;
       }
-      n_fixed_atoms += fx ? 1 : 0;
+      n_fixed_atoms += all_fx ? 1 : 0;
     }
-    any_fixed = n_fixed_atoms > 0;
   }
   pin_range(pot, positions, rows * D * sizeof(double));
   pin_range(pot, projected, mov * D * sizeof(double));
@@ -1090,7 +1110,6 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
                         double *const *forces, double *energies, double *variances, const double *const *boxes) {
   if (!pot) return 1;
   if (S <= 0 || N <= 0) return fail(pot, 2, "force_batch: nSystems and nAtoms must be positive");
-  if (N > kNbrIndexMask) return fail(pot, 2, "force_batch: more than %d atoms per system", kNbrIndexMask);
   CU_TRY(pot, cudaSetDevice(pot->device));
   // one topology / one box shared by all systems (the same pointer in every slot): keep a single copy
   bool same_Z = true, same_box = true;
@@ -1099,15 +1118,9 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
     same_box = same_box && boxes[s] == boxes[0];
   }
   const long SZ = same_Z ? 1 : S, SB = same_box ? 1 : S;
-  // unknown element -> 14324 (EAM.cpp:116-123)
-  if (pot->cfg.kind == EONB200_POT_EAM) {
-    for (long s = 0; s < SZ; s++)
-      for (long i = 0; i < N; i++) {
-        const int z = atomicNrs[s][i];
-        bool found = false;
-        for (const auto &r : pot->rows) found = found || r.Z == z;
-        if (!found) return fail(pot, 14324, "EAM: no parameter row for atomic number %d", z);
-      }
+  for (long s = 0; s < SZ; s++) {
+    const int rc = check_system(pot, N, atomicNrs[s], "force_batch");
+    if (rc) return rc;
   }
   const size_t D = 3 * static_cast<size_t>(N);
   const size_t strideR = (D + 1) / 2 * 2;  // even: every system starts 16-byte aligned
@@ -1189,6 +1202,10 @@ int eonb200_force_batch_device(EonB200Pot *pot, long S, long N, const double *d_
                                double *d_forces, double *d_energies, const double *d_boxes, int sync) {
   if (!pot) return 1;
   if (S <= 0 || N <= 0) return fail(pot, 2, "force_batch_device: nSystems and nAtoms must be positive");
+  {
+    const int rc = check_system(pot, N, nullptr, "force_batch_device");  // (atomic numbers live on the device: an
+    if (rc) return rc;                                                    // unknown element yields NaN energies)
+  }
   CU_TRY(pot, cudaSetDevice(pot->device));
   ForceBatchArgs a;
   memset(&a, 0, sizeof(a));

@@ -686,7 +686,7 @@ __device__ EONB200_NOINLINE int eam_n3_cold(FusedCold *fc, const NlBatch *nl, co
   for (int k = tid; k < 128; k += nt) sm.exp_tab[k] = P.exp_tab[k];
   const double Lbox[3] = {sys.box[0], sys.box[4], sys.box[8]};
   fill_sh27(sm, Lbox[0], Lbox[1], Lbox[2]);
-  const bool have = *sys.state != 0;
+  const bool have = nl_have_list(sys);
   const int z0 = sys.Z[0];
   double mixed_t = 0.0;
   for (int i = tid; i < N; i += nt)
@@ -800,6 +800,8 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   bx.Lz = sys.box[8];
   for (int k = tid; k < 16; k += nt) sm.t16[k] = P.exp_t16[k];
   const double lo[3] = {ld_cg(sys.lo_build), ld_cg(sys.lo_build + 1), ld_cg(sys.lo_build + 2)};
+  const double Lb[3] = {ld_cg(sys.box_build), ld_cg(sys.box_build + 4), ld_cg(sys.box_build + 8)};  // (the fast path
+  // is for orthorhombic use: EAM.cpp:31 reads the diagonal only; the cold path compares the whole cell)
   // build positions and atomic numbers of the atoms this thread converts in the first round
   double rb[3] = {0.0, 0.0, 0.0};
   int zz = 0;
@@ -859,7 +861,8 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   const int r0h = hdr.w & 0xff;
   // The common case is decided by ONE barrier; anything else takes the out-of-line path.
   const bool uniform_ok = a.force_rebuild == 0 && P.skin > 0.0 && tab_ok && P.eam_fast_ok != 0 &&
-                          hdr.y == sys.n3_lpa && hdr.x <= sys.slot_cap && r0h < P.n_rows && N <= kN3MaxAtoms;
+                          hdr.y == sys.n3_lpa && hdr.x <= sys.slot_cap && r0h < P.n_rows && N <= kN3MaxAtoms &&
+                          Lb[0] == bx.Lx && Lb[1] == bx.Ly && Lb[2] == bx.Lz;
   {
     const int rq = min(r0h, P.n_rows - 1);
     for (int k = tid; k < 18; k += nt) coef[k] = k < 9 ? P.rows[rq].c[k] : P.rows[rq].dc[k - 9];

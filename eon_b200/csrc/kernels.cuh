@@ -449,7 +449,7 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     }
   }
   const double Lbox[3] = {sys.box[0], sys.box[4], sys.box[8]};  // EAM.cpp:31 reads the diagonal only
-  const bool have = ld_cg(sys.state) != 0;
+  const bool have = nl_have_list(sys);
   const int z0 = sys.Z[0];
   int cls_first = 0;
   int cur[kFilterBatch];

@@ -506,6 +506,15 @@ __device__ inline int nl_build(const NlParams &np, const SysView &sys, Smem &sm)
   return row_max;
 }
 
+// A cached list is only good for the cell it was built in (image shifts and folds are stored per pair).
+__device__ __forceinline__ bool nl_have_list(const SysView &sys) {
+  bool have = ld_cg(sys.state) != 0;
+  if (have && sys.box_build) {
+    for (int k = 0; k < 9; k++) have = have && ld_cg(sys.box_build + k) == sys.box[k];
+  }
+  return have;
+}
+
 // Stage positions (sm.stage raw, sm.pos in the predicate's layout) and decide whether the cached candidate
 // list still covers them (Verlet check).  CTA-uniform result; every thread has read *sys.state on return.
 __device__ inline bool nl_stage_check(const NlParams &np, const SysView &sys, Smem &sm, uint32_t &phase,
@@ -513,7 +522,7 @@ __device__ inline bool nl_stage_check(const NlParams &np, const SysView &sys, Sm
   stage_raw_positions(sys, sm, phase);
   const double disp2 = prepare_positions(np, sys, sm, exp_tab_g, tables_ready);
   if (threadIdx.x == 0) sm.geom->disp2 = disp2;
-  const bool have = *sys.state != 0;
+  const bool have = nl_have_list(sys);
   const double lim = 0.5 * np.skin;
   const bool rebuild = force_rebuild || !have || np.skin <= 0.0 || !(disp2 <= lim * lim);
   __syncthreads();  // every thread has read *sys.state before it can change
@@ -530,6 +539,8 @@ __device__ EONB200_NOINLINE int nl_rebuild(const NlParams &np, const SysView &sy
     sys.rbuild[3 * i + 2] = p.z;
   }
   if (threadIdx.x == 0) {
+    if (sys.box_build)
+      for (int k = 0; k < 9; k++) sys.box_build[k] = sys.box[k];
     *sys.state = 1;
     atomicAdd(&sys.stats[0], 1ULL);
   }

@@ -64,6 +64,7 @@ struct NlBatch {
   int *cnt;        // [S][Np]     row fill
   double *rbuild;  // [S][3N]     positions the list was built from (Verlet displacement check)
   int *state;      // [S]         0 = no list yet, 1 = list valid for rbuild
+  double *box_build;  // [S][9]   cell the list was built for (a different cell invalidates it)
   int K, Np;
   int *overflow;             // [1] largest row fill any build needed (> K means the list is truncated)
   unsigned long long *stats; // [0] rebuilt, [1] reused, [2] ordered pairs of the last evaluation
@@ -111,6 +112,7 @@ struct SysView {
   int *cnt;          // [Np]
   double *rbuild;    // [3N]
   int *state;        // [1]
+  double *box_build; // [9]
   int K, Np;
   int *overflow;
   unsigned long long *stats;
@@ -149,6 +151,7 @@ __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, con
   v.cnt = nl.cnt + static_cast<size_t>(s) * nl.Np;
   v.rbuild = nl.rbuild + static_cast<size_t>(s) * 3 * N;
   v.state = nl.state + s;
+  v.box_build = nl.box_build ? nl.box_build + static_cast<size_t>(s) * 9 : nullptr;
   v.K = nl.K;
   v.Np = nl.Np;
   v.overflow = nl.overflow;

@@ -87,7 +87,8 @@ def band_forces(pot, positions, atomic_nrs, box, fixed=None, endpoint_energies=N
         Fm -= Fm.mean(axis=1, keepdims=True)
     F[:, 1:M + 1] = Fm.reshape(B, M, D)
     E[:, 1:M + 1] = np.asarray(Um).reshape(B, M)
-    n_free = N - int(np.asarray(fixed).reshape(N, 3).any(axis=1).sum()) if fixed is not None else N
+    # Matter::numberOfFreeAtoms counts an atom as fixed only when all three axes are (client/Matter.cpp getFixed)
+    n_free = N - int(np.asarray(fixed).reshape(N, 3).all(axis=1).sum()) if fixed is not None else N
     P, T, ci = neb_forces(pot, R, F, E, box, n_free, prm, **kw)
     return {"projected": P, "tangents": T, "climbing": ci, "energies": E, "forces": F[:, 1:M + 1]}
 
@@ -131,7 +132,7 @@ def convergence_force(projected, climbing=None, metric: str = "norm", fixed=None
     elif metric == "max_atom":
         a = np.linalg.norm(P.reshape(B, M, N, 3), axis=3)
         if fixed is not None:
-            a = a[:, :, ~np.asarray(fixed).reshape(N, 3).any(axis=1)]
+            a = a[:, :, ~np.asarray(fixed).reshape(N, 3).all(axis=1)]
         per = a.max(axis=2)
     elif metric == "max_component":
         per = P.max(axis=2)

@@ -16,6 +16,8 @@ from __future__ import annotations
 import math
 from typing import List, Optional, Sequence, Tuple
 
+import warnings
+
 import numpy as np
 
 from .hessian import assemble_hessian, displaced_systems
@@ -27,8 +29,9 @@ STATUS_FAILED_PREFACTOR = 10
 
 
 def _per_atom(fixed, n) -> np.ndarray:
+    """``Matter::getFixed(i)``: an atom counts as fixed only when all of its axes are."""
     f = np.asarray(fixed).reshape(n, -1)
-    return f.any(axis=1)
+    return f.all(axis=1)
 
 
 def _free_moves(min1, saddle, min2, cell, fixed) -> Tuple[np.ndarray, np.ndarray]:
@@ -104,13 +107,14 @@ def moved_atoms_pct(min1, saddle, min2, cell, fixed, filter_fraction: float = 0.
 
 
 def remove_zero_freqs(freqs: np.ndarray, n_atoms: int, zero_freq_value: float = 1e-6) -> Optional[np.ndarray]:
-    """``Hessian::removeZeroFreqs`` (client/Hessian.cpp:277-305): only when the Hessian spans all 3 N coordinates;
-    anything but 6 trivial modes is an error."""
+    """``Hessian::removeZeroFreqs`` (client/Hessian.cpp:277-305): only when the Hessian spans all 3 N coordinates.  A
+    count of trivial modes other than 6 is only logged there; the shortened vector is returned all the same and the
+    size check of `rate_prefactors` decides."""
     if freqs.size != 3 * n_atoms:
         return freqs
     keep = np.abs(freqs) > zero_freq_value
     if freqs.size - int(keep.sum()) != 6:
-        return None
+        warnings.warn("removeZeroFreqs: found %d trivial eigenmodes instead of 6" % (freqs.size - int(keep.sum())))
     return freqs[keep]
 
 

@@ -62,7 +62,8 @@ def process_results(out: Dict[str, object], initial_positions, cell, fixed, max_
     hold the endpoint positions after the reference's swap rule."""
     cell = np.asarray(cell, dtype=float).reshape(3, 3)
     init = np.asarray(initial_positions, dtype=float).reshape(-1, 3)
-    any_fixed = bool(np.asarray(fixed).any())
+    # translationRemove applies when Matter::numberOfFixedAtoms() == 0, an atom being fixed when all its axes are
+    any_fixed = bool(np.asarray(fixed).reshape(len(init), -1).all(axis=1).any())
     sad, m1, m2 = out["saddle"], out["min1"], out["min2"]
     W = len(sad.status)
     results = []

@@ -219,3 +219,30 @@ def test_resident_band_evaluation_matches_host_path(backend, oracle, system):
         scale = max(1.0, np.abs(ref["projected"]).max())
         assert np.abs(out["projected"] - ref["projected"]).max() <= 1e-10 * scale
         assert np.abs(again["projected"] - out["projected"]).max() <= 1e-10 * scale and again["tangents"] is None
+
+
+@pytest.mark.parametrize("kind,fixture", [("eam", "neb_al.json"), ("morse_pt", "morse_pt_saddle.json")])
+def test_cell_change_on_one_handle_invalidates_cached_lists(backend, oracle, kind, fixture):
+    """A handle evaluated in one cell and then in another (same positions, so no atom has moved) must not reuse the
+    lists and image shifts of the first cell: the build cell is recorded with every cached list and compared in the
+    Verlet check.  Checked against a fresh handle, through the resident band call and forceBatch."""
+    a = oracle.load_fixture(fixture)
+    Z, N = a["atomic_nrs"], len(a["atomic_nrs"])
+    cell_a = np.array(a["cell"], dtype=np.float64)
+    cell_b = cell_a.copy()
+    cell_b[0, 0] *= 0.97  # atoms near the +x face now see their periodic neighbours 3 % closer
+    M, B = 3, 2
+    rng = np.random.default_rng(5)
+    R = a["positions"][None, None] + rng.normal(0.0, 0.01, (B, M + 2, N, 3))
+    R = R.reshape(B, M + 2, -1)
+    with B200Potential(kind, lib=backend) as pot:
+        NEB.band_forces_resident(pot, R, Z, cell_a, None, climbing_image=1)
+        out = NEB.band_forces_resident(pot, R, Z, cell_b, None, climbing_image=1)
+        F1, U1, _ = pot.forceBatch(B * (M + 2), N, R.reshape(B * (M + 2), -1), Z, cell_a.reshape(9))
+    with B200Potential(kind, lib=backend) as pot:
+        ref = NEB.band_forces_resident(pot, R, Z, cell_b, None, climbing_image=1)
+    with B200Potential(kind, lib=backend) as pot:
+        F0, U0, _ = pot.forceBatch(B * (M + 2), N, R.reshape(B * (M + 2), -1), Z, cell_a.reshape(9))
+    assert np.abs(out["energies"] - ref["energies"]).max() <= 1e-9
+    assert np.abs(out["projected"] - ref["projected"]).max() <= 1e-10 * max(1.0, np.abs(ref["projected"]).max())
+    assert np.abs(U1 - U0).max() <= 1e-9 and np.abs(F1 - F0).max() <= 1e-10 * max(1.0, np.abs(F0).max())

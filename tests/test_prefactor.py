@@ -46,7 +46,9 @@ def test_rate_rules():
     z = np.concatenate([np.zeros(6), np.arange(1.0, 4.0)])
     assert PF.remove_zero_freqs(z, 3).tolist() == [1.0, 2.0, 3.0]
     assert PF.remove_zero_freqs(z[1:], 3) is z[1:] or PF.remove_zero_freqs(z[1:], 3).size == 8  # not 3N: untouched
-    assert PF.remove_zero_freqs(np.concatenate([np.zeros(5), np.arange(1.0, 5.0)]), 3) is None
+    # five trivial modes instead of six: Hessian.cpp:296-301 only logs it and returns the shortened vector
+    with pytest.warns(UserWarning):
+        assert PF.remove_zero_freqs(np.concatenate([np.zeros(5), np.arange(1.0, 5.0)]), 3).tolist() == [1.0, 2.0, 3.0, 4.0]
 
 
 def test_prefactors_known_answer(backend, oracle):
