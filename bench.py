@@ -45,8 +45,8 @@ NCU_DRAM_BYTES_PER_LAUNCH = 31.2e6
 NCU_TRAFFIC_SOURCE = ("profiles/r1c_fused_ncu_raw_selected.csv: 27.1 MB read + 4.0 MB written per launch (cold L2); the "
                       "64 N + 8 P_o = 33.7 MB of SURVEY.md 8d assume every list row is read twice from HBM -- rows certain "
                       "to be outside the cutoff are not read at all and the pair cache stays in L2")
-SEARCH_ROW_Z = 79  # the in-tree Au row: see DESIGN.md "Search workload"
-A0_AU = 4.092320738309691  # equilibrium fcc lattice constant of the in-tree EAM Au row (oracle)
+SEARCH_ROW_Z = WL.SEARCH_ROW_Z  # the in-tree Au row: see DESIGN.md "Search workload"
+A0_AU = WL.A0_AU  # equilibrium fcc lattice constant of the in-tree EAM Au row (oracle)
 
 
 def eam_flops(ordered_pairs: float, atoms: float) -> float:
@@ -138,12 +138,7 @@ def force_workload(first_walker: int):
 
 def search_workload():
     """akmc-al geometry scaled to the lattice constant of the in-tree EAM Au row; all atoms Z = 79."""
-    s = WL.load_structure("akmc_al.json")
-    scale = A0_AU / 4.05
-    s.positions = s.positions * scale
-    s.cell = s.cell * scale
-    s.atomic_nrs = np.full_like(s.atomic_nrs, SEARCH_ROW_Z)
-    return s, scale
+    return WL.akmc_al_on_au_row()
 
 
 SEARCH_PARAMS = dict(opt_method=1, opt_converged_force=1e-4, opt_max_iterations=1000, minmode_method=0,

@@ -190,3 +190,145 @@ def test_force_call_counter_counts_walker_evaluations(backend, oracle):
         h = wk.harvest(geometry=False)
         assert pot.forceCallCounter == 4 + int(h.force_calls.sum())
         wk.close()
+
+
+MANY_DOF_CASES = [
+    # the examples/akmc-al/config.ini settings: Lanczos (tolerance 0.05) + LBFGS
+    ("lanczos-lbfgs", dict(minmode_method=1, lanczos_tolerance=0.05, opt_method=1)),
+    ("lanczos-cg", dict(minmode_method=1, lanczos_tolerance=0.05, opt_method=0)),
+    ("dimer-cg", dict(minmode_method=0, opt_method=0)),
+    ("dimer-fire", dict(minmode_method=0, opt_method=2)),
+    ("dimer-sd-rotation-lbfgs", dict(minmode_method=0, dimer_opt_method=0, opt_method=1)),
+    ("dimer-lbfgs-rotation-lbfgs", dict(minmode_method=0, dimer_opt_method=2, opt_method=1)),
+    ("dimer-lbfgs-max-atom", dict(minmode_method=0, opt_method=1, convergence_metric=1)),
+    ("lanczos-lbfgs-max-component", dict(minmode_method=1, lanczos_tolerance=0.05, opt_method=1, convergence_metric=2)),
+]
+
+
+@pytest.fixture(scope="module")
+def al_slab_minimum(oracle):
+    """The akmc-al slab (385 atoms, 257 free) on the in-tree Au row (workloads.akmc_al_on_au_row: the Al row has no
+    stable crystal under F = -grad U), relaxed by the oracle."""
+    s, scale = WL.akmc_al_on_au_row()
+    opot = oracle.potential(oracle.POT_EAM_NL, conservative=True)
+    res, Rmin = oracle.relax(opot, oracle.search_params(opt_method=1, opt_converged_force=1e-3), s.positions,
+                             s.atomic_nrs, s.fixed, s.cell)
+    assert res.converged == 1
+    return s, Rmin, res.energy, scale
+
+
+@pytest.mark.parametrize("label,kw", MANY_DOF_CASES, ids=[c[0] for c in MANY_DOF_CASES])
+def test_many_dof_method_matrix(backend, oracle, al_slab_minimum, label, kw):
+    """Every min-mode method / optimizer / rotation optimizer / convergence metric on a system with 771 free degrees
+    of freedom (the 1-free-atom fixture exhausts Lanczos' Krylov space after three vectors and never exercises the
+    device QL solver beyond 3 x 3): walkers displaced as in examples/akmc-al land on the oracle's saddles with the
+    oracle's iteration and force-call counts."""
+    s, Rmin, E0, scale = al_slab_minimum
+    base = dict(opt_converged_force=1e-4, saddle_max_energy=10.0, saddle_max_iterations=600)  # akmc-al: 1e-4
+    base.update(kw)
+    oprm, prm = same_params(oracle, backend, **base)
+    opot = oracle.potential(oracle.POT_EAM_NL, conservative=True)
+    W = 2
+    _, R, M = WL.walkers_for(WL.AKMC_AL, Rmin, W, first_walker=7, struct=s, scale=scale)
+    with B200Potential("eam", lib=backend, conservative=True) as pot:
+        wk = Walkers(pot, s.atomic_nrs, s.fixed, s.cell, R, M)
+        wk.saddle_search(prm, E0)
+        h = wk.harvest()
+        wk.close()
+    n_good = 0
+    for w in range(W):
+        ref, Rref, Mref = oracle.saddle_search(opot, oprm, R[w], s.atomic_nrs, s.fixed, s.cell, M[w], E0)
+        assert h.status[w] == ref.status, (label, w, h.status[w], ref.status)
+        if ref.status == 0:
+            n_good += 1
+            assert abs(h.energies[w] - ref.energy) < E_TOL
+            assert mic_max(h.positions[w], Rref, s.cell) < R_TOL
+            # the curvature estimate of the last rotation is only as good as dimer_converged_angle / the Lanczos
+            # tolerance allow (the SD rotation leaves 2e-3 between two runs that differ in the last bit)
+            assert abs(h.eigenvalues[w] - ref.eigenvalue) < 5e-3
+            assert abs(abs(np.vdot(h.modes[w], Mref)) - 1.0) < 2e-3
+        # same trajectory: the step counts agree (a few per cent of slack: rounding differences of the two exp
+        # implementations move a convergence test by an iteration here and there)
+        assert abs(int(h.iterations[w]) - int(ref.iterations)) <= max(2, ref.iterations // 30), \
+            (label, w, h.iterations[w], ref.iterations)
+    assert n_good >= 1, label
+
+
+def test_c3_size_resident_walkers(backend, oracle):
+    """BASELINE configs[2] shape: a 2047-atom periodic fcc cell with one vacancy, all atoms free (6141 degrees of
+    freedom, more atoms than a CTA has threads), searched with the settings of examples/akmc-cu-vacancy/config.ini
+    (dimer with at most 20 rotations, LBFGS memory 25) on the in-tree Au row at its own lattice constant.  The walkers
+    start next to the vacancy and must land on the oracle's saddles."""
+    s = WL.fcc_vacancy(8, WL.A0_AU, WL.SEARCH_ROW_Z)
+    assert s.n_atoms == 2047
+    kw = dict(opt_method=1, opt_converged_force=1e-3, lbfgs_memory=25, minmode_method=0, dimer_rotations_max=20,
+              saddle_max_energy=10.0, saddle_max_iterations=300)
+    oprm, prm = same_params(oracle, backend, **kw)
+    opot = oracle.potential(oracle.POT_EAM_NL, conservative=True)
+    relp_o, relp = same_params(oracle, backend, opt_method=1, opt_converged_force=1e-3, lbfgs_memory=25)
+    res, Rmin = oracle.relax(opot, relp_o, s.positions, s.atomic_nrs, s.fixed, s.cell)
+    assert res.converged == 1
+    W = 2
+    # the vacancy sits at the origin: atom 0 of the list is one of its twelve neighbours
+    R = np.empty((W, s.n_atoms, 3))
+    M = np.empty((W, s.n_atoms, 3))
+    for w in range(W):
+        R[w], M[w] = WL.displace(s, Rmin, 0, 3.0 * WL.A0_AU / 3.615, 0.3, 42 + 2 * w)
+    with B200Potential("eam", lib=backend, conservative=True) as pot:
+        wk = Walkers(pot, s.atomic_nrs, s.fixed, s.cell, Rmin.reshape(1, -1).repeat(W, 0))
+        E0, _ = wk.matter_forces()
+        assert np.abs(E0 - res.energy).max() < 1e-7
+        wk.set(positions=R, modes=M)
+        wk.saddle_search(prm, E0)
+        h = wk.harvest()
+        wk.close()
+    n_good = 0
+    for w in range(W):
+        ref, Rref, _ = oracle.saddle_search(opot, oprm, R[w], s.atomic_nrs, s.fixed, s.cell, M[w], res.energy)
+        assert h.status[w] == ref.status
+        if ref.status == 0:
+            n_good += 1
+            assert abs(h.energies[w] - ref.energy) < E_TOL
+            assert mic_max(h.positions[w], Rref, s.cell) < R_TOL
+            assert abs(int(h.iterations[w]) - int(ref.iterations)) <= max(2, ref.iterations // 30)
+    assert n_good >= 1
+
+
+def test_c1_lj13_dimer_search(backend, oracle):
+    """BASELINE configs[0]: the LJ13 cluster with the reference's own saddle-search fixture
+    (client/unit_tests/SaddleSearchTest.cpp:33-54: CG, optimizer converged_force 0.01, max_move 0.1, dimer angle 0.01,
+    100 iterations, saddle converged_force 0.05, max_energy 20; atom 0 displaced by (+0.3, -0.2, 0); a random unit
+    mode).  The reference asserts a valid status and a finite eigenvalue; here the device walker must also follow the
+    oracle step for step.  Second case of the same file (:96-112): 2 iterations at 1e-10 cannot end GOOD."""
+    d = oracle.load_fixture("lj13.json")
+    Z, box, fixed = d["atomic_nrs"], d["cell"], d["fixed"]
+    R0 = d["positions"].copy()
+    R = R0.copy()
+    R[0, 0] += 0.3
+    R[0, 1] -= 0.2
+    rng = np.random.default_rng(13)
+    mode = rng.uniform(-1.0, 1.0, R.shape)  # AtomMatrix::Random: uniform in [-1, 1], then normalised
+    mode /= np.linalg.norm(mode)
+    base = dict(opt_method=0, opt_converged_force=0.01, max_move=0.1, dimer_converged_angle=0.01, minmode_method=0,
+                saddle_max_iterations=100, saddle_converged_force=0.05, saddle_max_energy=20.0)
+    opot = oracle.potential(oracle.POT_LJ)
+    E0, _ = oracle.force(opot, R, Z, box)  # the fixture takes the DISPLACED structure's energy as the reactant energy
+    # (1) the first 25 iterations, step for step.  Beyond ~30 iterations this search is chaotic: with a random mode in
+    # the convex region and a 0.01 rad rotation tolerance, last-bit differences of the summation order grow by a
+    # decade every few iterations (1e-13 eV after one iteration, 1e-7 after 30) until the two dimers pick different
+    # modes, so only a prefix can be compared between any two implementations.
+    # (2) the reference's own assertions on the full run; (3) its max-iterations case.
+    for extra, compare in ((dict(saddle_max_iterations=25), True), (dict(), False),
+                           (dict(saddle_max_iterations=2, saddle_converged_force=1e-10), True)):
+        oprm, prm = same_params(oracle, backend, **dict(base, **extra))
+        ref, Rref, Mref = oracle.saddle_search(opot, oprm, R, Z, fixed, box, mode, E0)
+        with B200Potential("lj", lib=backend) as pot:
+            wk = Walkers(pot, Z, fixed, box, R.reshape(1, -1), mode.reshape(1, -1))
+            wk.saddle_search(prm, E0)
+            h = wk.harvest()
+            wk.close()
+        assert 0 <= h.status[0] <= 21 and np.isfinite(h.eigenvalues[0])  # SaddleSearchTest.cpp:70-72,88-89
+        if compare:
+            assert h.status[0] == ref.status == 5  # SaddleSearchTest.cpp:110-111: not GOOD
+            assert h.iterations[0] == ref.iterations and h.force_calls[0] == ref.force_calls
+            assert abs(h.energies[0] - ref.energy) < 1e-6 and np.abs(h.positions[0] - Rref).max() < 1e-6
