@@ -15,7 +15,7 @@ MINMODE_DIMER, MINMODE_LANCZOS = 0, 1
 ROT_SD, ROT_CG, ROT_LBFGS = 0, 1, 2
 METRIC_NORM, METRIC_MAX_ATOM, METRIC_MAX_COMPONENT = 0, 1, 2
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 #: every symbol include/eonb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -25,6 +25,8 @@ SYMBOLS = [
     "eonb200_walkers_create", "eonb200_walkers_destroy", "eonb200_walkers_set",
     "eonb200_walkers_matter_forces", "eonb200_walkers_saddle_search", "eonb200_walkers_relax",
     "eonb200_walkers_displace_along_mode", "eonb200_walkers_harvest", "eonb200_walkers_last_ms",
+    "eonb200_walkers_set_active", "eonb200_walkers_groups", "eonb200_walkers_submit", "eonb200_walkers_poll",
+    "eonb200_walkers_harvest_group",
     "eonb200_measure_fp64_peak", "eonb200_kernel_launches", "eonb200_nl_stats",
     "eonb200_last_force_ms", "eonb200_phase_clocks", "eonb200_l2_flush",
     "eonb200_neb_params_default", "eonb200_neb_forces", "eonb200_neb_forces_device", "eonb200_neb_band_forces",
@@ -120,6 +122,16 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.eonb200_walkers_displace_along_mode.restype = C.c_int
     lib.eonb200_walkers_harvest.argtypes = [_vp, _ip, _lp, _lp, _dp, _dp, _dp, _dp, _dp]
     lib.eonb200_walkers_harvest.restype = C.c_int
+    lib.eonb200_walkers_set_active.argtypes = [_vp, _ip]
+    lib.eonb200_walkers_set_active.restype = C.c_int
+    lib.eonb200_walkers_groups.argtypes = [_vp, C.c_int]
+    lib.eonb200_walkers_groups.restype = C.c_int
+    lib.eonb200_walkers_submit.argtypes = [_vp, C.c_int, C.c_int, C.POINTER(SearchParams), C.c_long, C.c_long, _dp, _dp, _dp]
+    lib.eonb200_walkers_submit.restype = C.c_int
+    lib.eonb200_walkers_poll.argtypes = [_vp, C.c_int, C.c_int]
+    lib.eonb200_walkers_poll.restype = C.c_int
+    lib.eonb200_walkers_harvest_group.argtypes = [_vp, C.c_int, _ip, _lp, _lp, _dp, _dp, _dp, _dp, _dp]
+    lib.eonb200_walkers_harvest_group.restype = C.c_int
     lib.eonb200_walkers_last_ms.argtypes = [_vp]
     lib.eonb200_walkers_last_ms.restype = C.c_double
     lib.eonb200_measure_fp64_peak.argtypes = [_vp, C.c_int]

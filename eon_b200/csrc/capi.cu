@@ -6,6 +6,8 @@
 #include "neb.cuh"
 
 #include <algorithm>
+#include <array>
+#include <chrono>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -85,6 +87,8 @@ struct NlStore {
 
 }  // namespace
 
+constexpr int kPipeMax = 8;  // most chunks a batch is split into
+
 struct EonB200Pot {
   EonB200Config cfg;
   PotParams hp;
@@ -92,6 +96,9 @@ struct EonB200Pot {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  // chunked host <-> device pipeline of eonb200_force_batch: copy-in stream, second compute stream, copy-out stream
+  cudaStream_t s_in = nullptr, s_k2 = nullptr, s_out = nullptr;
+  cudaEvent_t ev_m = nullptr, ev_in[kPipeMax] = {}, ev_k[kPipeMax] = {}, ev_out[kPipeMax] = {};
   DevBuf<PotParams> dP;
   DevBuf<double> d_exp_tab;
   DevBuf<unsigned char> d_flush;  // eonb200_l2_flush scratch
@@ -108,6 +115,7 @@ struct EonB200Pot {
   PinBuf<double> hR, hF, hU, hbox;
   PinBuf<int> hZ;
   std::vector<double> last_boxes;
+  long z_cached_S = 0, z_cached_N = 0;  // shape of the atomic numbers held in hZ / dZ (0: none)
   std::vector<std::pair<const char *, size_t>> pinned;  // caller ranges page-locked by this handle (pin_host_buffers)
   NlStore nl;  // cache of the stateless batch slots
   DevBuf<double> neb_R, neb_F, neb_E, neb_P, neb_T;  // eonb200_neb_forces staging
@@ -137,6 +145,12 @@ struct EonB200Walkers {
   std::vector<double> h_box;
   double last_ms = 0.0;
   bool have_modes = false;
+  DevBuf<int> active;       // [W] 1 = takes part in the next launches
+  bool use_active = false;
+  // group-wise asynchronous jobs (eonb200_walkers_submit): one stream and one completion event per group
+  std::vector<cudaStream_t> g_stream;
+  std::vector<cudaEvent_t> g_done;
+  std::vector<std::array<long, 2>> g_range;  // [first, count] of the job in flight on the group, count 0 = idle
 };
 
 namespace {
@@ -544,8 +558,16 @@ bool pin_range(EonB200Pot *pot, const void *p, size_t bytes) {
 
 // Launch the batched force evaluation on device-resident arrays; handles truncated lists by
 // regrowing the row capacity and re-running.  Synchronises when it has to look at the flags.
+// A batch split into chunks of systems whose copy-in, kernel and copy-out overlap on three streams (chunk c + 1 comes
+// up while chunk c computes and chunk c - 1 goes back).  in / out enqueue the copies of systems [s0, s1) on the stream
+// they are given.
+struct BatchPipe {
+  int chunks = 1;
+  std::function<int(long s0, long s1, cudaStream_t st)> in, out;
+};
+
 int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double *h_box0, bool sync_and_check,
-                    const std::function<int()> &enqueue_readback = nullptr) {
+                    const std::function<int()> &enqueue_readback = nullptr, const BatchPipe *pipe = nullptr) {
   const long S = a.S, N = a.N;
   if (nl.S < S || nl.N != N || nl.K == 0) {
     double unit[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
@@ -614,60 +636,102 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
       view.slot_cap = slot_cap;
       view.n3_lpa = a.lpa;
     }
-    CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
+    // one launch (or launch pair) over Sc systems of the view vw / the arrays of ac, on stream st
+    auto launch = [&](const NlBatch &vw, const ForceBatchArgs &ac, long Sc, cudaStream_t st) -> int {
     if (n3) {
-      const dim3 grid(1u, static_cast<unsigned>(S));
+        const dim3 grid(1u, static_cast<unsigned>(Sc));
 #ifdef EONB200_EMU
-      EONB200_LAUNCH(k_eam_n3, grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+        EONB200_LAUNCH(k_eam_n3, grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
 #else
-      static const int n3_minb = getenv("EONB200_N3_MINB") ? atoi(getenv("EONB200_N3_MINB")) : 0;  // development aid
-      const bool two = n3_minb != 1 && 2 * (fused_smem + 1024) <= 227 * 1024;
-      if (n3_minb == 2 && fused_threads <= 224 && two)
-        EONB200_LAUNCH((k_eam_n3_t<224, 2>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
-      else if (n3_minb != 1 && fused_threads <= 224 && 4 * (fused_smem + 1024) <= 227 * 1024)
-        EONB200_LAUNCH((k_eam_n3_t<224, 4>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
-      else if (fused_threads <= 448 && two)
-        EONB200_LAUNCH((k_eam_n3_t<448, 2>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
-      else if (fused_threads <= 512 && two)
-        EONB200_LAUNCH((k_eam_n3_t<512, 2>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
-      else if (fused_threads <= 512)
-        EONB200_LAUNCH((k_eam_n3_t<512, 1>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
-      else if (fused_threads <= 800)
-        EONB200_LAUNCH((k_eam_n3_t<800, 1>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
-      else
-        EONB200_LAUNCH((k_eam_n3_t<1024, 1>), grid, fused_threads, fused_smem, pot->stream, pot->hp, pot->dP.p, view, a);
+        static const int n3_minb = getenv("EONB200_N3_MINB") ? atoi(getenv("EONB200_N3_MINB")) : 0;  // development aid
+        const bool two = n3_minb != 1 && 2 * (fused_smem + 1024) <= 227 * 1024;
+        if (n3_minb == 2 && fused_threads <= 224 && two)
+          EONB200_LAUNCH((k_eam_n3_t<224, 2>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
+        else if (n3_minb != 1 && fused_threads <= 224 && 4 * (fused_smem + 1024) <= 227 * 1024)
+          EONB200_LAUNCH((k_eam_n3_t<224, 4>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
+        else if (fused_threads <= 448 && two)
+          EONB200_LAUNCH((k_eam_n3_t<448, 2>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
+        else if (fused_threads <= 512 && two)
+          EONB200_LAUNCH((k_eam_n3_t<512, 2>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
+        else if (fused_threads <= 512)
+          EONB200_LAUNCH((k_eam_n3_t<512, 1>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
+        else if (fused_threads <= 800)
+          EONB200_LAUNCH((k_eam_n3_t<800, 1>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
+        else
+          EONB200_LAUNCH((k_eam_n3_t<1024, 1>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
 #endif
-      pot->launches += 1;
-    } else if (eam) {
-      const dim3 grid(static_cast<unsigned>(fused_T), static_cast<unsigned>(S));
+        pot->launches += 1;
+      } else if (eam) {
+        const dim3 grid(static_cast<unsigned>(fused_T), static_cast<unsigned>(Sc));
 #ifdef EONB200_EMU
-      EONB200_LAUNCH_CLUSTER(k_eam_fused, grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+        EONB200_LAUNCH_CLUSTER(k_eam_fused, grid, fused_threads, fused_smem, st, fused_T, pot->dP.p, vw, ac);
 #else
-      // register budgets: every walker of a few-hundred-walker batch must be resident at once
-      if (fused_threads <= 128)
-        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<128, 7>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
-      else if (fused_threads <= 224)
-        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<224, 4>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
-      else if (fused_threads <= 448)
-        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<448, 2>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
-      else if (2 * (fused_smem + 1024) <= 227 * 1024)
-        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<512, 2>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
-      else
-        EONB200_LAUNCH_CLUSTER((k_eam_fused_t<512, 1>), grid, fused_threads, fused_smem, pot->stream, fused_T, pot->dP.p, view, a);
+        // register budgets: every walker of a few-hundred-walker batch must be resident at once
+        if (fused_threads <= 128)
+          EONB200_LAUNCH_CLUSTER((k_eam_fused_t<128, 7>), grid, fused_threads, fused_smem, st, fused_T, pot->dP.p, vw, ac);
+        else if (fused_threads <= 224)
+          EONB200_LAUNCH_CLUSTER((k_eam_fused_t<224, 4>), grid, fused_threads, fused_smem, st, fused_T, pot->dP.p, vw, ac);
+        else if (fused_threads <= 448)
+          EONB200_LAUNCH_CLUSTER((k_eam_fused_t<448, 2>), grid, fused_threads, fused_smem, st, fused_T, pot->dP.p, vw, ac);
+        else if (2 * (fused_smem + 1024) <= 227 * 1024)
+          EONB200_LAUNCH_CLUSTER((k_eam_fused_t<512, 2>), grid, fused_threads, fused_smem, st, fused_T, pot->dP.p, vw, ac);
+        else
+          EONB200_LAUNCH_CLUSTER((k_eam_fused_t<512, 1>), grid, fused_threads, fused_smem, st, fused_T, pot->dP.p, vw, ac);
 #endif
-      pot->launches += 1;
-    } else {
-      EONB200_LAUNCH(k_prepare, dim3(static_cast<unsigned>(S)), prep_threads, smem, pot->stream, pot->dP.p, view, a);
-      CU_TRY(pot, cudaEventRecord(pot->ev[1], pot->stream));
-      const dim3 grid(static_cast<unsigned>(a.tiles), static_cast<unsigned>(S));
-      EONB200_LAUNCH(k_pair, grid, tile_threads, tile_smem, pot->stream, pot->dP.p, view, a);
-      pot->launches += 2;
+        pot->launches += 1;
+      } else {
+        EONB200_LAUNCH(k_prepare, dim3(static_cast<unsigned>(Sc)), prep_threads, smem, st, pot->dP.p, vw, ac);
+        CU_TRY(pot, cudaEventRecord(pot->ev[1], st));
+        const dim3 grid(static_cast<unsigned>(a.tiles), static_cast<unsigned>(Sc));
+        EONB200_LAUNCH(k_pair, grid, tile_threads, tile_smem, st, pot->dP.p, vw, ac);
+        pot->launches += 2;
+      }
+      return 0;
+    };
+    CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
+#ifndef EONB200_EMU
+    if (pipe && pipe->chunks > 1 && sync_and_check) {
+      const int nc = std::min(pipe->chunks, kPipeMax);
+      CU_TRY(pot, cudaEventRecord(pot->ev_m, pot->stream));  // the counters are cleared
+      CU_TRY(pot, cudaStreamWaitEvent(pot->s_k2, pot->ev_m, 0));
+      for (int c = 0; c < nc; c++) {
+        const long s0 = S * c / nc, s1 = S * (c + 1) / nc;
+        if (s1 <= s0) continue;
+        int rcp = pipe->in(s0, s1, pot->s_in);
+        if (rcp) return rcp;
+        CU_TRY(pot, cudaEventRecord(pot->ev_in[c], pot->s_in));
+        cudaStream_t ks = (c & 1) ? pot->s_k2 : pot->stream;
+        CU_TRY(pot, cudaStreamWaitEvent(ks, pot->ev_in[c], 0));
+        NlBatch vw = view;
+        offset_systems(vw, static_cast<int>(N), s0);
+        ForceBatchArgs ac = a;
+        ac.S = static_cast<int>(s1 - s0);
+        ac.R += static_cast<size_t>(s0) * a.strideR;
+        ac.Z += static_cast<size_t>(s0) * a.strideZ;
+        ac.box += static_cast<size_t>(s0) * a.strideBox;
+        ac.F += static_cast<size_t>(s0) * a.strideR;
+        ac.U += s0;
+        if (ac.clocks) ac.clocks += static_cast<size_t>(s0) * 16 * std::max(1, a.tiles);
+        rcp = launch(vw, ac, s1 - s0, ks);
+        if (rcp) return rcp;
+        CU_TRY(pot, cudaEventRecord(pot->ev_k[c], ks));
+        CU_TRY(pot, cudaStreamWaitEvent(pot->s_out, pot->ev_k[c], 0));
+        rcp = pipe->out(s0, s1, pot->s_out);
+        if (rcp) return rcp;
+        CU_TRY(pot, cudaEventRecord(pot->ev_out[c], pot->s_out));
+        if (c & 1) CU_TRY(pot, cudaStreamWaitEvent(pot->stream, pot->ev_k[c], 0));  // the counters are read on pot->stream
+      }
+    } else
+#endif
+    {
+      const int rcl = launch(view, a, S, pot->stream);
+      if (rcl) return rcl;
     }
     CU_TRY(pot, cudaEventRecord(pot->ev[2], pot->stream));
     CU_TRY(pot, cudaGetLastError());
     pot->force_calls += static_cast<unsigned long long>(S);
     if (!sync_and_check) return 0;
-    if (enqueue_readback) {  // results follow the kernel without a host round trip; a truncated list re-runs everything
+    if (enqueue_readback && !(pipe && pipe->chunks > 1)) {  // results follow the kernel without a host round trip; a truncated list re-runs everything
       const int rb = enqueue_readback();
       if (rb) return rb;
     }
@@ -791,6 +855,16 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
   }
   bool ok = cudaStreamCreate(&pot->stream) == cudaSuccess;
   for (int k = 0; k < 3 && ok; k++) ok = cudaEventCreate(&pot->ev[k]) == cudaSuccess;
+#ifndef EONB200_EMU
+  ok = ok && cudaStreamCreateWithFlags(&pot->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+       cudaStreamCreateWithFlags(&pot->s_k2, cudaStreamNonBlocking) == cudaSuccess &&
+       cudaStreamCreateWithFlags(&pot->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+       cudaEventCreateWithFlags(&pot->ev_m, cudaEventDisableTiming) == cudaSuccess;
+  for (int k = 0; k < kPipeMax && ok; k++)
+    ok = cudaEventCreateWithFlags(&pot->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&pot->ev_k[k], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&pot->ev_out[k], cudaEventDisableTiming) == cudaSuccess;
+#endif
   ok = ok && pot->dP.reserve(1) == cudaSuccess && pot->d_overflow.reserve(1) == cudaSuccess &&
        pot->d_stats.reserve(4) == cudaSuccess && pot->h_stats.reserve(4) == cudaSuccess &&
        pot->h_overflow.reserve(1) == cudaSuccess;
@@ -861,6 +935,17 @@ void eonb200_destroy(EonB200Pot *pot) {
 #endif
   for (int k = 0; k < 3; k++)
     if (pot->ev[k]) cudaEventDestroy(pot->ev[k]);
+#ifndef EONB200_EMU
+  for (int k = 0; k < kPipeMax; k++) {
+    if (pot->ev_in[k]) cudaEventDestroy(pot->ev_in[k]);
+    if (pot->ev_k[k]) cudaEventDestroy(pot->ev_k[k]);
+    if (pot->ev_out[k]) cudaEventDestroy(pot->ev_out[k]);
+  }
+  if (pot->ev_m) cudaEventDestroy(pot->ev_m);
+  if (pot->s_in) cudaStreamDestroy(pot->s_in);
+  if (pot->s_k2) cudaStreamDestroy(pot->s_k2);
+  if (pot->s_out) cudaStreamDestroy(pot->s_out);
+#endif
   if (pot->stream) cudaStreamDestroy(pot->stream);
   delete pot;
 }
@@ -1109,6 +1194,13 @@ int eonb200_last_force_ms(EonB200Pot *pot, double out[2]) {
 int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *positions, const int *const *atomicNrs,
                         double *const *forces, double *energies, double *variances, const double *const *boxes) {
   if (!pot) return 1;
+  static const bool trace = getenv("EONB200_TRACE") != nullptr;  // development aid: host-side phase times on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (trace)
+      fprintf(stderr, "[force_batch] %-12s %8.1f us\n", what,
+              std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count());
+  };
   if (S <= 0 || N <= 0) return fail(pot, 2, "force_batch: nSystems and nAtoms must be positive");
   CU_TRY(pot, cudaSetDevice(pot->device));
   // one topology / one box shared by all systems (the same pointer in every slot): keep a single copy
@@ -1118,15 +1210,15 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
     same_box = same_box && boxes[s] == boxes[0];
   }
   const long SZ = same_Z ? 1 : S, SB = same_box ? 1 : S;
-  for (long s = 0; s < SZ; s++) {
-    const int rc = check_system(pot, N, atomicNrs[s], "force_batch");
-    if (rc) return rc;
-  }
+  if (N > kNbrIndexMask) return fail(pot, 2, "force_batch: more than %d atoms per system", kNbrIndexMask);
+  lap("checked");
   const size_t D = 3 * static_cast<size_t>(N);
   const size_t strideR = (D + 1) / 2 * 2;  // even: every system starts 16-byte aligned
   CU_TRY(pot, pot->dR.reserve(S * strideR));
   CU_TRY(pot, pot->dF.reserve(S * strideR));
   CU_TRY(pot, pot->dU.reserve(S));
+  if (pot->dZ.n < static_cast<size_t>(S * N) || pot->hZ.n < static_cast<size_t>(S * N)) pot->z_cached_S = 0;  // regrown: contents lost
+  if (pot->dbox.n < static_cast<size_t>(S * 9)) pot->last_boxes.clear();
   CU_TRY(pot, pot->dbox.reserve(S * 9));
   CU_TRY(pot, pot->dZ.reserve(S * N));
   CU_TRY(pot, pot->hR.reserve(S * strideR));
@@ -1137,23 +1229,75 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   bool box_changed = pot->last_boxes.size() != static_cast<size_t>(SB) * 9;
   const bool direct_in = rows_contiguous(positions, S, D) && pin_range(pot, positions[0], S * D * sizeof(double));
   const bool direct_out = rows_contiguous(forces, S, D) && pin_range(pot, forces[0], S * D * sizeof(double));
-  for (long s = 0; s < S; s++) {
-    if (!direct_in) {
-      memcpy(pot->hR.p + s * strideR, positions[s], D * sizeof(double));
-      if (strideR > D) pot->hR.p[s * strideR + D] = 0.0;
+  // atomic numbers: checked (EAM.cpp:116-123) and sent only when they differ from the previous call's
+  bool z_changed = pot->z_cached_S != SZ || pot->z_cached_N != N;
+  for (long s = 0; s < SZ && !z_changed; s++)
+    z_changed = memcmp(pot->hZ.p + s * N, atomicNrs[s], N * sizeof(int)) != 0;
+  if (z_changed) {
+    pot->z_cached_S = pot->z_cached_N = 0;
+    for (long s = 0; s < SZ; s++) {
+      const int rc = check_system(pot, N, atomicNrs[s], "force_batch");
+      if (rc) return rc;
+      memcpy(pot->hZ.p + s * N, atomicNrs[s], N * sizeof(int));
     }
-    if (s < SZ) memcpy(pot->hZ.p + s * N, atomicNrs[s], N * sizeof(int));
-    if (s < SB) memcpy(pot->hbox.p + s * 9, boxes[s], 9 * sizeof(double));
   }
+  for (long s = 0; s < SB; s++) memcpy(pot->hbox.p + s * 9, boxes[s], 9 * sizeof(double));
   if (!box_changed) box_changed = memcmp(pot->last_boxes.data(), pot->hbox.p, SB * 9 * sizeof(double)) != 0;
   if (box_changed) pot->last_boxes.assign(pot->hbox.p, pot->hbox.p + SB * 9);
-  if (direct_in)  // straight from the caller's page-locked block, re-pitched to the 16-byte aligned device rows
-    CU_TRY(pot, cudaMemcpy2DAsync(pot->dR.p, strideR * sizeof(double), positions[0], D * sizeof(double), D * sizeof(double),
-                                  static_cast<size_t>(S), cudaMemcpyHostToDevice, pot->stream));
-  else
-    CU_TRY(pot, cudaMemcpyAsync(pot->dR.p, pot->hR.p, S * strideR * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
-  CU_TRY(pot, cudaMemcpyAsync(pot->dZ.p, pot->hZ.p, SZ * N * sizeof(int), cudaMemcpyHostToDevice, pot->stream));
-  CU_TRY(pot, cudaMemcpyAsync(pot->dbox.p, pot->hbox.p, SB * 9 * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  if (z_changed) {
+    CU_TRY(pot, cudaMemcpyAsync(pot->dZ.p, pot->hZ.p, SZ * N * sizeof(int), cudaMemcpyHostToDevice, pot->stream));
+    pot->z_cached_S = SZ;
+    pot->z_cached_N = N;
+  }
+  if (box_changed)
+    CU_TRY(pot, cudaMemcpyAsync(pot->dbox.p, pot->hbox.p, SB * 9 * sizeof(double), cudaMemcpyHostToDevice, pot->stream));
+  // positions of systems [s0, s1) up / forces and energies down, on the given stream
+  auto copy_in = [&](long s0, long s1, cudaStream_t st) -> int {
+    const size_t n = static_cast<size_t>(s1 - s0);
+    if (direct_in) {  // straight from the caller's page-locked block, re-pitched to the 16-byte aligned device rows
+      CU_TRY(pot, cudaMemcpy2DAsync(pot->dR.p + s0 * strideR, strideR * sizeof(double), positions[s0], D * sizeof(double),
+                                    D * sizeof(double), n, cudaMemcpyHostToDevice, st));
+    } else {
+      for (long s = s0; s < s1; s++) {
+        memcpy(pot->hR.p + s * strideR, positions[s], D * sizeof(double));
+        if (strideR > D) pot->hR.p[s * strideR + D] = 0.0;
+      }
+      CU_TRY(pot, cudaMemcpyAsync(pot->dR.p + s0 * strideR, pot->hR.p + s0 * strideR, n * strideR * sizeof(double),
+                                  cudaMemcpyHostToDevice, st));
+    }
+    return 0;
+  };
+  auto copy_out = [&](long s0, long s1, cudaStream_t st) -> int {
+    const size_t n = static_cast<size_t>(s1 - s0);
+    if (direct_out)
+      CU_TRY(pot, cudaMemcpy2DAsync(forces[s0], D * sizeof(double), pot->dF.p + s0 * strideR, strideR * sizeof(double),
+                                    D * sizeof(double), n, cudaMemcpyDeviceToHost, st));
+    else
+      CU_TRY(pot, cudaMemcpyAsync(pot->hF.p + s0 * strideR, pot->dF.p + s0 * strideR, n * strideR * sizeof(double),
+                                  cudaMemcpyDeviceToHost, st));
+    CU_TRY(pot, cudaMemcpyAsync(pot->hU.p + s0, pot->dU.p + s0, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return 0;
+  };
+  // Large batches go through in chunks: the copy of chunk c + 1 overlaps the kernel of chunk c and the read-back of
+  // chunk c - 1 (the serial H2D -> kernel -> D2H of one big launch left the PCIe link idle two thirds of the call).
+  BatchPipe pipe;
+  pipe.chunks = 1;
+#ifndef EONB200_EMU
+  {
+    static const int forced = getenv("EONB200_PIPE_CHUNKS") ? atoi(getenv("EONB200_PIPE_CHUNKS")) : 0;  // development aid
+    const size_t bytes = static_cast<size_t>(S) * D * sizeof(double);
+    if (forced > 0)
+      pipe.chunks = std::min<long>(std::min(forced, kPipeMax), S);
+    else if (S >= 64 && bytes >= (512u << 10))
+      pipe.chunks = static_cast<int>(std::min<long>(kPipeMax, std::max<long>(2, S / 64)));
+  }
+#endif
+  pipe.in = copy_in;
+  pipe.out = copy_out;
+  if (pipe.chunks == 1) {
+    const int rc0 = copy_in(0, S, pot->stream);
+    if (rc0) return rc0;
+  }
   ForceBatchArgs a;
   memset(&a, 0, sizeof(a));
   a.S = static_cast<int>(S);
@@ -1167,22 +1311,25 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   a.F = pot->dF.p;
   a.U = pot->dU.p;
   a.force_rebuild = box_changed ? 1 : 0;
-  auto readback = [&]() -> int {
-    if (direct_out)
-      CU_TRY(pot, cudaMemcpy2DAsync(forces[0], D * sizeof(double), pot->dF.p, strideR * sizeof(double), D * sizeof(double),
-                                    static_cast<size_t>(S), cudaMemcpyDeviceToHost, pot->stream));
-    else
-      CU_TRY(pot, cudaMemcpyAsync(pot->hF.p, pot->dF.p, S * strideR * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
-    CU_TRY(pot, cudaMemcpyAsync(pot->hU.p, pot->dU.p, S * sizeof(double), cudaMemcpyDeviceToHost, pot->stream));
-    return 0;
-  };
-  int rc = run_force_batch(pot, pot->nl, a, pot->hbox.p, true, readback);
+  auto readback = [&]() -> int { return copy_out(0, S, pot->stream); };
+  lap("staged");
+  int rc = run_force_batch(pot, pot->nl, a, pot->hbox.p, true, readback, &pipe);
   if (rc) return rc;
-  for (long s = 0; s < S; s++) {
-    if (!direct_out) memcpy(forces[s], pot->hF.p + s * strideR, D * sizeof(double));
-    energies[s] = pot->hU.p[s];
-    if (variances) variances[s] = 0.0;
+  lap("ran");
+  const int nc = pipe.chunks;
+  for (int c = 0; c < nc; c++) {
+    const long s0 = S * c / nc, s1 = S * (c + 1) / nc;
+    if (s1 <= s0) continue;
+#ifndef EONB200_EMU
+    if (nc > 1) CU_TRY(pot, cudaEventSynchronize(pot->ev_out[c]));  // chunk c is back; later chunks still in flight
+#endif
+    for (long s = s0; s < s1; s++) {
+      if (!direct_out) memcpy(forces[s], pot->hF.p + s * strideR, D * sizeof(double));
+      energies[s] = pot->hU.p[s];
+      if (variances) variances[s] = 0.0;
+    }
   }
+  lap("unpacked");
   return 0;
 }
 
@@ -1441,6 +1588,11 @@ void eonb200_walkers_destroy(EonB200Walkers *w) {
   if (!w) return;
   cudaSetDevice(w->pot->device);
   cudaStreamSynchronize(w->pot->stream);
+  for (size_t g = 0; g < w->g_stream.size(); g++) {
+    cudaStreamSynchronize(w->g_stream[g]);
+    cudaEventDestroy(w->g_done[g]);
+    cudaStreamDestroy(w->g_stream[g]);
+  }
   delete w;
 }
 
@@ -1497,7 +1649,10 @@ int walkers_workspace(EonB200Walkers *w, const EonB200SearchParams *prm) {
   return 0;
 }
 
-int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, int remove_net_force, double scalar) {
+// group < 0: all walkers (or the slice [first, first + count)) on the handle's stream, synchronous, with the row-capacity
+// check; group >= 0: the slice on that group's stream, asynchronous (rows must have been sized before).
+int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, int remove_net_force, double scalar,
+                   long first = 0, long count = -1, int group = -1) {
   EonB200Pot *pot = w->pot;
   CU_TRY(pot, cudaSetDevice(pot->device));
   EonB200SearchParams local;
@@ -1513,8 +1668,11 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
     return fail(pot, 2, "dimer rotations_max above the supported %d for the lbfgs rotation", kMaxRotHistory - 1);
   int rc = walkers_workspace(w, job == 0 ? nullptr : prm);
   if (rc) return rc;
-  CU_TRY(pot, cudaMemcpyAsync(w->prm.p, prm, sizeof(*prm), cudaMemcpyHostToDevice, pot->stream));
+  cudaStream_t st = group >= 0 ? w->g_stream[group] : pot->stream;
+  CU_TRY(pot, cudaMemcpyAsync(w->prm.p, prm, sizeof(*prm), cudaMemcpyHostToDevice, st));
   const long W = w->W, N = w->N;
+  if (count < 0) count = W - first;
+  if (first < 0 || count <= 0 || first + count > W) return fail(pot, 2, "walkers: slice [%ld, %ld) outside 0..%ld", first, first + count, W);
   if (w->nl.S < W || w->nl.N != N || w->nl.K == 0) {
     rc = nl_alloc(pot, w->nl, W, N, std::max(w->nl.K, guess_K(pot->hp.rc_list, N, w->h_box.data())));
     if (rc) return rc;
@@ -1525,6 +1683,8 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
   wl.job = job;
   wl.remove_net_force = remove_net_force;
   wl.scalar = scalar;
+  wl.first = static_cast<int>(first);
+  wl.active = w->use_active ? w->active.p : nullptr;
   const int threads = pick_threads(pot, N, wl.lpa);
   size_t smem;
   rc = check_smem(pot, N, wl.maxCells, &smem);
@@ -1569,19 +1729,25 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
   wa.convergence = w->conv.p;
   // a job that may move atoms needs head-room in the rows: probe the fill with a force-only pass first
   for (int attempt = 0; attempt < 6; attempt++) {
-    CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
-    CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
+    if (group < 0) {
+      CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), st));
+      CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
+    }
     NlBatch view = nl_view(pot, w->nl);
-    CU_TRY(pot, cudaEventRecord(pot->ev[0], pot->stream));
+    if (group < 0) CU_TRY(pot, cudaEventRecord(pot->ev[0], st));
 #ifndef EONB200_EMU
     if (threads <= 448 && 2 * (smem + 17 * 1024) <= 220 * 1024 && W > pot->sm_count)
-      EONB200_LAUNCH(k_walkers_x2, static_cast<unsigned>(W), threads, smem, pot->stream, pot->dP.p, view, wa, wl, w->prm.p);
+      EONB200_LAUNCH(k_walkers_x2, static_cast<unsigned>(count), threads, smem, st, pot->dP.p, view, wa, wl, w->prm.p);
     else
 #endif
-      EONB200_LAUNCH(k_walkers, static_cast<unsigned>(W), threads, smem, pot->stream, pot->dP.p, view, wa, wl, w->prm.p);
-    CU_TRY(pot, cudaEventRecord(pot->ev[2], pot->stream));
+      EONB200_LAUNCH(k_walkers, static_cast<unsigned>(count), threads, smem, st, pot->dP.p, view, wa, wl, w->prm.p);
     pot->launches += 1;
     CU_TRY(pot, cudaGetLastError());
+    if (group >= 0) {  // asynchronous: the caller polls the group's event and harvests the slice
+      CU_TRY(pot, cudaEventRecord(w->g_done[group], st));
+      return 0;
+    }
+    CU_TRY(pot, cudaEventRecord(pot->ev[2], pot->stream));
     CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
     CU_TRY(pot, cudaMemcpyAsync(pot->h_stats.p, pot->d_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                 pot->stream));
@@ -1599,9 +1765,12 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
     if ((job != 0 && job != 4) || need <= w->nl.K) {
       // count the force calls the walkers made
       if (job != 3 && job != 4) {
-        std::vector<long long> fc(W);
-        CU_TRY(pot, cudaMemcpy(fc.data(), w->fcalls.p, sizeof(long long) * W, cudaMemcpyDeviceToHost));
-        for (long long v : fc) pot->force_calls += static_cast<unsigned long long>(v);
+        std::vector<long long> fc(count);
+        std::vector<int> act(count, 1);
+        CU_TRY(pot, cudaMemcpy(fc.data(), w->fcalls.p + first, sizeof(long long) * count, cudaMemcpyDeviceToHost));
+        if (w->use_active) CU_TRY(pot, cudaMemcpy(act.data(), w->active.p + first, sizeof(int) * count, cudaMemcpyDeviceToHost));
+        for (long k = 0; k < count; k++)
+          if (act[k]) pot->force_calls += static_cast<unsigned long long>(fc[k]);
       }
       return 0;
     }
@@ -1697,6 +1866,130 @@ int eonb200_walkers_harvest(EonB200Walkers *w, int *status, long *iterations, lo
   if (modes)
     CU_TRY(pot, cudaMemcpy2D(modes, w->D * sizeof(double), w->mode.p, w->Dp * sizeof(double), w->D * sizeof(double), W,
                              cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int eonb200_walkers_set_active(EonB200Walkers *w, const int *active) {
+  if (!w) return 1;
+  EonB200Pot *pot = w->pot;
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  w->use_active = active != nullptr;
+  if (active) {
+    CU_TRY(pot, w->active.reserve(static_cast<size_t>(w->W)));
+    CU_TRY(pot, cudaMemcpy(w->active.p, active, sizeof(int) * w->W, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+
+int eonb200_walkers_groups(EonB200Walkers *w, int nGroups) {
+  if (!w) return 1;
+  EonB200Pot *pot = w->pot;
+  if (nGroups < 1 || nGroups > 64) return fail(pot, 2, "walkers_groups: 1..64 groups");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  int rc = walkers_size_rows(w);  // asynchronous jobs cannot regrow the neighbour rows: size them now
+  if (rc) return rc;
+  while (static_cast<int>(w->g_stream.size()) < nGroups) {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr;
+#ifdef EONB200_EMU
+    CU_TRY(pot, cudaStreamCreate(&st));
+    CU_TRY(pot, cudaEventCreate(&ev));
+#else
+    CU_TRY(pot, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU_TRY(pot, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+#endif
+    w->g_stream.push_back(st);
+    w->g_done.push_back(ev);
+    w->g_range.push_back({0, 0});
+  }
+  return 0;
+}
+
+int eonb200_walkers_submit(EonB200Walkers *w, int group, int job, const EonB200SearchParams *prm, long first, long count,
+                           const double *positions, const double *modes, const double *reactant_energies) {
+  if (!w || !prm) return 1;
+  EonB200Pot *pot = w->pot;
+  if (group < 0 || group >= static_cast<int>(w->g_stream.size())) return fail(pot, 2, "walkers_submit: no such group");
+  if (job != 1 && job != 2) return fail(pot, 2, "walkers_submit: job must be 1 (saddle search) or 2 (relax)");
+  if (first < 0 || count <= 0 || first + count > w->W) return fail(pot, 2, "walkers_submit: slice outside the walkers");
+  if (w->g_range[group][1] != 0) return fail(pot, 2, "walkers_submit: group %d still has a job in flight", group);
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  cudaStream_t st = w->g_stream[group];
+  const size_t D = w->D, Dp = w->Dp;
+  if (positions) {
+    CU_TRY(pot, cudaMemcpy2DAsync(w->pos.p + first * Dp, Dp * sizeof(double), positions, D * sizeof(double),
+                                  D * sizeof(double), count, cudaMemcpyHostToDevice, st));
+    std::vector<int> ones(count, 1);
+    CU_TRY(pot, cudaMemcpyAsync(w->dirty.p + first, ones.data(), sizeof(int) * count, cudaMemcpyHostToDevice, st));
+    CU_TRY(pot, cudaStreamSynchronize(st));  // (ones is a stack object; the copies are a few KB)
+  }
+  if (modes) {
+    CU_TRY(pot, cudaMemcpy2DAsync(w->mode.p + first * Dp, Dp * sizeof(double), modes, D * sizeof(double), D * sizeof(double),
+                                  count, cudaMemcpyHostToDevice, st));
+    w->have_modes = true;
+  }
+  if (job == 1 && !w->have_modes) return fail(pot, 2, "walkers_submit: no initial modes uploaded");
+  if (reactant_energies)
+    CU_TRY(pot, cudaMemcpyAsync(w->react.p + first, reactant_energies, sizeof(double) * count, cudaMemcpyHostToDevice, st));
+  else if (job == 1)
+    CU_TRY(pot, cudaMemsetAsync(w->react.p + first, 0, sizeof(double) * count, st));
+  const int rc = walkers_launch(w, job, prm, prm->remove_net_force, 0.0, first, count, group);
+  if (rc) return rc;
+  w->g_range[group] = {first, count};
+  return 0;
+}
+
+int eonb200_walkers_poll(EonB200Walkers *w, int group, int wait) {
+  if (!w) return -1;
+  EonB200Pot *pot = w->pot;
+  if (group < 0 || group >= static_cast<int>(w->g_stream.size())) return -1;
+  if (w->g_range[group][1] == 0) return 1;  // idle
+#ifdef EONB200_EMU
+  (void)wait;
+  return 1;  // the emulation runs jobs to completion inside submit
+#else
+  cudaSetDevice(pot->device);
+  if (wait) return cudaEventSynchronize(w->g_done[group]) == cudaSuccess ? 1 : -1;
+  const cudaError_t e = cudaEventQuery(w->g_done[group]);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) return 0;
+  cudaGetLastError();
+  return -1;
+#endif
+}
+
+int eonb200_walkers_harvest_group(EonB200Walkers *w, int group, int *status, long *iterations, long *force_calls,
+                                  double *energies, double *eigenvalues, double *convergence, double *positions,
+                                  double *modes) {
+  if (!w) return 1;
+  EonB200Pot *pot = w->pot;
+  if (group < 0 || group >= static_cast<int>(w->g_stream.size())) return fail(pot, 2, "walkers_harvest_group: no such group");
+  const long first = w->g_range[group][0], n = w->g_range[group][1];
+  if (n == 0) return fail(pot, 2, "walkers_harvest_group: group %d is idle", group);
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  cudaStream_t st = w->g_stream[group];
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  const size_t D = w->D, Dp = w->Dp;
+  std::vector<long long> it(n), fc(n);
+  if (status) CU_TRY(pot, cudaMemcpyAsync(status, w->status.p + first, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaMemcpyAsync(it.data(), w->iters.p + first, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaMemcpyAsync(fc.data(), w->fcalls.p + first, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+  if (energies) CU_TRY(pot, cudaMemcpyAsync(energies, w->energy.p + first, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (eigenvalues) CU_TRY(pot, cudaMemcpyAsync(eigenvalues, w->eig.p + first, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (convergence) CU_TRY(pot, cudaMemcpyAsync(convergence, w->conv.p + first, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (positions)
+    CU_TRY(pot, cudaMemcpy2DAsync(positions, D * sizeof(double), w->pos.p + first * Dp, Dp * sizeof(double),
+                                  D * sizeof(double), n, cudaMemcpyDeviceToHost, st));
+  if (modes)
+    CU_TRY(pot, cudaMemcpy2DAsync(modes, D * sizeof(double), w->mode.p + first * Dp, Dp * sizeof(double), D * sizeof(double),
+                                  n, cudaMemcpyDeviceToHost, st));
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  for (long k = 0; k < n; k++) {
+    if (iterations) iterations[k] = static_cast<long>(it[k]);
+    if (force_calls) force_calls[k] = static_cast<long>(fc[k]);
+    pot->force_calls += static_cast<unsigned long long>(fc[k]);
+  }
+  w->g_range[group] = {0, 0};
   return 0;
 }
 

@@ -655,6 +655,8 @@ struct WalkerLaunch {
   int job;  // 0 = Matter forces only, 1 = saddle search, 2 = relax, 3 = displace along mode, 4 = list probe
   int remove_net_force;
   double scalar;  // displacement for job 3
+  int first;      // walker of CTA 0: a launch may cover the slice [first, first + gridDim.x) of the handle's walkers
+  const int *active;  // [W] 0 = leave this walker alone (null: all active)
 };
 
 __device__ inline void setup_ctx(Ctx &c, const PotParams *Pp, const NlBatch &nl, const WalkerArrays &wa,
@@ -694,8 +696,8 @@ __device__ __forceinline__ void walkers_body(const PotParams *__restrict__ Pp, c
   EONB200_DYN_SMEM(smem_raw);
   __shared__ EonB200SearchParams prm_sh;
   __shared__ double cell_sh[19];
-  const int w = blockIdx.x;
-  if (w >= wa.W) return;
+  const int w = blockIdx.x + wl.first;
+  if (w >= wa.W || (wl.active && wl.active[w] == 0)) return;
   Smem sm = carve_smem(smem_raw, wa.N, wl.maxCells, wl.fast_smem != 0);
   if (threadIdx.x == 0) {
     mbar_init(sm.mbar, 1);

@@ -183,6 +183,42 @@ __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, con
   return v;
 }
 
+// The same store seen from system s0 on (a launch over a chunk of the batch): every per-system array moves by s0
+// strides -- the strides of make_sys.
+__host__ __device__ inline void offset_systems(NlBatch &nl, int N, long s0) {
+  const size_t s = static_cast<size_t>(s0);
+  const size_t kn = s * nl.K * nl.Np;
+#define EONB200_OFF(field, stride) \
+  if (nl.field) nl.field += s * (stride)
+  nl.nbr += kn;
+  nl.cnt += s * nl.Np;
+  nl.rbuild += s * 3 * N;
+  nl.state += s;
+  EONB200_OFF(box_build, 9);
+  if (nl.pairA) nl.pairA += kn;
+  if (nl.pairB) nl.pairB += kn;
+  if (nl.nbr2) nl.nbr2 += kn;
+  EONB200_OFF(cnt2, nl.Np);
+  EONB200_OFF(cls, nl.Np);
+  EONB200_OFF(cellscratch, nl.scratch_stride);
+  EONB200_OFF(pos4, nl.Np);
+  EONB200_OFF(dfd, nl.Np);
+  EONB200_OFF(rowid, nl.Np);
+  EONB200_OFF(flags, 1);
+  EONB200_OFF(upart, kMaxTiles * 4);
+  EONB200_OFF(done, 1);
+  if (nl.own_cs) nl.own_cs += kn;
+  if (nl.recv_code) nl.recv_code += kn;
+  if (nl.own_ab) nl.own_ab += kn;
+  EONB200_OFF(lhdr, nl.Np * 2);
+  EONB200_OFF(roff, 2 * nl.Np + 1);
+  EONB200_OFF(lane_atom, nl.Np);
+  EONB200_OFF(atom_lane, nl.Np);
+  EONB200_OFF(hl_hdr, 8);
+  EONB200_OFF(lo_build, 4);
+#undef EONB200_OFF
+}
+
 // Cell geometry of one system, computed by thread 0 of the CTA from the box.
 struct Geom {
   double H[9];

@@ -87,18 +87,33 @@ private:
   std::mutex m_mu;
 };
 
-// eonc::Potential for PotType::{LJ, LJCLUSTER, MORSE_PT, EAM_AL}, evaluated on a B200.
+// What a [Potential] section may set beyond the potential's name (INTEGRATION.md lists the config keys).
+struct B200Options {
+  int device = 0;
+  bool pinHostBuffers = false;   // page-lock the caller's position / force blocks on first use (EonB200Config)
+  bool eamConservative = false;  // in-tree EAM with F = -grad U instead of the sign of EAM.cpp:203-215
+  double skin = -1.0;            // Verlet skin of the cached lists; < 0 keeps the library default
+  double cutoff = -1.0;          // LJ / Morse cutoff; < 0 keeps the default
+  std::string library;           // path of libeonb200.so; empty: EONB200_LIBRARY or the loader path
+};
+
+// eonc::Potential for PotType::{LJ, LJCLUSTER, MORSE_PT} and the in-tree EAM class, evaluated on a B200.
 class B200Potential : public Potential {
 public:
   // `kind` is an EONB200_POT_* value; `ptype` the reference tag the instance reports through
   // getType() / PotRegistry (include/eon/BaseStructures.h:36-71).
   B200Potential(PotType ptype, int kind, int device = 0, const std::string &library = std::string())
-      : Potential(ptype) {
+      : B200Potential(ptype, kind, with(device, library)) {}
+  B200Potential(PotType ptype, int kind, const B200Options &opt) : Potential(ptype) {
     auto &l = B200Loader::instance();
-    l.require_loaded(library);
+    l.require_loaded(opt.library);
     EonB200Config cfg;
     l.config_default(&cfg, kind);
-    cfg.device = device;
+    cfg.device = opt.device;
+    cfg.pin_host_buffers = opt.pinHostBuffers ? 1 : 0;
+    cfg.eam_conservative = opt.eamConservative ? 1 : 0;
+    if (opt.skin >= 0.0) cfg.skin = opt.skin;
+    if (opt.cutoff > 0.0) cfg.cutoff = opt.cutoff;
     std::array<char, 1024> err{};
     m_handle = l.create(&cfg, err.data(), err.size());
     if (!m_handle) throw std::runtime_error(std::string("B200Potential: create failed: ") + err.data());
@@ -169,6 +184,12 @@ public:
   [[nodiscard]] EonB200Pot *handle() const noexcept { return m_handle; }
 
 private:
+  static B200Options with(int device, const std::string &library) {
+    B200Options o;
+    o.device = device;
+    o.library = library;
+    return o;
+  }
   void check(int rc) {
     if (rc == 0) return;
     if (rc == 14324) throw 14324;  // client/potentials/EAM/EAM.cpp:116-123

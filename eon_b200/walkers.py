@@ -135,6 +135,89 @@ class Walkers:
         return Harvest(st, it, fc, E, ev, cv, R.reshape(W, N, 3) if geometry else None,
                        M.reshape(W, N, 3) if geometry else None)
 
+    def set_active(self, active=None):
+        """Mask for the following launches: walkers with active == 0 are left alone (``None``: all take part)."""
+        if active is None:
+            self._check(self._lib.eonb200_walkers_set_active(self._h, None))
+        else:
+            a = np.ascontiguousarray(np.asarray(active).astype(np.int32).reshape(self.W))
+            self._check(self._lib.eonb200_walkers_set_active(self._h, _ip(a)))
+
+    # ---- streaming: a queue of searches through the handle's W slots ------------------------------------------
+    def stream_search(self, prm: _capi.SearchParams, positions, modes, reactant_energies=None, groups: int = 32,
+                      geometry: bool = True, job: int = 1) -> Harvest:
+        """Run Q >= 1 searches (job 1) or relaxations (job 2) through the W slots of this handle, Q arbitrary.
+
+        The slots are split into `groups` slices with a stream each; every slice is refilled from the queue as soon as
+        its walkers are done, the way eon/communicator.py:525-559 hands the next job to a free core, so a walker that
+        runs into ``max_iterations`` only holds up its own slice.  Results come back in queue order."""
+        R = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3 * self.N)
+        Q = R.shape[0]
+        M = None if modes is None else np.ascontiguousarray(modes, dtype=np.float64).reshape(Q, 3 * self.N)
+        E0 = None
+        if reactant_energies is not None:
+            E0 = np.ascontiguousarray(np.broadcast_to(np.asarray(reactant_energies, dtype=np.float64), (Q,)))
+        G = max(1, min(int(groups), self.W, 64))
+        self._check(self._lib.eonb200_walkers_groups(self._h, G))
+        bounds = [self.W * g // G for g in range(G + 1)]
+        out = Harvest(np.zeros(Q, np.int32), np.zeros(Q, np.int64), np.zeros(Q, np.int64), np.zeros(Q), np.zeros(Q),
+                      np.zeros(Q), np.zeros((Q, 3 * self.N)) if geometry else None,
+                      np.zeros((Q, 3 * self.N)) if geometry else None)
+        lp = C.POINTER(C.c_long)
+        nxt = 0
+        inflight = {}  # group -> (queue start, count)
+
+        def submit(g):
+            nonlocal nxt
+            cap = bounds[g + 1] - bounds[g]
+            n = min(cap, Q - nxt)
+            if n <= 0:
+                return
+            q0 = nxt
+            nxt += n
+            self._check(self._lib.eonb200_walkers_submit(
+                self._h, g, job, C.byref(prm), bounds[g], n, _dp(R[q0:q0 + n]),
+                _dp(M[q0:q0 + n]) if M is not None else None, _dp(E0[q0:q0 + n]) if E0 is not None else None))
+            inflight[g] = (q0, n)
+
+        def harvest(g):
+            q0, n = inflight.pop(g)
+            it = np.zeros(n, np.int64)
+            fc = np.zeros(n, np.int64)
+            st = np.zeros(n, np.int32)
+            E, ev, cv = np.zeros(n), np.zeros(n), np.zeros(n)
+            P = np.zeros((n, 3 * self.N)) if geometry else None
+            Mo = np.zeros((n, 3 * self.N)) if geometry else None
+            self._check(self._lib.eonb200_walkers_harvest_group(
+                self._h, g, _ip(st), it.ctypes.data_as(lp), fc.ctypes.data_as(lp), _dp(E), _dp(ev), _dp(cv),
+                _dp(P) if geometry else None, _dp(Mo) if geometry else None))
+            sl = slice(q0, q0 + n)
+            out.status[sl], out.iterations[sl], out.force_calls[sl] = st, it, fc
+            out.energies[sl], out.eigenvalues[sl], out.convergence[sl] = E, ev, cv
+            if geometry:
+                out.positions[sl], out.modes[sl] = P, Mo
+
+        for g in range(G):
+            submit(g)
+        while inflight:
+            progressed = False
+            for g in list(inflight):
+                state = self._lib.eonb200_walkers_poll(self._h, g, 0)
+                if state < 0:
+                    raise PotentialError(100, "walkers_poll failed")
+                if state == 1:
+                    harvest(g)
+                    submit(g)
+                    progressed = True
+            if not progressed:  # nothing finished: block on the oldest group instead of spinning
+                g = next(iter(inflight))
+                if self._lib.eonb200_walkers_poll(self._h, g, 1) < 0:
+                    raise PotentialError(100, "walkers_poll failed")
+        if geometry:
+            out.positions = out.positions.reshape(Q, self.N, 3)
+            out.modes = out.modes.reshape(Q, self.N, 3)
+        return out
+
     @property
     def last_ms(self) -> float:
         return float(self._lib.eonb200_walkers_last_ms(self._h))
@@ -146,10 +229,24 @@ class Walkers:
         self.saddle_search(prm, reactant_energies)
         saddle = self.harvest()
         out = {"saddle": saddle}
-        for name, sign in (("min1", -1.0), ("min2", +1.0)):  # ProcessSearchJob.cpp:190-202: min1 = saddle - offset * mode
-            self.set(positions=saddle.positions, modes=saddle.modes)
-            self.displace_along_mode(sign * offset)
-            self.relax(prm)
-            out[name] = self.harvest()
+        # ProcessSearchJob.cpp:184-186 returns right after a failed saddle search: those walkers sit out the two
+        # minimisations (no force calls, and no relaxation from a failed geometry)
+        good = saddle.status == STATUS_GOOD
+        self.set_active(good)
+        try:
+            for name, sign in (("min1", -1.0), ("min2", +1.0)):  # ProcessSearchJob.cpp:190-202: min1 = saddle - offset * mode
+                self.set(positions=saddle.positions, modes=saddle.modes)
+                if good.any():
+                    self.displace_along_mode(sign * offset)
+                    self.relax(prm)
+                h = self.harvest()
+                bad = ~good
+                h.status[bad] = 1
+                h.iterations[bad] = 0
+                h.force_calls[bad] = 0
+                h.energies[bad] = np.nan
+                out[name] = h
+        finally:
+            self.set_active(None)
         self.set(positions=saddle.positions, modes=saddle.modes)
         return out

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONB200_ABI_VERSION 4
+#define EONB200_ABI_VERSION 5
 
 #if defined(_WIN32)
 #define EONB200_API __declspec(dllexport)
@@ -224,6 +224,32 @@ EONB200_API int eonb200_walkers_displace_along_mode(EonB200Walkers *w, double si
 EONB200_API int eonb200_walkers_harvest(EonB200Walkers *w, int *status, long *iterations, long *force_calls,
                                         double *energies, double *eigenvalues, double *convergence,
                                         double *positions, double *modes);
+
+/* Which walkers take part in the following saddle_search / relax / displace launches: active [W], 0 = leave the walker
+ * alone (its slot keeps its last results).  NULL: all.  ProcessSearchJob returns right after a failed saddle search
+ * (client/ProcessSearchJob.cpp:184-186): the batched tail masks those walkers out of the two minimisations. */
+EONB200_API int eonb200_walkers_set_active(EonB200Walkers *w, const int *active);
+
+/* ---- streaming: keep every slot busy -------------------------------------------------------------------------------
+ * The reference keeps its cores busy by handing out the next search as soon as one returns
+ * (eon/communicator.py:525-559).  Here the W slots of a handle are worked in groups: every group has its own stream,
+ * a job on a slice of slots is submitted without waiting, and a finished group is harvested and refilled while the
+ * others keep running -- a walker that runs into max_iterations only holds up its own group.
+ *   groups(n)        create n group streams (1..64) and size the neighbour rows (asynchronous jobs cannot regrow them)
+ *   submit(g, job, prm, first, count, positions, modes, reactant_energies)
+ *                    upload the inputs of slots [first, first + count) ([count][3N], [count]; positions / modes may be
+ *                    NULL to keep what the slots hold) and start job 1 (saddle search) or 2 (relax) on them; every job
+ *                    in flight must use the same prm
+ *   poll(g, wait)    1 = done or idle, 0 = still running, -1 = error; wait != 0 blocks until done
+ *   harvest_group(g, ...)  outputs of the group's slice, sized [count] / [count][3N] like harvest; frees the group */
+EONB200_API int eonb200_walkers_groups(EonB200Walkers *w, int nGroups);
+EONB200_API int eonb200_walkers_submit(EonB200Walkers *w, int group, int job, const EonB200SearchParams *prm, long first,
+                                       long count, const double *positions, const double *modes,
+                                       const double *reactant_energies);
+EONB200_API int eonb200_walkers_poll(EonB200Walkers *w, int group, int wait);
+EONB200_API int eonb200_walkers_harvest_group(EonB200Walkers *w, int group, int *status, long *iterations,
+                                              long *force_calls, double *energies, double *eigenvalues,
+                                              double *convergence, double *positions, double *modes);
 
 /* Device time in milliseconds of the last walkers_* launch sequence (CUDA events on the
  * handle's stream), for the measurement harness. */

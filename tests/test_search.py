@@ -332,3 +332,44 @@ def test_c1_lj13_dimer_search(backend, oracle):
             assert h.status[0] == ref.status == 5  # SaddleSearchTest.cpp:110-111: not GOOD
             assert h.iterations[0] == ref.iterations and h.force_calls[0] == ref.force_calls
             assert abs(h.energies[0] - ref.energy) < 1e-6 and np.abs(h.positions[0] - Rref).max() < 1e-6
+
+
+def test_streamed_searches_equal_one_launch(backend, oracle):
+    """Seven searches fed through three slots in two groups (refilled as groups finish) give exactly what one launch
+    over seven walkers gives, in queue order; masked-out walkers are left alone by a relax launch."""
+    d = oracle.load_fixture("morse_pt_saddle.json")
+    Z, box, fixed = d["atomic_nrs"], d["cell"], d["fixed"]
+    Q = 7
+    rng = np.random.default_rng(3)
+    free = (1 - fixed).reshape(1, -1, 3)
+    R = d["displacement_positions"][None] + rng.normal(0.0, 0.02, (Q,) + d["positions"].shape) * free
+    M = d["direction"][None] + rng.normal(0.0, 0.05, (Q,) + d["positions"].shape) * free
+    M /= np.linalg.norm(M.reshape(Q, -1), axis=1).reshape(Q, 1, 1)
+    prm = search_params(lib=backend, opt_method=1)
+    opot = oracle.potential(oracle.POT_MORSE_PT)
+    E0, _ = oracle.force(opot, d["positions"], Z, box)
+    with B200Potential("morse_pt", lib=backend) as pot:
+        wk = Walkers(pot, Z, fixed, box, R.reshape(Q, -1), M.reshape(Q, -1))
+        wk.saddle_search(prm, E0)
+        ref = wk.harvest()
+        calls_one = pot.forceCallCounter
+        wk.close()
+    with B200Potential("morse_pt", lib=backend) as pot:
+        wk = Walkers(pot, Z, fixed, box, R[:3].reshape(3, -1), M[:3].reshape(3, -1))
+        h = wk.stream_search(prm, R.reshape(Q, -1), M.reshape(Q, -1), E0, groups=2)
+        assert np.array_equal(h.status, ref.status) and np.array_equal(h.force_calls, ref.force_calls)
+        assert np.array_equal(h.iterations, ref.iterations)
+        assert np.abs(h.energies - ref.energies).max() < 1e-12
+        assert np.abs(h.positions - ref.positions).max() < 1e-12 and np.abs(h.modes - ref.modes).max() < 1e-12
+        assert pot.forceCallCounter >= int(ref.force_calls.sum()) and pot.forceCallCounter <= calls_one + 3
+        # active mask: walker 1 sits a relaxation out
+        wk.set(positions=R[:3].reshape(3, -1))  # the displaced start geometries: well off any minimum
+        wk.matter_forces()
+        before = wk.harvest()
+        wk.set_active([1, 0, 1])
+        wk.relax(search_params(lib=backend, opt_method=1, opt_converged_force=1e-3))
+        after = wk.harvest()
+        wk.set_active(None)
+        assert np.array_equal(after.positions[1], before.positions[1]) and after.force_calls[1] == before.force_calls[1]
+        assert after.status[0] == 0 and after.status[2] == 0 and after.energies[0] < before.energies[0] - 0.01
+        wk.close()
