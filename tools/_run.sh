@@ -1,2 +1,1 @@
-EONB200_TRACE=1 python tools/e2e_bench.py steps=2 chunks=1,4 errlines=10 2>&1 | tail -70
-python tools/e2e_bench.py steps=50 chunks=1,2,4,8
+for c in 1 2 4; do EONB200_PIPE_CHUNKS=$c python tools/e2e_py.py steps=100 2>&1 | grep "pin 1"; done
