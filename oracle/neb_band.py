@@ -6,10 +6,12 @@ numpy restatement, image by image, of what ``NudgedElasticBand::updateForces`` d
 (client/NEBSpringForce.cpp:17-42,113-136), the projections (client/NEBProjection.cpp:17-45), ``computeDNEB``,
 ``climbingImageForce`` and ``zeroTranslation`` (client/NEBForceProjection.cpp:65-110).
 
-Parity pinning: the reference's NEB cannot be built here (needs eonclient); the restatement is
-pinned by the analytic properties the reference's own unit tests assert for these helpers (NEBTangentTest /
-NEBForceProjectionTest style: unit tangents, perpendicularity of the nudged force, climbing-image inversion, zero net
-translation) in tests/test_neb.py.
+Parity pinning: the reference's NEB cannot be built here (needs eonclient).  Every helper below
+is pinned by the hand-computed vectors of the reference's own unit tests, client/unit_tests/NEBSubsystemTest.cpp:47-353
+(tangent cases, forcePerp (0, 4, 0), climbingImageForce (-3, 4), computeDNEB switching 2/pi atan(1/4), zeroTranslation,
+uniform / weighted spring 8 t) and :376-477 (cubic extrema), reproduced in
+tests/test_neb.py::test_reference_neb_subsystem_vectors; `band_forces` is composed of exactly these helpers.  The band
+OPTIMISER's known answer (data/reference/neb_lj.dat) is not reproduced: see DESIGN.md section 8-2.
 """
 import numpy as np
 
@@ -66,6 +68,36 @@ def dneb(f_spring, t, f_perp):
     return np.zeros_like(t)
 
 
+def force_perp(f, t):
+    """client/NEBForceProjection.cpp forcePerp"""
+    return f - np.sum(f * t) * t
+
+
+def climbing_image_force(f, t, f_dneb=0.0):
+    """client/NEBForceProjection.cpp climbingImageForce: F - 2 (F.t) t + DNEB part"""
+    return f - 2.0 * np.sum(f * t) * t + f_dneb
+
+
+def zero_translation(f, n_free, n_atoms):
+    """client/NEBForceProjection.cpp zeroTranslation: only when every atom is free"""
+    return f - f.sum(axis=0) / n_atoms if n_free == n_atoms else f
+
+
+def uniform_spring_par(ksp, t, dist_next, dist_prev):
+    """client/NEBSpringForce.cpp:17-30"""
+    return ksp * (dist_next - dist_prev) * t
+
+
+def weighted_spring_par(k, i, t, dist_next, dist_prev):
+    """client/NEBSpringForce.cpp:32-42: (k[i] d_next - k[i - 1] d_prev) t, full spring force zero"""
+    return (k[i] * dist_next - k[i - 1] * dist_prev) * t
+
+
+def cubic(U1, U2, F1, F2):
+    """client/NEBSplineExtrema.cpp:105-108"""
+    return U1, -F1, 3.0 * (U2 - U1) + 2.0 * F1 + F2, -2.0 * (U2 - U1) - (F1 + F2)
+
+
 def band_forces(R, F, E, cell, n_free, ksp=5.0, climbing_image=False, old_tangent=False, projection=0,
                 energy_weighted=False, k_min=0.97, k_max=9.7):
     """One band: R, F [M + 2, N, 3]; E [M + 2].  Returns (projected [M, N, 3], tangents [M, N, 3], climbing image)."""
@@ -86,23 +118,22 @@ def band_forces(R, F, E, cell, n_free, ksp=5.0, climbing_image=False, old_tangen
         ln, lp = np.linalg.norm(dn), np.linalg.norm(dp)
         t = tangent(dn, dp, E[i], E[i - 1], E[i + 1], old_tangent)
         if energy_weighted:
-            f_par = (kk[i] * ln - kk[i - 1] * lp) * t
+            f_par = weighted_spring_par(kk, i, t, ln, lp)
             f_spring = np.zeros_like(t)
         else:
-            f_par = ksp * (ln - lp) * t
+            f_par = uniform_spring_par(ksp, t, ln, lp)
             f_spring = ksp * pbc(dn - dp, cell)
         f = F[i]
-        f_perp = f - np.sum(f * t) * t
+        f_perp = force_perp(f, t)
         if climbing_image and i == imax:
             extra = dneb(f_spring, t, f_perp) if projection == 1 else 0.0
-            out = f - 2.0 * np.sum(f * t) * t + extra
+            out = climbing_image_force(f, t, extra)
         elif projection == 2:
             out = f_spring + f
         elif projection == 1:
             out = f_par + f_perp + dneb(f_spring, t, f_perp)
         else:
             out = f_par + f_perp
-        if n_free == N:
-            out = out - out.sum(axis=0) / N
+        out = zero_translation(out, n_free, N)
         P[i - 1], T[i - 1] = out, t
     return P, T, (imax if climbing_image else 0)

@@ -6,7 +6,7 @@ import sys
 import numpy as np
 import pytest
 
-from eon_b200 import B200Potential, neb as NEB
+from eon_b200 import B200Potential, Walkers, neb as NEB, search_params
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
 import neb_band as ONEB  # noqa: E402
@@ -246,3 +246,126 @@ def test_cell_change_on_one_handle_invalidates_cached_lists(backend, oracle, kin
     assert np.abs(out["energies"] - ref["energies"]).max() <= 1e-9
     assert np.abs(out["projected"] - ref["projected"]).max() <= 1e-10 * max(1.0, np.abs(ref["projected"]).max())
     assert np.abs(U1 - U0).max() <= 1e-9 and np.abs(F1 - F0).max() <= 1e-10 * max(1.0, np.abs(F0).max())
+
+
+def _m3(*vals):
+    return np.array(vals, dtype=float).reshape(3, 3)
+
+
+def _device_image(backend, d_next, d_prev, e, e_prev, e_next, force, n_free=2, **kw):
+    """One movable image between two endpoints on the device: tangent and projected force of the middle image."""
+    cur = np.full((3, 3), 50.0) + np.arange(9).reshape(3, 3)  # far from the faces of a 100 A cell: no wrap
+    R = np.stack([cur - d_prev, cur, cur + d_next]).reshape(1, 3, 9)
+    F = np.zeros((1, 3, 9))
+    F[0, 1] = np.asarray(force, dtype=float).reshape(9)
+    E = np.array([[e_prev, e, e_next]], dtype=float)
+    with B200Potential("lj", lib=backend) as pot:
+        P, T, ci = NEB.neb_forces(pot, R, F, E, np.eye(3) * 100.0, n_free, **kw)
+    return P[0, 0].reshape(3, 3), T[0, 0].reshape(3, 3), int(ci[0])
+
+
+def test_reference_neb_subsystem_vectors(backend):
+    """Every hand-computed expectation of client/unit_tests/NEBSubsystemTest.cpp:47-353 (tangents, forcePerp,
+    climbingImageForce, computeDNEB, zeroTranslation, springs) and :376-477 (cubic extrema), against the numpy oracle's
+    helpers, the product's `spline_extrema`, and -- wherever a three-image band can express the case -- the device
+    kernel."""
+    nx = _m3(1, 0, 0, 1, 0, 0, 1, 0, 0)
+    # SimpleTangent (:47-74): normalised, along diffNext, blind to energies and diffPrev
+    t = ONEB.tangent(nx, -nx, 0.0, 0.0, 0.0, old_tangent=True)
+    assert np.linalg.norm(t) == pytest.approx(1.0, rel=1e-12) and (t * nx).sum() > 0
+    d2, d3 = _m3(0, 2, 0, 0, 2, 0, 0, 2, 0), _m3(-3, 0, 0, -3, 0, 0, -3, 0, 0)
+    assert np.allclose(ONEB.tangent(d2, d3, 1.0, 0.5, 2.0, True), ONEB.tangent(d2, d3, 5.0, 10.0, -3.0, True), atol=1e-12)
+    _, T, _ = _device_image(backend, d2, d3, 1.0, 0.5, 2.0, np.zeros(9), old_tangent=1)
+    assert np.allclose(T, d2 / np.linalg.norm(d2), atol=1e-12)
+    # ImprovedTangent (:78-151)
+    dn, dp = _m3(1, 0, 0, 0, 0, 0, 0, 0, 0), _m3(0, 1, 0, 0, 0, 0, 0, 0, 0)
+    for (e, ep, en), want in (((1.0, 0.0, 2.0), dn), ((1.0, 2.0, 0.0), dp), ((0.0, 3.0, 1.0), dn * 1.0 + dp * 3.0),
+                              ((5.0, 2.0, 1.0), dn * 3.0 + dp * 4.0)):
+        want = want / np.linalg.norm(want)
+        got = ONEB.tangent(dn, dp, e, ep, en)
+        assert np.linalg.norm(got) == pytest.approx(1.0, rel=1e-12) and np.allclose(got, want, atol=1e-10)
+        _, T, _ = _device_image(backend, dn, dp, e, ep, en, np.zeros(9))
+        assert np.allclose(T, want, atol=1e-10)
+    # forcePerp (:155-197)
+    tx = dn / np.linalg.norm(dn)
+    f34 = _m3(3, 4, 0, 0, 0, 0, 0, 0, 0)
+    fp = ONEB.force_perp(f34, tx)
+    assert abs((fp * tx).sum()) < 1e-12 and abs(fp[0, 0]) < 1e-12 and fp[0, 1] == pytest.approx(4.0)
+    assert np.linalg.norm(ONEB.force_perp(_m3(5, 0, 0, 0, 0, 0, 0, 0, 0), tx)) < 1e-12
+    f7 = _m3(0, 7, 0, 0, 0, 0, 0, 0, 0)
+    assert np.allclose(ONEB.force_perp(f7, tx), f7, atol=1e-12)
+    # device: equal spacing along x, rising energies -> tangent x, no parallel spring force: projected = forcePerp
+    P, T, _ = _device_image(backend, dn, dn, 1.0, 0.0, 2.0, f34)
+    assert np.allclose(T, tx, atol=1e-12) and np.allclose(P, _m3(0, 4, 0, 0, 0, 0, 0, 0, 0), atol=1e-12)
+    # climbingImageForce (:201-229): (3, 4) -> (-3, 4); with a DNEB part (0, 1): (3, 0) -> (-3, 1)
+    assert np.allclose(ONEB.climbing_image_force(f34, tx)[0], [-3.0, 4.0, 0.0])
+    assert np.allclose(ONEB.climbing_image_force(_m3(3, 0, 0, 0, 0, 0, 0, 0, 0), tx, _m3(0, 1, 0, 0, 0, 0, 0, 0, 0))[0],
+                       [-3.0, 1.0, 0.0])
+    P, _, ci = _device_image(backend, dn, dn, 1.0, 0.0, 2.0, f34, climbing_image=1)  # the only image climbs
+    assert ci == 1 and np.allclose(P[0], [-3.0, 4.0, 0.0], atol=1e-12)
+    # computeDNEB (:233-281)
+    assert np.linalg.norm(ONEB.dneb(_m3(0, 2, 0, 0, 0, 0, 0, 0, 0), tx, np.zeros((3, 3)))) < 1e-12
+    assert np.linalg.norm(ONEB.dneb(_m3(5, 0, 0, 0, 0, 0, 0, 0, 0), tx, _m3(0, 3, 0, 0, 0, 0, 0, 0, 0))) < 1e-12
+    dn3 = ONEB.dneb(_m3(0, 0, 2, 0, 0, 0, 0, 0, 0), tx, _m3(0, 1, 0, 0, 0, 0, 0, 0, 0))
+    assert dn3[0, 2] == pytest.approx(2.0 * (2.0 / np.pi * np.arctan(0.25)), rel=1e-10)
+    assert abs(dn3[0, 0]) < 1e-12 and abs(dn3[0, 1]) < 1e-12
+    # zeroTranslation (:285-309)
+    f369 = _m3(3, 6, 9, 1, 2, 3, 2, 4, 6)
+    assert np.allclose(ONEB.zero_translation(f369, 3, 3).sum(axis=0), 0.0, atol=1e-12)
+    assert np.array_equal(ONEB.zero_translation(f369, 2, 3), f369)
+    P3, _, _ = _device_image(backend, dn, dn, 1.0, 0.0, 2.0, f369, n_free=3)
+    P2, _, _ = _device_image(backend, dn, dn, 1.0, 0.0, 2.0, f369, n_free=2)
+    assert np.allclose(P3.sum(axis=0), 0.0, atol=1e-12)
+    assert np.allclose(P2, ONEB.force_perp(f369, tx), atol=1e-12)  # untouched beyond the projection
+    # UniformSpring (:313-345): ksp (dNext - dPrev) t
+    assert np.linalg.norm(ONEB.uniform_spring_par(5.0, tx, 1.0, 1.0)) < 1e-12
+    assert np.allclose(ONEB.uniform_spring_par(5.0, tx, 2.0, 1.0), 5.0 * tx, atol=1e-12)
+    P, _, _ = _device_image(backend, 2.0 * dn, dn, 1.0, 0.0, 2.0, np.zeros(9), spring_constant=5.0)
+    assert np.allclose(P, 5.0 * tx, atol=1e-12)
+    # WeightedSpring (:349-372): k = {2, 4, 6}, image 1, distances 3 and 2 -> 8 t
+    ty = dp / np.linalg.norm(dp)
+    assert np.allclose(ONEB.weighted_spring_par([2.0, 4.0, 6.0], 1, ty, 3.0, 2.0), 8.0 * ty, atol=1e-12)
+    # cubic extrema (:376-477)
+    a, b, c, d = ONEB.cubic(0.0, 0.0, -1.0, 1.0)
+    assert (a, b, c, d) == (0.0, 1.0, -1.0, 0.0)
+    pos, en, cu = NEB.spline_extrema([0.0, 0.0], [-1.0, 1.0], [1.0])
+    assert pos.tolist() == [0.5] and en[0] == pytest.approx(0.25) and cu[0] == pytest.approx(-2.0)
+    a, b, c, d = ONEB.cubic(0.0, 0.5, -2.0, 0.5)
+    assert (b, c, d) == (2.0, -2.0, 0.5) and c * c - 3.0 * b * d > 0
+    pos, en, cu = NEB.spline_extrema([0.0, 0.5], [-2.0, 0.5], [1.0])
+    assert len(pos) >= 1
+    for f in pos:
+        assert abs((3 * d * f + 2 * c) * f + b) < 1e-10
+    a, b, c, d = ONEB.cubic(0.0, 10.0, -20.0, -20.0)
+    assert c * c - 3.0 * b * d < 0 and len(NEB.spline_extrema([0.0, 10.0], [-20.0, -20.0], [1.0])[0]) == 0
+
+
+@pytest.mark.parametrize("images", [4, 5])
+def test_band_optimiser_converges_to_the_dimer_saddle(backend, oracle, images):
+    """`run_bands` (NudgedElasticBand::compute with LBFGS over the concatenated images, every evaluation one
+    eonb200_neb_band_forces call): a climbing-image band between the two minima of the reference's Pt adatom hop
+    (process_search_morse_pt.dat) converges, and its climbing image / spline maximum sit on the saddle the dimer finds
+    (saddle energy of the golden, 1e-3 eV).  Two identical bands in one batch stay identical."""
+    g = oracle.goldens()["process_search_lbfgs"]
+    d = oracle.load_fixture("morse_pt_saddle.json")
+    Z, box, fixed = d["atomic_nrs"], d["cell"], d["fixed"]
+    prm = search_params(lib=backend, opt_method=1, opt_converged_force=1e-3, saddle_max_energy=10.0)
+    with B200Potential("morse_pt", lib=backend) as pot:
+        wk = Walkers(pot, Z, fixed, box, d["positions"].reshape(1, -1))
+        E0, _ = wk.matter_forces()
+        wk.set(positions=d["displacement_positions"].reshape(1, -1), modes=d["direction"].reshape(1, -1))
+        out = wk.process_search(prm, E0)
+        wk.close()
+        m1, m2 = out["min1"].positions[0], out["min2"].positions[0]
+        r = NEB.run_bands(pot, np.stack([m1, m1]), np.stack([m2, m2]), Z, box, fixed, images=images, spring=5.0,
+                          max_iterations=300, converged_force=0.01, max_move=0.2)
+    assert np.all(r["status"] == 0) and np.all(r["iterations"] < 100)
+    assert np.array_equal(r["force_calls"], (r["iterations"] + 2) * images)  # first evaluation + curvature probe + steps
+    E = r["energies"]
+    assert np.abs(E[0] - E[1]).max() < 1e-12
+    assert E[0].max() == pytest.approx(g["energy_saddle"], abs=1e-3)
+    assert E[0, 0] == pytest.approx(out["min1"].energies[0], abs=1e-8) and E[0, -1] == pytest.approx(out["min2"].energies[0], abs=1e-8)
+    pos, en, cu = r["extrema"][0]
+    k = int(np.argmax(en))
+    assert en[k] == pytest.approx(g["energy_saddle"], abs=1e-3) and cu[k] < 0
+    assert abs(pos[k] - r["climbing"][0]) < 0.25
