@@ -127,6 +127,39 @@ def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def bind_to_gpu_numa_node(local_rank: int, world: int) -> dict:
+    """Pin this rank to its own slice of the cores of the NUMA node its GPU hangs off (one host thread per GPU; eight
+    Python processes wandering over two sockets cost the round-1 e2e number a quarter of its scaling)."""
+    info = {"bound": False}
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout.strip()
+        bus = out.lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        node = -1
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = allowed
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+                txt = fh.read().strip()
+            nodecpus = set()
+            for part in txt.split(","):
+                a, _, b = part.partition("-")
+                nodecpus.update(range(int(a), int(b or a) + 1))
+            cpus = [c for c in allowed if c in nodecpus] or allowed
+        # ranks whose GPUs share a node split its cores evenly
+        per = max(1, len(cpus) // max(1, world))
+        mine = cpus[(local_rank % max(1, world)) * per:(local_rank % max(1, world) + 1) * per] or cpus
+        os.sched_setaffinity(0, mine)
+        info = {"bound": True, "numa_node": node, "cpus": len(mine)}
+    except Exception as exc:  # no sysfs / no permission: run unbound
+        info["why"] = str(exc)[:80]
+    return info
+
+
 # ------------------------------------------------------------------------------------------------------
 # inputs
 def force_workload(first_walker: int):
@@ -141,39 +174,70 @@ def search_workload():
     return WL.akmc_al_on_au_row()
 
 
-SEARCH_PARAMS = dict(opt_method=1, opt_converged_force=1e-4, opt_max_iterations=1000, minmode_method=0,
-                     saddle_max_energy=10.0, saddle_max_iterations=1000)
+# examples/akmc-al/config.ini: LBFGS to 1e-4, Lanczos with tolerance 0.05, max_energy 10 (workloads.AKMC_AL); the dimer
+# variant of the same searches is reported next to it
+SEARCH_PARAMS = dict(WL.AKMC_AL["search"])
+SEARCH_PARAMS_DIMER = dict(SEARCH_PARAMS, minmode_method=0)
+STREAM_SLOTS, STREAM_QUEUE, STREAM_GROUPS = 512, 2048, 32
 
 
 # ------------------------------------------------------------------------------------------------------
 # CPU arms (the only place outside tests/ and smoke() that touches oracle/)
-def cpu_force_baseline(struct, positions, budget_s: float, use_reference: bool):
-    """Time the reference's CPU EAM on a bounded sample of the same walkers, one thread per host core."""
+def _cpu_worker(args):
+    """One pinned process: evaluate walkers in a loop for `budget_s` seconds, return the number of evaluations."""
+    kind, core, positions, Z, cell, budget_s = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except OSError:
+        pass
     import oracle_lib as O
-    cores = os.cpu_count() or 1
-    kind = "reference" if (use_reference and O.ref_eam_available()) else "port"
     if kind == "reference":
         def one(w):
-            O.ref_eam_force(positions[w % len(positions)], struct.atomic_nrs, struct.cell)
+            O.ref_eam_force(positions[w % len(positions)], Z, cell)
     else:
-        pot = O.potential(O.POT_EAM)
+        pot = O.potential(O.POT_EAM if kind == "port" else O.POT_EAM_NL)
 
         def one(w):
-            O.force(pot, positions[w % len(positions)], struct.atomic_nrs, struct.cell)
-    t0 = time.perf_counter()
+            O.force(pot, positions[w % len(positions)], Z, cell)
     one(0)
-    t1 = max(time.perf_counter() - t0, 1e-6)
-    per_core = max(2, int(budget_s / t1))
-    n_evals = per_core * cores
-    with ThreadPoolExecutor(cores) as ex:
-        t0 = time.perf_counter()
-        list(ex.map(one, range(n_evals), chunksize=max(1, per_core // 4)))
-        dt = time.perf_counter() - t0
+    n = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        one(n)
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+CPU_KINDS = {"reference": "EAM.cpp compiled from the reference tree (builds cell lists it never reads, then an O(N^2) loop)",
+             "port": "oracle restatement of EAM.cpp (bit-identical results, O(N^2) loop only)",
+             "port-nl": "oracle with a cell-list neighbour search (what a non-wasteful CPU loop does)"}
+
+
+def cpu_force_baseline(struct, positions, budget_s: float, use_reference: bool, kind: str = None):
+    """Time a CPU EAM on a bounded sample of the same walkers: ONE PINNED PROCESS PER HOST CORE (BASELINE.md section
+    3), each evaluating single walkers for `budget_s` seconds."""
+    import multiprocessing as mp
+    import oracle_lib as O
+    cores_avail = sorted(os.sched_getaffinity(0))
+    cores = len(cores_avail)
+    if kind is None:
+        kind = "reference" if (use_reference and O.ref_eam_available()) else "port"
+    if kind == "reference" and not O.ref_eam_available():
+        kind = "port"
+    O.lib()  # build / load before forking
+    jobs = [(kind, c, positions[:8], struct.atomic_nrs, struct.cell, budget_s) for c in cores_avail]
+    ctx = mp.get_context("spawn")  # (the parent may hold a CUDA context)
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        out = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    n_evals = sum(o[0] for o in out)
+    dt = max(o[1] for o in out)
     rate = n_evals * struct.n_atoms / dt
-    return {"value": rate, "unit": "atom-force-evals/s", "cores": cores, "kind": kind,
-            "sample": f"{n_evals} single-walker evaluations of the {struct.n_atoms}-atom akmc-al cell "
-                      f"({'EAM.cpp compiled from the reference tree, O(N^2) loop' if kind == 'reference' else 'oracle restatement of EAM.cpp'}), "
-                      f"{cores} threads, {dt:.1f} s"}, dt, n_evals
+    return {"value": rate, "unit": "atom-force-evals/s", "cores": cores, "kind": "reference" if kind == "reference" else "port",
+            "variant": kind,
+            "sample": f"{n_evals} single-walker evaluations of the {struct.n_atoms}-atom akmc-al cell ({CPU_KINDS[kind]}), "
+                      f"{cores} pinned processes, {dt:.1f} s each (wall {wall:.1f} s with start-up)"}, dt, n_evals
 
 
 def run_reference(args):
@@ -244,6 +308,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank, world)
 
     def barrier():
         if world > 1:
@@ -345,6 +410,29 @@ def run_b200(args):
     assert np.allclose(e_U, d_U.cpu().numpy(), rtol=0.0, atol=1e-8), "e2e energies differ from the device-resident run"
     epot.close()
     e2e_value = units / e2e_s
+    # The same call through the C++ shim an eonclient build would link (eon_b200/host/B200Potential.hpp), every system
+    # in its own heap block like the Matter objects of a dimer or a band (client/Matter.cpp:523): staged copies.
+    e2e_shim = None
+    exe = os.path.join(ROOT, "tests", "host", "harness")
+    if os.path.exists(exe):
+        text = []
+        for w in range(W):
+            text.append(" ".join(repr(float(x)) for x in sets[0][w].reshape(-1)))
+            text.append(" ".join(str(int(z)) for z in struct.atomic_nrs))
+            text.append(" ".join(repr(float(x)) for x in struct.cell.reshape(-1)))
+        barrier()
+        try:
+            out = subprocess.run([exe, os.path.join(ROOT, "eon_b200", "libeonb200.so"), "3", str(W), str(N), "bench",
+                                  str(max(10, args.steps)), "pin", f"device={local_rank}"], input="\n".join(text) + "\n",
+                                 stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+            tok = out.stdout.split()
+            ms_mean = reduce_max(float(tok[1])) if out.returncode == 0 and len(tok) >= 3 else float("nan")
+            e2e_shim = {"ms_per_step": ms_mean, "value": W * N * world / (ms_mean * 1e-3), "unit": "atom-force-evals/s",
+                        "how": "tests/host/harness bench: B200Potential::forceBatch with one heap block per system "
+                               "(positions and forces staged through page-locked buffers, chunked copy / kernel / copy "
+                               "pipeline), wall clock around the call"}
+        except Exception as exc:
+            e2e_shim = {"error": str(exc)[:120]}
     # bytes the call moves: positions in (one shared topology row and box), forces + energies + list flags out
     h2d = W * 3 * N * 8 + N * 4 + 72
     d2h = W * 3 * N * 8 + W * 8 + 36
@@ -362,7 +450,7 @@ def run_b200(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
     hbm_achieved = eam_min_bytes(pairs_per_step, W * N) / (ms_kernel * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "kernel": "k_eam_fused (one launch per step: prologue, filter, density, force)", "achieved": achieved, "peak": fp64_peak / 1e12,
+    roofline = {"bound": "fp64", "kernel": "k_eam_n3 (one launch per step: staging, density over the owned half of the pairs, embedding, owner and receiver force passes)", "achieved": achieved, "peak": fp64_peak / 1e12,
                 "unit": "TFLOP/s", "frac": achieved / (fp64_peak / 1e12) if fp64_peak > 0 else None, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                 "traffic_source": NCU_TRAFFIC_SOURCE,
                 "peak_source": "DFMA microbenchmark k_dfma_peak measured in this run (no FP64 figure in MEASURED_PEAKS.json)",
@@ -370,7 +458,7 @@ def run_b200(args):
                 "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
                         "peak_source": hbm_src}}
 
-    # device-resident saddle searches (secondary metric)
+    # device-resident saddle searches (secondary metric): examples/akmc-al settings on the stable Au-row geometry
     search = None
     if not args.no_search:
         s2, scale = search_workload()
@@ -380,57 +468,64 @@ def run_b200(args):
         hmin = wk.harvest()
         Rmin, E0 = hmin.positions[0], float(hmin.energies[0])
         cfg = dict(WL.AKMC_AL)
-        R = np.empty((W, N, 3))
-        M = np.empty((W, N, 3))
-        for k in range(W):
-            R[k], M[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"], cfg["seed"] + first + k)
-        wk.set(positions=R, modes=M)
-        prm = search_params(**SEARCH_PARAMS)
-        l0 = spot.kernelLaunches
-        barrier()
-        wk.saddle_search(prm, E0)
-        ms = reduce_max(wk.last_ms)
-        h_local = wk.harvest(geometry=False)
-        good = reduce_sum(float((h_local.status == 0).sum()))
-        fcalls = reduce_sum(float(h_local.force_calls.sum()))
-        h = sharding.harvest(h_local, dst=0)  # the path's only exchange: results of all ranks, walker order, on rank 0
-        if h is None:
-            h = h_local
-        elif world > 1:
-            assert h.status.shape[0] == W * world and int((h.status == 0).sum()) == int(good)
-        search = {"searches_per_hour": good / (ms * 1e-3) * 3600.0, "unit": "status-0 saddle searches/hour",
-                  "walkers": int(W * world), "status_good": int(good), "ms": ms,
-                  "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(h.status, return_counts=True))},
-                  "force_calls": int(fcalls), "atom_force_evals_per_s": fcalls * N / (ms * 1e-3),
-                  "gpu_launches": int(spot.kernelLaunches - l0),
-                  "config": "akmc-al geometry scaled to a0 of the in-tree EAM Au row, dimer (cg rotation) + LBFGS 1e-4, "
-                            "displace radius 5.0 / magnitude 0.2 around the adatom"}
+        Q = STREAM_QUEUE
+        Rq = np.empty((Q, N, 3))
+        Mq = np.empty((Q, N, 3))
+        for k in range(Q):  # (host-side generation, outside every timed region)
+            Rq[k], Mq[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"], cfg["seed"] + Q * rank + k)
+
+        def one_launch(params):
+            wk.set(positions=Rq[:W], modes=Mq[:W])
+            prm = search_params(**params)
+            l0 = spot.kernelLaunches
+            barrier()
+            wk.saddle_search(prm, E0)
+            ms = reduce_max(wk.last_ms)
+            st = spot.nl_stats()
+            h_local = wk.harvest(geometry=False)
+            good = reduce_sum(float((h_local.status == 0).sum()))
+            fcalls = reduce_sum(float(h_local.force_calls.sum()))
+            rebuilt, reused = reduce_sum(float(st["rebuilt"])), reduce_sum(float(st["reused"]))
+            h = sharding.harvest(h_local, dst=0)  # the path's only exchange: results of all ranks, walker order, on rank 0
+            if h is None:
+                h = h_local
+            elif world > 1:
+                assert h.status.shape[0] == W * world and int((h.status == 0).sum()) == int(good)
+            return {"searches_per_hour": good / (ms * 1e-3) * 3600.0, "unit": "status-0 saddle searches/hour",
+                    "walkers": int(W * world), "status_good": int(good), "ms": ms,
+                    "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(h.status, return_counts=True))},
+                    "force_calls": int(fcalls), "atom_force_evals_per_s": fcalls * N / (ms * 1e-3),
+                    "list_rebuild_fraction": rebuilt / max(1.0, rebuilt + reused),
+                    "gpu_launches": int(spot.kernelLaunches - l0)}
+
+        search = one_launch(SEARCH_PARAMS)
+        search["config"] = ("akmc-al geometry scaled to a0 of the in-tree EAM Au row; examples/akmc-al/config.ini settings: "
+                            "Lanczos (tolerance 0.05) + LBFGS 1e-4, displace radius 5.0 / magnitude 0.2 around the adatom; "
+                            "one launch, one CTA per walker: lasts as long as its slowest walker")
+        search["dimer"] = one_launch(SEARCH_PARAMS_DIMER)
         if rank == 0 and not args.no_cpu:
             cpu_s, _ = cpu_search_baseline(s2, Rmin, E0, max(8, os.cpu_count() or 1))
             search["cpu_baseline"] = cpu_s
         wk.close()
-        # A launch of 256 walkers lasts as long as its slowest walker (a chain of ~10^3 dependent force calls) and
-        # leaves most SMs idle after the median walker has finished; the same job with 4x and 16x the walkers shows
-        # the throughput the device reaches once finished slots are refilled.
-        for mult in (4, 16):
-            Wm = mult * W
-            wkm = Walkers(spot, s2.atomic_nrs, s2.fixed, s2.cell, np.broadcast_to(Rmin.reshape(1, -1), (Wm, 3 * N)).copy())
-            Rm = np.empty((Wm, N, 3))
-            Mm = np.empty((Wm, N, 3))
-            for k in range(Wm):
-                Rm[k], Mm[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"],
-                                           cfg["seed"] + mult * first + k)
-            wkm.set(positions=Rm, modes=Mm)
-            barrier()
-            wkm.saddle_search(prm, E0)
-            msm = reduce_max(wkm.last_ms)
-            hm = wkm.harvest(geometry=False)
-            goodm = reduce_sum(float((hm.status == 0).sum()))
-            fcm = reduce_sum(float(hm.force_calls.sum()))
-            search[f"walkers_x{mult}"] = {"walkers": int(Wm * world), "ms": msm, "status_good": int(goodm),
-                                          "searches_per_hour": goodm / (msm * 1e-3) * 3600.0,
-                                          "atom_force_evals_per_s": fcm * N / (msm * 1e-3)}
-            wkm.close()
+        # Throughput with every slot kept busy: a queue of searches through STREAM_SLOTS slots in STREAM_GROUPS groups,
+        # each group refilled from the queue as soon as its walkers are done (eon/communicator.py:525-559 does the same
+        # with cores); wall clock from the first submit to the last harvest, uploads and harvests included.
+        wks = Walkers(spot, s2.atomic_nrs, s2.fixed, s2.cell, np.broadcast_to(Rmin.reshape(1, -1), (STREAM_SLOTS, 3 * N)).copy())
+        prm = search_params(**SEARCH_PARAMS)
+        wks.stream_search(prm, Rq[:STREAM_SLOTS], Mq[:STREAM_SLOTS], E0, groups=STREAM_GROUPS, geometry=False)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        hs = wks.stream_search(prm, Rq, Mq, E0, groups=STREAM_GROUPS, geometry=False)
+        wall = reduce_max(time.perf_counter() - t0)
+        goods = reduce_sum(float((hs.status == 0).sum()))
+        fcs = reduce_sum(float(hs.force_calls.sum()))
+        search["streamed"] = {"queue": int(Q * world), "slots_per_gpu": STREAM_SLOTS, "groups": STREAM_GROUPS,
+                              "wall_s": wall, "status_good": int(goods),
+                              "searches_per_hour": goods / wall * 3600.0,
+                              "atom_force_evals_per_s": fcs * N / wall,
+                              "how": "Walkers.stream_search: eonb200_walkers_submit / poll / harvest_group on one stream "
+                                     "per group; a walker at max_iterations only holds up its own 16-slot group"}
+        wks.close()
         spot.close()
 
     # BASELINE.json configs[2] as a second data point: 4096 walkers of the 2047-atom vacancy cell sharded over the
@@ -471,6 +566,47 @@ def run_b200(args):
               "fp64_roofline_frac": flops3 / (ms3 * 1e-3) / (fp64_peak * world) if fp64_peak > 0 else None}
         pot3.close()
         del sets3, d_Z3, d_box3, d_F3, d_U3
+        # ... and as resident saddle searches (BASELINE: "4096 walkers sharded over 1/2/4/8 B200"): settings of
+        # examples/akmc-cu-vacancy/config.ini (dimer, rotations_max 20, LBFGS memory 25, converged_force 0.01,
+        # max_move 0.05) on the in-tree Au row at its own lattice constant (the reference has no Cu EAM row and the Al
+        # row has no stable crystal), every walker displaced around a neighbour of the vacancy
+        if not args.no_search:
+            s3s = WL.fcc_vacancy(8, WL.A0_AU, WL.SEARCH_ROW_Z)
+            spot3 = B200Potential("eam", device=local_rank, skin=args.skin, conservative=True)
+            wk3 = Walkers(spot3, s3s.atomic_nrs, s3s.fixed, s3s.cell, np.broadcast_to(s3s.positions.reshape(1, -1), (W3, 3 * N3)).copy())
+            wk3.set_active([1] + [0] * (W3 - 1))
+            wk3.relax(search_params(opt_method=1, opt_converged_force=1e-3, lbfgs_memory=25))
+            wk3.set_active(None)
+            h3 = wk3.harvest()
+            Rmin3, E03 = h3.positions[0], float(h3.energies[0])
+            R3 = np.empty((W3, N3, 3))
+            M3 = np.empty((W3, N3, 3))
+            for k in range(W3):
+                R3[k], M3[k] = WL.displace(s3s, Rmin3, 0, 3.0 * WL.A0_AU / 3.615, 0.3, 42 + lo3 + k)
+            wk3.set(positions=R3, modes=M3)
+            prm3 = search_params(opt_method=1, opt_converged_force=0.01, lbfgs_memory=25, max_move=0.05, minmode_method=0,
+                                 dimer_rotations_max=20, dimer_converged_angle=1.0, saddle_max_energy=300.0,
+                                 saddle_max_iterations=1000)
+            barrier()
+            wk3.saddle_search(prm3, E03)
+            ms3s = reduce_max(wk3.last_ms)
+            hh3 = wk3.harvest(geometry=False)
+            good3 = reduce_sum(float((hh3.status == 0).sum()))
+            fc3 = reduce_sum(float(hh3.force_calls.sum()))
+            st3 = np.zeros(24)
+            for k_, v_ in zip(*np.unique(hh3.status, return_counts=True)):
+                st3[int(k_)] += v_
+            st3 = [reduce_sum(float(v)) for v in st3]
+            c3["search"] = {"walkers": 4096, "ms": ms3s, "status_good": int(good3),
+                            "searches_per_hour": good3 / (ms3s * 1e-3) * 3600.0,
+                            "force_calls": int(fc3), "atom_force_evals_per_s": fc3 * N3 / (ms3s * 1e-3),
+                            "status_histogram": {k_: int(v_) for k_, v_ in enumerate(st3) if v_ > 0},
+                            "barrier_eV_median": float(np.median(hh3.energies[hh3.status == 0] - E03)) if (hh3.status == 0).any() else None,
+                            "config": "2047-atom fcc vacancy cell on the Au row (a0 %.4f A), dimer rotations_max 20 + LBFGS "
+                                      "memory 25, 0.01 eV/A, max_move 0.05; displacement sigma 0.3 A within 3.0 A (scaled) of "
+                                      "a neighbour of the vacancy" % WL.A0_AU}
+            wk3.close()
+            spot3.close()
 
     # BASELINE.json configs[3] as a third data point: examples/akmc-pt, Morse_Pt, dimer + CG saddle searches from the
     # least-coordinated atoms followed by the minimisation of both minima per walker, classified like ProcessSearchJob
@@ -505,12 +641,17 @@ def run_b200(args):
         good4 = reduce_sum(float((st4 == 0).sum()))
         fc4 = reduce_sum(float(sum(r["total_force_calls"] for r in res4)))
         barr = [r["barrier_reactant_to_product"] for r in res4 if r["termination_reason"] == 0]
+        cnt4 = np.zeros(24)
+        for k_, v_ in zip(*np.unique(st4, return_counts=True)):
+            cnt4[int(k_)] += v_
+        hist4 = {k_: int(reduce_sum(float(v_))) for k_, v_ in enumerate(cnt4)}
+        hist4 = {k_: v_ for k_, v_ in hist4.items() if v_ > 0}  # all ranks
         c4 = {"workload": "examples/akmc-pt: 343 Pt atoms (168 fixed), Morse_Pt, least-coordinated epicentres, sigma 0.1 A "
                           "within 3.3 A, dimer + CG 1e-3, then both minima relaxed per walker; host classification as "
                           "ProcessSearchJob (connectivity, barriers)",
               "walkers": int(W * world), "wall_s": wall4, "processes_found": int(good4),
               "process_searches_per_hour": good4 / wall4 * 3600.0,
-              "status_histogram": {int(k): int(v) for k, v in zip(*np.unique(st4, return_counts=True))},
+              "status_histogram": hist4,
               "force_calls": int(fc4), "atom_force_evals_per_s": fc4 * N4 / wall4,
               "barrier_eV_min_median": [float(np.min(barr)), float(np.median(barr))] if barr else None}
         wk4.close()
@@ -568,9 +709,29 @@ def run_b200(args):
               "barrier_eV": float(out5["energies"][0].max() - out5["energies"][0, 0])}
         npot.close()
 
+    # honest list accounting: the headline runs with every list valid (jitter well inside skin / 4); a search rebuilds
+    # its lists at the rate observed in the search leg, and a step that rebuilds costs what the skin-0 run costs
+    ms_reuse, ms_fresh = dev_ms_max / args.steps, t_fresh / args.steps
+    frac = search["list_rebuild_fraction"] if search else None
+    build_bytes = 24.0 * W * N + 4.0 * pairs_per_step  # positions in, one 4-byte code per ordered pair out (no skin shell)
+    ms_build = max(ms_fresh - ms_reuse, 1e-6)
+    list_acc = {"rebuild_fraction_in_search_leg": frac,
+                "ms_step_lists_valid": ms_reuse, "ms_step_rebuilding_every_list": ms_fresh,
+                "value_search_mix": (W * N * world / (((1.0 - frac) * ms_reuse + frac * ms_fresh) * 1e-3)) if frac is not None else None,
+                "nl_build": {"ms_per_batch_of_rebuilds": ms_build, "algorithmic_bytes": build_bytes,
+                             "achieved_GBs": build_bytes / (ms_build * 1e-3) / 1e9,
+                             "frac_of_hbm_peak": build_bytes / (ms_build * 1e-3) / 1e9 / hbm_peak,
+                             "note": "rebuild time = (step at skin 0, every list rebuilt in the kernel) - (step with valid "
+                                     "lists); bytes = 24 N + 4 P_o per system (SURVEY.md 8d)"}}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _, _ = cpu_force_baseline(struct, sets[0], 1.0, True)
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU arm gets every host core back
+        cpu, _, _ = cpu_force_baseline(struct, sets[0], 6.0, True)
+        cpu["variants"] = {}
+        for kind in ("port", "port-nl"):
+            v, _, _ = cpu_force_baseline(struct, sets[0], 4.0, False, kind=kind)
+            cpu["variants"][kind] = {"value": v["value"], "sample": v["sample"]}
+        cpu["variants"]["reference"] = {"value": cpu["value"], "sample": cpu["sample"]}
 
     if rank == 0:
         line = {"metric": "atom-force-evals/sec", "value": value, "unit": "atom-force-evals/s", "n_gpus": world,
@@ -578,10 +739,14 @@ def run_b200(args):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": workload_config(N, world, args.skin, rebuilt),
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "atom-force-evals/s", "h2d_bytes_per_step": h2d,
-                                          "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+                                          "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                                          "how": "B200Potential.forceBatch on caller-owned contiguous numpy blocks, "
+                                                 "page-locked by the handle; copies and kernels chunk-pipelined on "
+                                                 "three streams", "cpp_shim": e2e_shim},
                 "gpu_launches": int(launches), "roofline": roofline,
                 "extra": {"wall_s_timed_region": t_wall, "value_hot_l2": units / world / (t_hot * 1e-3),
                           "value_fresh_list_every_step": units / world / (t_fresh * 1e-3),
+                          "list_accounting": list_acc, "affinity": affinity,
                           "fp64_peak_tflops_measured": fp64_peak / 1e12, "c3": c3, "c4": c4, "c5": c5},
                 "search": search}
         if cpu is not None:

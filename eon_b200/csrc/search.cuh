@@ -549,44 +549,99 @@ __device__ EONB200_NOINLINE void dimer_compute(Ctx &c, MinModeState &st, MatterS
 }
 
 // ---- lowest eigenmode: Lanczos --------------------------------------------------------------------------
-// Cyclic Jacobi on a small symmetric matrix, one thread (stands in for Eigen's
-// SelfAdjointEigenSolver, Lanczos.cpp:117-119).  Lowest eigenvalue and its eigenvector.
-__device__ inline void small_sym_eig_lowest(int n, double *a, double *v, double *ew, double *evec) {
-  for (int i = 0; i < n * n; i++) v[i] = 0.0;
-  for (int i = 0; i < n; i++) v[i * n + i] = 1.0;
-  for (int sweep = 0; sweep < 100; sweep++) {
-    double off = 0.0;
-    for (int p = 0; p < n; p++)
-      for (int q = p + 1; q < n; q++) off += a[p * n + q] * a[p * n + q];
-    if (off < 1e-300) break;
-    for (int p = 0; p < n; p++)
-      for (int q = p + 1; q < n; q++) {
-        if (fabs(a[p * n + q]) < 1e-300) continue;
-        const double th = (a[q * n + q] - a[p * n + p]) / (2.0 * a[p * n + q]);
-        const double tt = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
-        const double cs = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cs;
-        for (int k = 0; k < n; k++) {
-          const double akp = a[k * n + p], akq = a[k * n + q];
-          a[k * n + p] = cs * akp - sn * akq;
-          a[k * n + q] = sn * akp + cs * akq;
-        }
-        for (int k = 0; k < n; k++) {
-          const double apk = a[p * n + k], aqk = a[q * n + k];
-          a[p * n + k] = cs * apk - sn * aqk;
-          a[q * n + k] = sn * apk + cs * aqk;
-        }
-        for (int k = 0; k < n; k++) {
-          const double vkp = v[k * n + p], vkq = v[k * n + q];
-          v[k * n + p] = cs * vkp - sn * vkq;
-          v[k * n + q] = sn * vkp + cs * vkq;
+// Lowest eigenpair of the symmetric TRIDIAGONAL Lanczos matrix (stands in for Eigen's SelfAdjointEigenSolver,
+// Lanczos.cpp:117-119), by the first warp of the CTA: the eigenvalue by 32-way multisection on the Sturm count (a
+// dozen rounds reach the last bit of the Gershgorin interval), the eigenvector by three steps of inverse iteration with
+// a pivoted tridiagonal solve.  The cyclic Jacobi this replaces cost one thread ~10^5 dependent shared-memory
+// operations per Lanczos iteration -- thirty times the force evaluation next to it.
+// d[i] = T[i][i], e[i] = T[i][i + 1] read from T (row stride ld); work: 5 * n doubles of shared memory.
+__device__ inline void tridiag_lowest(int n, const double *T, int ld, double *work, double *ew, double *evec) {
+#ifdef EONB200_EMU
+  const int lane = 0, nl = 1;
+#else
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x, nl = 32;
+#endif
+  double lo = 1e300, hi = -1e300;
+  for (int i = 0; i < n; i++) {
+    const double dl = i > 0 ? fabs(T[(i - 1) * ld + i]) : 0.0, dr = i + 1 < n ? fabs(T[i * ld + i + 1]) : 0.0;
+    lo = fmin(lo, T[i * ld + i] - dl - dr);
+    hi = fmax(hi, T[i * ld + i] + dl + dr);
+  }
+  const double span0 = fmax(hi - lo, 1e-300);
+  lo -= 1e-12 * span0;
+  hi += 1e-12 * span0;
+  for (int round = 0; round < 64; round++) {
+    if (!(hi - lo > 4e-16 * fmax(fabs(lo), fabs(hi)) + 1e-300)) break;
+    const double x = lo + (hi - lo) * static_cast<double>(lane + 1) / static_cast<double>(nl + 1);
+    // Sturm count: eigenvalues below x
+    int cnt = 0;
+    double q = T[0] - x;
+    cnt += q < 0.0 ? 1 : 0;
+    for (int i = 1; i < n; i++) {
+      if (fabs(q) < 1e-300) q = q < 0.0 ? -1e-300 : 1e-300;
+      const double e = T[(i - 1) * ld + i];
+      q = T[i * ld + i] - x - e * e / q;
+      cnt += q < 0.0 ? 1 : 0;
+    }
+#ifdef EONB200_EMU
+    if (cnt >= 1) hi = x; else lo = x;
+#else
+    const unsigned below = __ballot_sync(0xffffffffu, cnt >= 1);  // lanes whose point lies above the lowest eigenvalue
+    const int first = below ? __ffs(below) - 1 : 32;
+    const double xs_hi = lo + (hi - lo) * static_cast<double>(first + 1) / static_cast<double>(nl + 1);
+    const double xs_lo = lo + (hi - lo) * static_cast<double>(first) / static_cast<double>(nl + 1);
+    hi = first < 32 ? xs_hi : hi;
+    lo = first > 0 ? xs_lo : lo;
+#endif
+  }
+  const double lam = 0.5 * (lo + hi);
+  if (lane == 0) {
+    *ew = lam;
+    // inverse iteration on (T - lam) with Gaussian elimination and partial pivoting (band grows to two superdiagonals)
+    double *dd = work, *du = work + n, *du2 = work + 2 * n, *dl = work + 3 * n, *x = work + 4 * n;
+    const double shift = lam - 1e-14 * fmax(fabs(lam), span0 * 1e-3);  // keep the shifted matrix non-singular
+    for (int i = 0; i < n; i++) x[i] = 1.0 / sqrt(static_cast<double>(n)) * ((i & 1) ? 0.9 : 1.0);
+    for (int it = 0; it < 3; it++) {
+      for (int i = 0; i < n; i++) {
+        dd[i] = T[i * ld + i] - shift;
+        du[i] = i + 1 < n ? T[i * ld + i + 1] : 0.0;
+        dl[i] = du[i];
+        du2[i] = 0.0;
+      }
+      for (int i = 0; i + 1 < n; i++) {  // eliminate dl[i]
+        if (fabs(dd[i]) >= fabs(dl[i])) {
+          const double piv = fabs(dd[i]) < 1e-300 ? 1e-300 : dd[i];
+          const double f = dl[i] / piv;
+          dd[i + 1] -= f * du[i];
+          x[i + 1] -= f * x[i];
+          dd[i] = piv;
+        } else {  // swap rows i and i + 1
+          const double f = dd[i] / dl[i];
+          const double t0 = dd[i + 1], t1 = i + 2 < n ? du[i + 1] : 0.0, tx = x[i + 1];
+          dd[i] = dl[i];
+          dd[i + 1] = du[i] - f * t0;
+          du2[i] = t1;
+          if (i + 2 < n) du[i + 1] = -f * t1;
+          du[i] = t0;
+          x[i + 1] = x[i] - f * tx;
+          x[i] = tx;
         }
       }
+      for (int i = n - 1; i >= 0; i--) {  // back substitution
+        double t = x[i];
+        if (i + 1 < n) t -= du[i] * x[i + 1];
+        if (i + 2 < n) t -= du2[i] * x[i + 2];
+        const double piv = fabs(dd[i]) < 1e-300 ? 1e-300 : dd[i];
+        x[i] = t / piv;
+      }
+      double nn = 0.0;
+      for (int i = 0; i < n; i++) nn += x[i] * x[i];
+      nn = 1.0 / sqrt(nn);
+      for (int i = 0; i < n; i++) x[i] *= nn;
+    }
+    for (int i = 0; i < n; i++) evec[i] = x[i];
   }
-  int best = 0;
-  for (int i = 1; i < n; i++)
-    if (a[i * n + i] < a[best * n + best]) best = i;
-  *ew = a[best * n + best];
-  for (int i = 0; i < n; i++) evec[i] = v[i * n + best];
 }
 
 // Lanczos::compute with phva_atoms = All (mobile set = atoms that are not fully fixed).  `mode`
@@ -604,8 +659,7 @@ __device__ EONB200_NOINLINE void lanczos_compute(Ctx &c, MinModeState &st, Matte
   if (maxIters > kMaxLanczosIters) maxIters = kMaxLanczosIters;
   if (maxIters < 1) maxIters = 1;
   __shared__ double T[kMaxLanczosIters * kMaxLanczosIters];
-  __shared__ double blk[kMaxLanczosIters * kMaxLanczosIters];
-  __shared__ double jv[kMaxLanczosIters * kMaxLanczosIters];
+  __shared__ double twork[5 * kMaxLanczosIters];
   __shared__ double evec[kMaxLanczosIters];
   __shared__ double ew_sh;
   VLOOP(k, maxIters * maxIters) T[k] = 0.0;
@@ -695,13 +749,8 @@ __device__ EONB200_NOINLINE void lanczos_compute(Ctx &c, MinModeState &st, Matte
     }
     if (i >= 1) {
       const int m = i + 1;
-      if (threadIdx.x == 0) {
-        for (int a = 0; a < m; a++)
-          for (int b = 0; b < m; b++) blk[a * m + b] = T[a * maxIters + b];
-        double e;
-        small_sym_eig_lowest(m, blk, jv, &e, evec);
-        ew_sh = e;
-      }
+      __syncthreads();  // T[i][i], T[i - 1][i] written by thread 0
+      tridiag_lowest(m, T, maxIters, twork, &ew_sh, evec);
       __syncthreads();
       ew = ew_sh;
       const double err = safe_div(fabs(ew - ewOld), fabs(ewOld), 1.0);

@@ -242,15 +242,21 @@ def test_many_dof_method_matrix(backend, oracle, al_slab_minimum, label, kw):
         if ref.status == 0:
             n_good += 1
             assert abs(h.energies[w] - ref.energy) < E_TOL
-            assert mic_max(h.positions[w], Rref, s.cell) < R_TOL
+            # (Lanczos: two different paths end anywhere inside the convergence ball around the saddle, whose radius
+            # along the softest mode -- 1e-4 eV/A over ~0.3 eV/A^2 -- is a few 1e-4 A)
+            assert mic_max(h.positions[w], Rref, s.cell) < (R_TOL if kw.get("minmode_method") != 1 else 5 * R_TOL)
             # the curvature estimate of the last rotation is only as good as dimer_converged_angle / the Lanczos
             # tolerance allow (the SD rotation leaves 2e-3 between two runs that differ in the last bit)
-            assert abs(h.eigenvalues[w] - ref.eigenvalue) < 5e-3
-            assert abs(abs(np.vdot(h.modes[w], Mref)) - 1.0) < 2e-3
+            ev_tol = 5e-3 + (0.05 * abs(ref.eigenvalue) if kw.get("minmode_method") == 1 else 0.0)  # Lanczos stops at 5 %
+            assert abs(h.eigenvalues[w] - ref.eigenvalue) < ev_tol
+            assert abs(abs(np.vdot(h.modes[w], Mref)) - 1.0) < (2e-2 if kw.get("minmode_method") == 1 else 2e-3)
         # same trajectory: the step counts agree (a few per cent of slack: rounding differences of the two exp
         # implementations move a convergence test by an iteration here and there)
-        assert abs(int(h.iterations[w]) - int(ref.iterations)) <= max(2, ref.iterations // 30), \
-            (label, w, h.iterations[w], ref.iterations)
+        # (Lanczos stopped at a 5 % eigenvalue change hands the translation a direction that moves with the last bits of
+        # the Ritz vector: the two implementations -- Jacobi on the host, Sturm multisection + inverse iteration on the
+        # device -- reach the same saddle along paths whose lengths differ by tens of per cent)
+        slack = max(2, ref.iterations // 30) if kw.get("minmode_method") != 1 else max(5, ref.iterations // 2)
+        assert abs(int(h.iterations[w]) - int(ref.iterations)) <= slack, (label, w, h.iterations[w], ref.iterations)
     assert n_good >= 1, label
 
 
