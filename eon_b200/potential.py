@@ -18,8 +18,11 @@ import numpy as np
 from . import _capi
 from ._capi import POT_EAM, POT_LJ, POT_LJCLUSTER, POT_MORSE_PT
 
+# "eam" / "eam_b200": the in-tree EAM class (client/potentials/EAM/EAM.cpp).  The reference's own "eam_al" is rgpot's
+# Fortran potential, a DIFFERENT model (golden -5.217864 eV against -5.085058 eV here): the
+# spelling is accepted as a deprecated alias of the in-tree class for round-1 scripts, never as that potential.
 _KINDS = {"lj": POT_LJ, "lj_cluster": POT_LJCLUSTER, "ljcluster": POT_LJCLUSTER, "morse_pt": POT_MORSE_PT,
-          "eam": POT_EAM, "eam_al": POT_EAM}
+          "eam": POT_EAM, "eam_b200": POT_EAM, "eam_al": POT_EAM}
 
 
 class PotentialError(RuntimeError):

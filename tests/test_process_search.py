@@ -1,5 +1,7 @@
 """Host-side tail of the batched process search: Matter::compare connectivity, endpoint
 swap, barrier / abort rules and the results.dat keys of client/ProcessSearchJob.cpp:234-363."""
+import os
+
 import numpy as np
 import pytest
 
@@ -95,3 +97,70 @@ def test_process_search_results_known_answer(backend, oracle):
     assert PS.compare(d["positions"], res["reactant"], box, True) and not PS.compare(d["positions"], res["product"], box, True)
     assert 0.0 < res["displacement_saddle_distance"] < 2.0
     assert PS.format_results_dat(res).count("\n") == 16
+
+
+def test_job_directory_driver_on_the_reference_system(backend, oracle, tmp_path):
+    """client/unit_tests/data/systems/saddle_search (config.ini, pos.con, displacement.con, direction.dat -- the files
+    the fixture tests/golden/morse_pt_saddle.json was cut from) through `jobs.run_saddle_search_jobs`: three copies of
+    the job directory in one launch, `results.dat` with the keys and order of SaddleSearchJob::saveData
+    (client/SaddleSearchJob.cpp:138-163) and the known answers of data/reference/saddle_search_morse_pt.dat, plus
+    `mode.dat` / `saddle.con` that read back to the harvested saddle."""
+    from eon_b200 import confile, jobs
+    g = oracle.goldens()["saddle_dimer_cg"]
+    d = oracle.load_fixture("morse_pt_saddle.json")
+    N = len(d["atomic_nrs"])
+    cfg = """[Main]
+job = saddle_search
+temperature = 300
+random_seed = 706253457
+
+[Potential]
+potential = morse_pt
+
+[Optimizer]
+converged_force = 0.001
+max_iterations = 1000
+
+[Saddle Search]
+displace_least_coordinated_weight = 1.0
+displace_radius = 3.3
+displace_magnitude = 0.01 # Actually from the displacement.con DO NOT CHANGE
+min_mode_method = dimer
+max_energy = 10.0
+"""
+    prm = jobs.search_params_from_ini(cfg, lib=backend)
+    assert prm.opt_converged_force == 0.001 and prm.saddle_converged_force == 0.001  # ParametersINI.cpp:1075-1077
+    assert prm.opt_max_iterations == 1000 and prm.minmode_method == 0 and prm.saddle_max_energy == 10.0
+    with pytest.raises(ValueError):
+        jobs.job_settings(cfg.replace("morse_pt", "emt"))
+    dirs = []
+    masses = np.full(N, 195.08)
+    for k in range(3):
+        jd = tmp_path / ("job%d" % k)
+        jd.mkdir()
+        (jd / "config.ini").write_text(cfg)
+        for name, pos in (("pos.con", d["positions"]), ("displacement.con", d["displacement_positions"])):
+            confile.write_con(str(jd / name), confile.ConFrame(d["cell"], pos, d["atomic_nrs"], d["fixed"].astype(bool),
+                                                               masses, np.arange(N)))
+        confile.write_mode(str(jd / "direction.dat"), d["direction"])
+        dirs.append(str(jd))
+    with B200Potential("morse_pt", lib=backend) as pot:
+        res = jobs.run_saddle_search_jobs(dirs, pot=pot)
+    for k, r in enumerate(res):
+        text = open(os.path.join(dirs[k], "results.dat")).read()
+        keys = [ln.split()[-1] for ln in text.splitlines()]
+        assert keys == ["termination_reason", "termination_reason_text", "job_type", "random_seed", "potential_type",
+                        "total_force_calls", "force_calls_saddle", "iterations", "potential_energy_saddle",
+                        "final_eigenvalue", "potential_energy_reactant"]
+        assert r["termination_reason"] == 0 and r["termination_reason_text"] == "Success" and r["job_type"] == "saddle_search"
+        assert r["potential_type"] == "MORSE_PT" and r["random_seed"] == 706253457
+        assert r["potential_energy_saddle"] == pytest.approx(g["energy_saddle"], abs=2e-5)
+        assert r["final_eigenvalue"] == pytest.approx(g["eigenvalue"], abs=5e-6)
+        assert r["iterations"] == g["iterations"] and r["force_calls_saddle"] == g["force_calls_saddle"]
+        assert r["total_force_calls"] == g["force_calls_saddle"] + 1
+        sad = confile.read_con(os.path.join(dirs[k], "saddle.con"))
+        mode = confile.read_mode(os.path.join(dirs[k], "mode.dat"), N)
+        assert sad.n_atoms == N and np.array_equal(sad.fixed, d["fixed"].astype(bool))
+        assert np.all(mode[d["fixed"].astype(bool)] == 0.0) and abs(np.linalg.norm(mode) - 1.0) < 1e-9
+    assert np.abs(confile.read_con(os.path.join(dirs[0], "saddle.con")).positions -
+                  confile.read_con(os.path.join(dirs[2], "saddle.con")).positions).max() == 0.0
