@@ -469,10 +469,13 @@ def run_b200(args):
         Rmin, E0 = hmin.positions[0], float(hmin.energies[0])
         cfg = dict(WL.AKMC_AL)
         Q = STREAM_QUEUE
-        Rq = np.empty((Q, N, 3))
-        Mq = np.empty((Q, N, 3))
-        for k in range(Q):  # (host-side generation, outside every timed region)
-            Rq[k], Mq[k] = WL.displace(s2, Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"], cfg["seed"] + Q * rank + k)
+        # start geometries and modes of the whole queue on the device (k_displace: Philox per (walker, atom); the
+        # reference's server draws them with numpy, eon/displace.py:180-263), read back once for the streamed leg
+        gen = Walkers(spot, s2.atomic_nrs, s2.fixed, s2.cell, np.broadcast_to(Rmin.reshape(1, -1), (Q, 3 * N)).copy())
+        gen.displace(Rmin, N - 1, cfg["radius"] * scale, cfg["magnitude"], cfg["seed"], first_walker_id=Q * rank)
+        hq = gen.harvest()
+        Rq, Mq = hq.positions, hq.modes
+        gen.close()
 
         def one_launch(params):
             wk.set(positions=Rq[:W], modes=Mq[:W])

@@ -25,7 +25,7 @@ SYMBOLS = [
     "eonb200_walkers_create", "eonb200_walkers_destroy", "eonb200_walkers_set",
     "eonb200_walkers_matter_forces", "eonb200_walkers_saddle_search", "eonb200_walkers_relax",
     "eonb200_walkers_displace_along_mode", "eonb200_walkers_harvest", "eonb200_walkers_last_ms",
-    "eonb200_walkers_set_active", "eonb200_walkers_groups", "eonb200_walkers_submit", "eonb200_walkers_poll",
+    "eonb200_walkers_displace", "eonb200_walkers_set_active", "eonb200_walkers_groups", "eonb200_walkers_submit", "eonb200_walkers_poll",
     "eonb200_walkers_harvest_group",
     "eonb200_measure_fp64_peak", "eonb200_kernel_launches", "eonb200_nl_stats",
     "eonb200_last_force_ms", "eonb200_phase_clocks", "eonb200_l2_flush",
@@ -122,6 +122,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.eonb200_walkers_displace_along_mode.restype = C.c_int
     lib.eonb200_walkers_harvest.argtypes = [_vp, _ip, _lp, _lp, _dp, _dp, _dp, _dp, _dp]
     lib.eonb200_walkers_harvest.restype = C.c_int
+    lib.eonb200_walkers_displace.argtypes = [_vp, _dp, C.c_long, _ip, C.c_double, C.c_double, C.c_ulonglong, C.c_long]
+    lib.eonb200_walkers_displace.restype = C.c_int
     lib.eonb200_walkers_set_active.argtypes = [_vp, _ip]
     lib.eonb200_walkers_set_active.restype = C.c_int
     lib.eonb200_walkers_groups.argtypes = [_vp, C.c_int]

@@ -1877,6 +1877,56 @@ int eonb200_walkers_harvest(EonB200Walkers *w, int *status, long *iterations, lo
   return 0;
 }
 
+int eonb200_walkers_displace(EonB200Walkers *w, const double *reference_positions, long nReferences, const int *epicentres,
+                             double radius, double sigma, unsigned long long seed, long first_walker_id) {
+  if (!w || !reference_positions || !epicentres) return 1;
+  EonB200Pot *pot = w->pot;
+  if (nReferences != 1 && nReferences != w->W) return fail(pot, 2, "walkers_displace: one reference or one per walker");
+  if (!(radius >= 0.0) || !(sigma >= 0.0)) return fail(pot, 2, "walkers_displace: radius and magnitude must not be negative");
+  for (long k = 0; k < w->W; k++)
+    if (epicentres[k] < 0 || epicentres[k] >= w->N) return fail(pot, 2, "walkers_displace: epicentre %d of walker %ld", epicentres[k], k);
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  const size_t D = w->D, Dp = w->Dp;
+  DevBuf<double> ref;
+  DevBuf<int> epi;
+  CU_TRY(pot, ref.reserve(static_cast<size_t>(nReferences) * Dp));
+  CU_TRY(pot, epi.reserve(static_cast<size_t>(w->W)));
+  CU_TRY(pot, cudaMemcpy2DAsync(ref.p, Dp * sizeof(double), reference_positions, D * sizeof(double), D * sizeof(double),
+                                nReferences, cudaMemcpyHostToDevice, pot->stream));
+  CU_TRY(pot, cudaMemcpyAsync(epi.p, epicentres, sizeof(int) * w->W, cudaMemcpyHostToDevice, pot->stream));
+  WalkerArrays wa;
+  memset(&wa, 0, sizeof(wa));
+  wa.W = static_cast<int>(w->W);
+  wa.N = static_cast<int>(w->N);
+  wa.D = w->D;
+  wa.Dp = w->Dp;
+  wa.pos = w->pos.p;
+  wa.mode = w->mode.p;
+  wa.dirty = w->dirty.p;
+  wa.mask = w->mask.p;
+  wa.box = w->box.p;
+  DisplaceArgs da;
+  da.ref = ref.p;
+  da.ref_stride = nReferences == 1 ? 0 : Dp;
+  da.epicentre = epi.p;
+  da.radius = radius;
+  da.sigma = sigma;
+  da.seed = seed;
+  da.first_id = first_walker_id;
+  const int threads = std::max(32, std::min<int>(kMaxThreadsPerWalker, static_cast<int>((w->N + 31) / 32 * 32)));
+#ifdef EONB200_EMU
+  EONB200_LAUNCH(k_displace, static_cast<unsigned>(w->W), 1, 0, pot->stream, wa, da);
+  (void)threads;
+#else
+  EONB200_LAUNCH(k_displace, static_cast<unsigned>(w->W), threads, 0, pot->stream, wa, da);
+#endif
+  pot->launches += 1;
+  CU_TRY(pot, cudaGetLastError());
+  CU_TRY(pot, cudaStreamSynchronize(pot->stream));
+  w->have_modes = true;
+  return 0;
+}
+
 int eonb200_walkers_set_active(EonB200Walkers *w, const int *active) {
   if (!w) return 1;
   EonB200Pot *pot = w->pot;

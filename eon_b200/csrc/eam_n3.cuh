@@ -247,6 +247,9 @@ __device__ __forceinline__ void n3_unpack(const int4 &h, const N3Box &bx, N3Lane
 // the one-step reduction (|k| <= ~1200 times the rounding of ln2/16) < 5e-15 relative: five orders below the parity
 // bar of 1e-10.  No underflow guard (PotParams::eam_fast_ok).
 __device__ __forceinline__ double exp_t16(double x, const double *T) {
+#ifdef EONB200_ABL_EXP  // timing ablation (never defined in the product build): no exponential
+  return fma(x, 1e-3, T[0]);
+#endif
   const double kInv = 23.083120654223414;    // 16 / ln 2
   const double kShift = 6755399441055744.0;  // 1.5 * 2^52
   const double kLn2_16 = 6.93147180559945309417e-01 / 16.0;
@@ -283,7 +286,11 @@ __device__ __forceinline__ double exp_t16(double x, const double *T) {
 // d = r_i - r_j folded by the image recorded at build time.  pxyb / pzwb: the position arrays as bytes.
 __device__ __forceinline__ void n3_vec(const unsigned char *pxyb, const unsigned char *pzwb, int c, const N3Lane &L,
                                        double xi, double yi, double zi, double &dx, double &dy, double &dz, double &wj) {
+#ifdef EONB200_ABL_GATHER
+  const int o = ((threadIdx.x & 255) << 4) + 0 * c;
+#else
   const int o = c & kN3OffMask;
+#endif
   const double2 jxy = *reinterpret_cast<const double2 *>(pxyb + o);
   const double2 jzw = *reinterpret_cast<const double2 *>(pzwb + o);
   dx = xi - jxy.x;
@@ -296,7 +303,11 @@ __device__ __forceinline__ void n3_vec(const unsigned char *pxyb, const unsigned
 }
 __device__ __forceinline__ void n3_vec3(const unsigned char *pxyb, const unsigned char *pzwb, int c, const N3Lane &L,
                                         double xi, double yi, double zi, double &dx, double &dy, double &dz) {
+#ifdef EONB200_ABL_GATHER  // timing ablation: conflict-free, lane-consecutive "gather"
+  const int o = ((threadIdx.x & 255) << 4) + 0 * c;
+#else
   const int o = c & kN3OffMask;
+#endif
   const double2 jxy = *reinterpret_cast<const double2 *>(pxyb + o);
   const double jz = *reinterpret_cast<const double *>(pzwb + o);
   dx = xi - jxy.x;

@@ -762,6 +762,98 @@ __global__ void __launch_bounds__(448, 2) k_walkers_x2(const PotParams *__restri
 }
 #endif
 
+// ---- displaced start geometries on the device (eon/displace.py:180-263) --------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): counter (atom, walker, 0, 0), key = the job's seed -- one independent stream
+// per (walker, atom), reproducible from the seed alone whatever the launch shape.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+  for (int r = 0; r < 10; r++) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0, p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0, n1 = static_cast<uint32_t>(p1);
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1, n3 = static_cast<uint32_t>(p0);
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+struct DisplaceArgs {
+  const double *ref;     // [W][Dp] or [Dp] (ref_stride 0): the minimum the walkers start from
+  size_t ref_stride;
+  const int *epicentre;  // [W] atom around which walker w is displaced
+  double radius, sigma;  // displace_radius, displace_magnitude ([Saddle Search], client/ParametersINI.cpp:1059-1064)
+  unsigned long long seed;
+  long long first_id;    // global id of walker 0 of this handle (walkers shard across ranks)
+};
+
+// One CTA per walker: every free axis of the epicentre and of the atoms within `radius` of it (minimum image) gets a
+// normal deviate of standard deviation sigma; positions = reference + displacement, mode = displacement / |.|.
+__global__ void __launch_bounds__(kMaxThreadsPerWalker) k_displace(WalkerArrays wa, DisplaceArgs da) {
+  __shared__ double red[kMaxWarps];
+  __shared__ double cell_sh[19];
+  const int w = blockIdx.x;
+  if (w >= wa.W) return;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 9; k++) cell_sh[k] = wa.box[k];
+    cell_sh[18] = invert3(cell_sh, cell_sh + 9) ? 1.0 : 0.0;
+  }
+  __syncthreads();
+  const double *H = cell_sh, *Hi = cell_sh + 9;
+  const bool cell_ok = cell_sh[18] != 0.0;
+  const double *ref = da.ref + static_cast<size_t>(w) * da.ref_stride;
+  double *pos = wa.pos + static_cast<size_t>(w) * wa.Dp, *mode = wa.mode + static_cast<size_t>(w) * wa.Dp;
+  const int e = da.epicentre[w];
+  const double ex = ref[3 * e], ey = ref[3 * e + 1], ez = ref[3 * e + 2];
+  const unsigned long long wid = static_cast<unsigned long long>(da.first_id + w);
+  double s = 0.0;
+  VLOOP(i, wa.N) {
+    double d[3] = {ref[3 * i] - ex, ref[3 * i + 1] - ey, ref[3 * i + 2] - ez};
+    if (cell_ok) {  // Matter::pbc (include/eon/Matter.h:42-50): fractional coordinates folded into [-1/2, 1/2)
+      double f[3];
+      for (int k = 0; k < 3; k++) {
+        f[k] = d[0] * Hi[k] + d[1] * Hi[3 + k] + d[2] * Hi[6 + k];
+        f[k] -= floor(f[k] + 0.5);
+      }
+      for (int k = 0; k < 3; k++) d[k] = f[0] * H[k] + f[1] * H[3 + k] + f[2] * H[6 + k];
+    }
+    const bool near = i == e || d[0] * d[0] + d[1] * d[1] + d[2] * d[2] < da.radius * da.radius;
+    double g[3] = {0.0, 0.0, 0.0};
+    if (near) {
+      uint32_t r[4];
+      philox4x32_10(static_cast<uint32_t>(i), static_cast<uint32_t>(wid), static_cast<uint32_t>(wid >> 32), 0u,
+                    static_cast<uint32_t>(da.seed), static_cast<uint32_t>(da.seed >> 32), r);
+      // Box-Muller on (0, 1) uniforms with 32 random bits each
+      const double u0 = (static_cast<double>(r[0]) + 0.5) * 2.3283064365386963e-10;
+      const double u1 = (static_cast<double>(r[1]) + 0.5) * 2.3283064365386963e-10;
+      const double u2 = (static_cast<double>(r[2]) + 0.5) * 2.3283064365386963e-10;
+      const double u3 = (static_cast<double>(r[3]) + 0.5) * 2.3283064365386963e-10;
+      const double ra = sqrt(-2.0 * log(u0)), rb = sqrt(-2.0 * log(u2));
+      g[0] = ra * cos(2.0 * kPi * u1);
+      g[1] = ra * sin(2.0 * kPi * u1);
+      g[2] = rb * cos(2.0 * kPi * u3);
+    }
+    for (int k = 0; k < 3; k++) {
+      const double dk = da.sigma * g[k] * wa.mask[3 * i + k];  // fixed axes stay put
+      mode[3 * i + k] = dk;
+      s += dk * dk;
+    }
+  }
+  const double nrm = sqrt(block_sum1(s, red));
+  const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+  VLOOP(k, wa.D) {
+    pos[k] = ref[k] + mode[k];
+    mode[k] *= inv;
+  }
+  if (threadIdx.x == 0) wa.dirty[w] = 1;
+}
+
 // Register-resident DFMA chain: the non-tensor FP64 roofline denominator.
 __global__ void k_dfma_peak(double *out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0,

@@ -135,6 +135,16 @@ class Walkers:
         return Harvest(st, it, fc, E, ev, cv, R.reshape(W, N, 3) if geometry else None,
                        M.reshape(W, N, 3) if geometry else None)
 
+    def displace(self, reference_positions, epicentres, radius: float, magnitude: float, seed: int,
+                 first_walker_id: int = 0):
+        """Displaced start geometries and modes for all W walkers, generated on the device (eon/displace.py:180-263):
+        no per-walker Python loop and no upload of W geometries.  `reference_positions`: [N, 3] shared or [W, N, 3];
+        `epicentres`: one atom index or [W]."""
+        ref = np.ascontiguousarray(reference_positions, dtype=np.float64).reshape(-1, 3 * self.N)
+        epi = np.ascontiguousarray(np.broadcast_to(np.asarray(epicentres, dtype=np.int32), (self.W,)))
+        self._check(self._lib.eonb200_walkers_displace(self._h, _dp(ref), ref.shape[0], _ip(epi), float(radius),
+                                                       float(magnitude), int(seed) & (2 ** 64 - 1), int(first_walker_id)))
+
     def set_active(self, active=None):
         """Mask for the following launches: walkers with active == 0 are left alone (``None``: all take part)."""
         if active is None:

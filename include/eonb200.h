@@ -225,6 +225,16 @@ EONB200_API int eonb200_walkers_harvest(EonB200Walkers *w, int *status, long *it
                                         double *energies, double *eigenvalues, double *convergence,
                                         double *positions, double *modes);
 
+/* Start geometries and initial modes made on the device (eon/displace.py:180-263, the displacement the server makes
+ * for every job it hands out): walker w is displaced around atom epicentres[w] -- that atom and every atom within
+ * `radius` of it (minimum image) get a normal deviate of standard deviation `sigma` on each free axis -- starting from
+ * reference_positions ([3N] shared when nReferences == 1, else [W][3N]); its mode is the normalised displacement.
+ * Random numbers: Philox4x32-10, counter (atom, global walker id = first_walker_id + w), key `seed`; the reference
+ * draws from numpy's generator, so displacements are reproducible from the seed here, not bit-identical to the server's. */
+EONB200_API int eonb200_walkers_displace(EonB200Walkers *w, const double *reference_positions, long nReferences,
+                                         const int *epicentres, double radius, double sigma, unsigned long long seed,
+                                         long first_walker_id);
+
 /* Which walkers take part in the following saddle_search / relax / displace launches: active [W], 0 = leave the walker
  * alone (its slot keeps its last results).  NULL: all.  ProcessSearchJob returns right after a failed saddle search
  * (client/ProcessSearchJob.cpp:184-186): the batched tail masks those walkers out of the two minimisations. */

@@ -29,8 +29,14 @@ else:
 nsets = len(sets)
 N = struct.n_atoms
 dev = torch.device("cuda", 0)
+libpath = opt.get("lib")  # another build of the library (timing ablations)
+lib = None
+if libpath:
+    import ctypes
+    from eon_b200 import _capi
+    lib = _capi.bind(ctypes.CDLL(os.path.abspath(libpath)))
 rot = int(opt.get("rot", 1))  # handles cycled (each with its own walkers and lists): inputs larger than L2, no flush
-pots = [B200Potential("eam", device=0, skin=skin, eam_pair_mode=mode, threads_per_walker=threads) for _ in range(rot)]
+pots = [B200Potential("eam", device=0, skin=skin, eam_pair_mode=mode, threads_per_walker=threads, lib=lib) for _ in range(rot)]
 pot = pots[0]
 d_R = torch.from_numpy(sets.reshape(nsets, W, 3 * N)).to(dev)
 d_Z = torch.from_numpy(np.broadcast_to(struct.atomic_nrs, (W, N)).copy()).to(dev)
