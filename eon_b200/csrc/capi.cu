@@ -375,18 +375,44 @@ int pick_n3_threads(const EonB200Pot *pot, long N, int lpa) {
 
 bool use_n3(const EonB200Pot *pot, long N) {
   return pot->cfg.kind == EONB200_POT_EAM && pot->cfg.eam_pair_mode != 1 &&
-         N <= kN3MaxAtoms && static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0)) + 8 * 8 * N <= pot->max_dyn_smem &&
+         N <= kN3MaxAtoms && static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0, 4)) + 8 * 8 * N <= pot->max_dyn_smem &&
          pot->cfg.skin > 0.0;
 }
 
-// Receiver slots the next launch reserves shared memory for: what the lists built so far needed plus a margin, or --
-// before the first build -- an estimate from the row capacity; never more than the SM has.
-int pick_slot_cap(const EonB200Pot *pot, const NlStore &nl, long N) {
-  long want = nl.slots_seen > 0 ? nl.slots_seen + nl.slots_seen / 16 + 64 : N * nl.K / 3;
-  const long room = (pot->max_dyn_smem - static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0))) / 8 - 16;
+// Receiver slots a launch wants shared memory for: what the lists built so far needed plus a margin, or -- before the
+// first build -- an estimate from the row capacity.
+long n3_slots_wanted(const NlStore &nl, long N) {
+  const long want = nl.slots_seen > 0 ? nl.slots_seen + nl.slots_seen / 16 + 64 : N * nl.K / 4;
+  return std::max<long>(want, 3 * N + 4);  // the raw coordinates land in the slot buffer
+}
+
+// Copies of every atom in the kernel's shared position arrays, as n3_shift = 4 + log2(copies): eight (conflict-free
+// gathers, eam_n3.cuh) when they fit beside the receiver slots, fewer for larger systems.  Lists carry the shift they
+// were built for (N3H_VALID); slots_seen only grows, so a store changes its shift at most three times.
+int pick_n3_shift(const EonB200Pot *pot, const NlStore &nl, long N) {
+#ifdef EONB200_EMU
+  (void)pot;
+  (void)nl;
+  (void)N;
+  return 5;  // (two copies: the emulation exercises the copy arithmetic)
+#else
+  static const int forced = getenv("EONB200_N3_REP") ? atoi(getenv("EONB200_N3_REP")) : 0;  // development aid: 1, 2, 4, 8
+  const long want = n3_slots_wanted(nl, N);
+  for (int shift = 7; shift > 4; shift--) {
+    if (forced > 0 && (16 << (shift - 4)) != 16 * forced) continue;
+    if (static_cast<long>(smem_bytes_n3(static_cast<int>(N), static_cast<int>(want), shift)) <= pot->max_dyn_smem) return shift;
+  }
+  return 4;
+#endif
+}
+
+// Receiver slots the next launch reserves shared memory for; never more than the SM has.
+int pick_slot_cap(const EonB200Pot *pot, const NlStore &nl, long N, int shift) {
+  long want = n3_slots_wanted(nl, N);
+  const long room = (pot->max_dyn_smem - static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0, shift))) / 8 - 16;
   want = std::min(want, room);
   // two CTAs per SM when that is within reach
-  const long two = ((227 * 1024) / 2 - 1024 - static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0))) / 8 - 16;
+  const long two = ((227 * 1024) / 2 - 1024 - static_cast<long>(smem_bytes_n3(static_cast<int>(N), 0, shift))) / 8 - 16;
   if (nl.slots_seen > 0 && nl.slots_seen <= two) want = std::min(want, two);
   want = std::max<long>(want, 3 * N + 4);  // the raw coordinates land in the slot buffer
   return static_cast<int>((std::max<long>(want, 0) + 15) / 16 * 16);
@@ -513,6 +539,7 @@ NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
   b.lo_build = nl.n3 ? nl.lo_build.p : nullptr;
   b.slot_cap = 0;
   b.n3_lpa = 1;
+  b.n3_shift = 4;
   return b;
 }
 
@@ -631,10 +658,12 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
     NlBatch view = nl_view(pot, nl);
     if (n3) {
-      slot_cap = pick_slot_cap(pot, nl, N);
-      fused_smem = smem_bytes_n3(static_cast<int>(N), slot_cap);
+      const int shift = pick_n3_shift(pot, nl, N);
+      slot_cap = pick_slot_cap(pot, nl, N, shift);
+      fused_smem = smem_bytes_n3(static_cast<int>(N), slot_cap, shift);
       view.slot_cap = slot_cap;
       view.n3_lpa = a.lpa;
+      view.n3_shift = shift;
     }
     // one launch (or launch pair) over Sc systems of the view vw / the arrays of ac, on stream st
     auto launch = [&](const NlBatch &vw, const ForceBatchArgs &ac, long Sc, cudaStream_t st) -> int {
@@ -653,6 +682,8 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
           EONB200_LAUNCH((k_eam_n3_t<448, 2>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
         else if (fused_threads <= 512 && two)
           EONB200_LAUNCH((k_eam_n3_t<512, 2>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
+        else if (fused_threads <= 416)  // (one CTA per SM: up to 152 registers per thread)
+          EONB200_LAUNCH((k_eam_n3_t<416, 1>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
         else if (fused_threads <= 512)
           EONB200_LAUNCH((k_eam_n3_t<512, 1>), grid, fused_threads, fused_smem, st, pot->hp, pot->dP.p, vw, ac);
         else if (fused_threads <= 800)
@@ -907,6 +938,8 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<512, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              pot->max_dyn_smem) == cudaSuccess &&
+         cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<416, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&
          cudaFuncSetAttribute(reinterpret_cast<const void *>(k_eam_n3_t<800, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize,
                               pot->max_dyn_smem) == cudaSuccess &&

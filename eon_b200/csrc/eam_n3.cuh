@@ -38,13 +38,44 @@ constexpr int kN3UD = EONB200_N3_UD;   // pairs per iteration of the density loo
 constexpr int kN3UF = EONB200_N3_UF;   // pairs per iteration of the force loops; owned / received rows are padded to this
 constexpr int kN3Slack = 8;  // list rows a loop may request beyond a row's end (the allocations carry this many extra)
 
-// List words of this kernel: bits 0..15 = 16 j, the byte offset of atom j in the two position arrays (x, y) and
-// (z, F') -- 16-byte strides, so that a gather over random atoms uses every bank -- (j <= 2047; the ghost atom is j = N); bits 16, 17, 18 = "add this atom's box fold along x, y, z" -- an atom in the upper half of the
-// box only ever meets images at -L, one in the lower half at +L (EAM.cpp:152-172 with wrapped coordinates), so the
-// sign is a property of the lane (N3Lane::sL*), not of the pair.
-constexpr int kN3OffMask = 0xffff;
-constexpr int kN3FoldX = 1 << 16, kN3FoldY = 1 << 17, kN3FoldZ = 1 << 18;
+// List words of this kernel: bits n3_shift.. = j << n3_shift, the byte offset of atom j's first copy in the two position
+// arrays (x, y) and (z, F') (j <= 2047; the ghost atom is j = N); bits 0, 1, 2 = "add this atom's box fold along x, y, z"
+// -- an atom in the upper half of the box only ever meets images at -L, one in the lower half at +L (EAM.cpp:152-172
+// with wrapped coordinates), so the sign is a property of the lane (N3Lane::sL*), not of the pair.
+//
+// The position arrays hold `rep` = 8 (4, 2, 1 when shared memory is short: SysView::n3_shift = 4 + log2 rep) copies of
+// every atom, 16 bytes each, one per 16-byte bank group of shared memory (128 bytes per atom and array), and lane l
+// always reads copy l & (rep - 1): the eight lanes a 128-bit shared load serves per wavefront then hit eight different
+// bank groups WHATEVER atoms they ask for.  A gather over random atoms costs the minimum of four wavefronts; with one
+// copy it cost 9 - 12 (ncu, profiles/r2_n3_*: 68 % of the kernel's shared-memory wavefronts were bank conflicts of
+// these gathers, and the L1 data stage was its busiest unit).
+constexpr int kN3FoldX = 1, kN3FoldY = 2, kN3FoldZ = 4;
 constexpr int kN3MaxAtoms = 2047;
+__device__ __forceinline__ int n3_code_atom(int code, int shift) { return static_cast<unsigned>(code) >> shift; }
+// what N3H_VALID holds for lists built for this launch shape
+__device__ __forceinline__ int n3_valid_tag(const SysView &sys) { return sys.n3_lpa | (sys.n3_shift << 8); }
+// byte offset of this lane's copy inside an atom's 16 rep bytes
+__device__ __forceinline__ int n3_lane_off(int shift) {
+#ifdef EONB200_EMU
+  (void)shift;
+  return 0;
+#else
+  return (static_cast<int>(threadIdx.x) << 4) & ((1 << shift) - 1);
+#endif
+}
+// all copies of atom i (copy order rotated by the lane, so that the lanes of a warp store into different bank groups)
+__device__ __forceinline__ void n3_store_xy(double2 *pxy, int shift, int i, double x, double y) {
+  const int rep = 1 << (shift - 4);
+  for (int k = 0; k < rep; k++) pxy[(i << (shift - 4)) + ((k + static_cast<int>(threadIdx.x)) & (rep - 1))] = make_double2(x, y);
+}
+__device__ __forceinline__ void n3_store_zw(double2 *pzw, int shift, int i, double z, double w) {
+  const int rep = 1 << (shift - 4);
+  for (int k = 0; k < rep; k++) pzw[(i << (shift - 4)) + ((k + static_cast<int>(threadIdx.x)) & (rep - 1))] = make_double2(z, w);
+}
+__device__ __forceinline__ void n3_store_w(double2 *pzw, int shift, int i, double w) {
+  const int rep = 1 << (shift - 4);
+  for (int k = 0; k < rep; k++) pzw[(i << (shift - 4)) + ((k + static_cast<int>(threadIdx.x)) & (rep - 1))].y = w;
+}
 
 // hl_hdr words of a walker
 enum { N3H_SLOTS = 0, N3H_VALID = 1, N3H_ROWS = 2, N3H_ROWZ = 3, N3H_CONFLICT = 4 };  // VALID: 0, or the lists' lanes per atom
@@ -52,8 +83,16 @@ enum { N3H_SLOTS = 0, N3H_VALID = 1, N3H_ROWS = 2, N3H_ROWZ = 3, N3H_CONFLICT = 
 // The atom that evaluates the unordered pair {i, j}: the one with the shorter row (surface atoms own all their pairs
 // with bulk atoms, so that every atom owns about the same number); between atoms of equal row length the lower index
 // when i + j is even, the higher when odd.
+#ifndef EONB200_N3_OWNER
+#define EONB200_N3_OWNER 1
+#endif
 __device__ __forceinline__ bool n3_owner(int i, int j, int deg_i, int deg_j) {
+#if EONB200_N3_OWNER == 0
   if (deg_i != deg_j) return deg_i < deg_j;
+#elif EONB200_N3_OWNER == 2
+  if (deg_i + 8 < deg_j) return true;
+  if (deg_j + 8 < deg_i) return false;
+#endif
   return (i < j) == (((i + j) & 1) == 0);
 }
 __device__ __forceinline__ int n3_deg(const SysView &sys, int i) {
@@ -103,7 +142,8 @@ __device__ inline void n3_build(const SysView &sys, const Smem &sm, const PotPar
     sys.atom_lane[i] = rank;
   }
   __syncthreads();
-  const int ghost = N << 4;
+  const int shift = sys.n3_shift;
+  const int ghost = N << shift;
   int rows = 0;  // rows of the owner / receiver arrays in use
   for (int i = tid; i < N; i += nt) {
     const size_t col0 = static_cast<size_t>(sys.atom_lane[i]) * lpa;
@@ -116,7 +156,7 @@ __device__ inline void n3_build(const SysView &sys, const Smem &sm, const PotPar
       if (j == i) continue;  // a self image only exists in boxes the fast path never sees
       const int id = static_cast<unsigned>(code) >> kNbrIndexBits;  // (fx + 1) + 3 (fy + 1) + 9 (fz + 1), pack_mic
       const int f[3] = {id % 3 - 1, (id / 3) % 3 - 1, id / 9 - 1};   // sh27: offset added to r_i - r_j is -f L
-      int w = j << 4;
+      int w = j << shift;
       for (int a = 0; a < 3; a++) {
         if (f[a] != 0) w |= kN3FoldX << a;
         if (f[a] > 0) minus |= 1 << a;
@@ -140,7 +180,7 @@ __device__ inline void n3_build(const SysView &sys, const Smem &sm, const PotPar
         sys.own_cs[k * step + col0 + h] = make_int2(ghost, -1);
         sys.own_ab[k * step + col0 + h] = make_double2(0.0, 0.0);
       }
-      for (int k = nr_h; k < nr_pad && k < krows; k++) sys.recv_code[k * step + col0 + h] = i << 4;  // zero-length pairs
+      for (int k = nr_h; k < nr_pad && k < krows; k++) sys.recv_code[k * step + col0 + h] = i << shift;  // zero-length pairs
       sys.lhdr[col0 + h] = make_int4(nso_h | (nown_h << 16), nr_h, 0, i | (minus << 24));
       sys.roff[col0 + h] = nr_h;
       rows = max(rows, max(nown_pad, nr_pad));
@@ -193,11 +233,11 @@ __device__ inline void n3_build(const SysView &sys, const Smem &sm, const PotPar
       const int code = sys.own_cs[k * step + col].x;
       int slot = total;
       if (k < nown_h) {
-        const size_t cj = static_cast<size_t>(sys.atom_lane[(code & kN3OffMask) >> 4]) * lpa;
+        const size_t cj = static_cast<size_t>(sys.atom_lane[n3_code_atom(code, shift)]) * lpa;
         int nrj = 0;
         for (int q = 0; q < lpa; q++) nrj += sys.lhdr[cj + q].y;
         int r = 0;
-        while (r < nrj && ((sys.recv_code[(r / lpa) * step + cj + r % lpa] & kN3OffMask) >> 4) != i) r++;
+        while (r < nrj && n3_code_atom(sys.recv_code[(r / lpa) * step + cj + r % lpa], shift) != i) r++;
         if (r >= nrj) r = 0;
         slot = sys.roff[cj + r % lpa] + r / lpa;
       }
@@ -215,7 +255,7 @@ __device__ inline void n3_build(const SysView &sys, const Smem &sm, const PotPar
     atomicMax(&sys.stats[3], static_cast<unsigned long long>(total + kN3UF));
   }
   __syncthreads();
-  if (tid == 0 && ld_cg(sys.hl_hdr + N3H_ROWS) <= krows) sys.hl_hdr[N3H_VALID] = lpa;
+  if (tid == 0 && ld_cg(sys.hl_hdr + N3H_ROWS) <= krows) sys.hl_hdr[N3H_VALID] = n3_valid_tag(sys);
   __syncthreads();
 }
 
@@ -225,17 +265,20 @@ struct N3Lane {  // what one lane carries through the passes for one of its atom
   int atom;              // the atom this lane works for (lanes take the atoms by rank, see n3_build)
   int nso, nown, nrecv;  // owned sure-in pairs, owned pairs, received pairs
   int rbase;             // its first slot
+  int off, mask;         // n3_lane_off(): the copy of the position arrays this lane reads; mask of a code's offset bits
 };
 
 struct N3Box {
   double Lx, Ly, Lz;
 };
 
-__device__ __forceinline__ void n3_unpack(const int4 &h, const N3Box &bx, N3Lane &L) {
+__device__ __forceinline__ void n3_unpack(const int4 &h, const N3Box &bx, int shift, N3Lane &L) {
   L.nso = h.x & 0xffff;
   L.nown = static_cast<unsigned>(h.x) >> 16;
   L.nrecv = h.y;
   L.rbase = h.z;
+  L.off = n3_lane_off(shift);
+  L.mask = ~((1 << shift) - 1);
   L.atom = h.w & 0xffffff;
   L.sLx = (h.w & (1 << 24)) ? -bx.Lx : bx.Lx;
   L.sLy = (h.w & (1 << 25)) ? -bx.Ly : bx.Ly;
@@ -289,7 +332,7 @@ __device__ __forceinline__ void n3_vec(const unsigned char *pxyb, const unsigned
 #ifdef EONB200_ABL_GATHER
   const int o = ((threadIdx.x & 255) << 4) + 0 * c;
 #else
-  const int o = c & kN3OffMask;
+  const int o = (c & L.mask) | L.off;
 #endif
   const double2 jxy = *reinterpret_cast<const double2 *>(pxyb + o);
   const double2 jzw = *reinterpret_cast<const double2 *>(pzwb + o);
@@ -306,7 +349,7 @@ __device__ __forceinline__ void n3_vec3(const unsigned char *pxyb, const unsigne
 #ifdef EONB200_ABL_GATHER  // timing ablation: conflict-free, lane-consecutive "gather"
   const int o = ((threadIdx.x & 255) << 4) + 0 * c;
 #else
-  const int o = c & kN3OffMask;
+  const int o = (c & L.mask) | L.off;
 #endif
   const double2 jxy = *reinterpret_cast<const double2 *>(pxyb + o);
   const double jz = *reinterpret_cast<const double *>(pzwb + o);
@@ -332,8 +375,9 @@ __device__ __forceinline__ void n3_density(const N3K &K, const SysView &sys, con
   const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
   const int2 *oc = sys.own_cs + t + kN3UD * step;
   double2 *oab = sys.own_ab + t;
-  const double2 pixy = sm.pxy[L.atom];
-  const double piz = sm.pzw[L.atom].x;
+  const int own = (L.atom << sys.n3_shift) | L.off;
+  const double2 pixy = *reinterpret_cast<const double2 *>(pxyb + own);
+  const double piz = *reinterpret_cast<const double *>(pzwb + own);
   double dens = 0.0, e_acc = 0.0;
   int npairs = 0;
   const int nown = L.nown, nso = L.nso;
@@ -426,8 +470,9 @@ __device__ __forceinline__ void n3_force_own(const SysView &sys, const Smem &sm,
   const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
   const int2 *oc = sys.own_cs + t + kN3UF * step;
   const double2 *oab = sys.own_ab + t + kN3UF * step;
-  const double2 pixy = sm.pxy[L.atom];
-  const double piz = sm.pzw[L.atom].x;
+  const int own = (L.atom << sys.n3_shift) | L.off;
+  const double2 pixy = *reinterpret_cast<const double2 *>(pxyb + own);
+  const double piz = *reinterpret_cast<const double *>(pzwb + own);
   const double ndfi = -L.dfd;
   double fx = 0.0, fy = 0.0, fz = 0.0;
   const int nown = L.nown;
@@ -471,8 +516,9 @@ __device__ __forceinline__ void n3_force_recv(const SysView &sys, const Smem &sm
   const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
   const int *rc = sys.recv_code + t + kN3UF * step;
   const double *sl = sm.slots + L.rbase;
-  const double2 pixy = sm.pxy[L.atom];
-  const double piz = sm.pzw[L.atom].x;
+  const int own = (L.atom << sys.n3_shift) | L.off;
+  const double2 pixy = *reinterpret_cast<const double2 *>(pxyb + own);
+  const double piz = *reinterpret_cast<const double *>(pzwb + own);
   double fx = L.fx, fy = L.fy, fz = L.fz;
   const int nr = L.nrecv;
   for (int k0 = 0; k0 < nr; k0 += kN3UF) {
@@ -536,14 +582,18 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
   int2 cq[kN3UF];
   double2 wq[kN3UF];
   int rq[kN3UF];
-  n3_unpack(h0, bx, L);
+  n3_unpack(h0, bx, sys.n3_shift, L);
   L.rho_own = 0.0;
+  // staging row of the outgoing forces (the cold paths' position block, idle here): element `fhead` is 16-byte aligned
+  // in shared memory exactly when it is in the caller's row, as a bulk copy wants
+  const int fhead = (reinterpret_cast<uintptr_t>(F) & 15u) ? 1 : 0;
+  double *fstage = reinterpret_cast<double *>(sm.pos) + fhead;
   if (SINGLE) {
     if (tid < C) n3_density(K, sys, sm, tid, L, cd, acc);
   } else {
     for (int t = tid; t < C; t += nt) {
       if (t != tid) {
-        n3_unpack(ld_cg(sys.lhdr + t), bx, L);
+        n3_unpack(ld_cg(sys.lhdr + t), bx, sys.n3_shift, L);
 #pragma unroll
         for (int u = 0; u < kN3UD; u++) cd[u] = ld_cg(sys.own_cs + t + u * step);
       }
@@ -551,6 +601,7 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
       sys.dfd[t] = L.rho_own;
     }
   }
+  phase_clock_last(clk, 5);
   if (SINGLE && tid < C) {  // first words of the two force passes
     n3_own_prefetch(sys, tid, cq, wq);
     n3_recv_prefetch(sys, tid, rq);
@@ -565,24 +616,24 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
       L.dfd = eam_dembed(dc, part);
       if (first) {
         acc[0] += eam_embed(c, part);
-        sm.pzw[L.atom].y = L.dfd;
+        n3_store_w(sm.pzw, sys.n3_shift, L.atom, L.dfd);
       }
     }
   } else {
     for (int t = tid; t < C; t += nt) {
-      n3_unpack(ld_cg(sys.lhdr + t), bx, L);
+      n3_unpack(ld_cg(sys.lhdr + t), bx, sys.n3_shift, L);
       L.rho_own = sys.dfd[t];
       const double dens = n3_rho_part(sm, L);
       acc[0] += eam_embed(c, dens);
-      sm.pzw[L.atom].y = eam_dembed(dc, dens);
+      n3_store_w(sm.pzw, sys.n3_shift, L.atom, eam_dembed(dc, dens));
     }
   }
   __syncthreads();
   phase_clock(clk, 8);
   for (int t = tid; t < C; t += nt) {
     if (!SINGLE) {
-      n3_unpack(ld_cg(sys.lhdr + t), bx, L);
-      L.dfd = sm.pzw[L.atom].y;
+      n3_unpack(ld_cg(sys.lhdr + t), bx, sys.n3_shift, L);
+      L.dfd = sm.pzw[L.atom << (sys.n3_shift - 4)].y;
       n3_own_prefetch(sys, t, cq, wq);
     }
     n3_force_own(sys, sm, t, L, cq, wq);
@@ -592,6 +643,7 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
       F[3 * L.atom + 2] = L.fz;
     }
   }
+  phase_clock_last(clk, 11);
   __syncthreads();
   phase_clock(clk, 9);
   if (SINGLE) {
@@ -604,14 +656,16 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
       L.fy = n3_pair_sum(L.fy);
       L.fz = n3_pair_sum(L.fz);
     }
+    // Forces leave through shared memory: lanes hold atoms in rank order, so direct stores would be 3 N scattered
+    // 8-byte writes; one bulk copy moves the walker's row instead (issued below, after the energy reduction's barrier).
     if (tid < C && first) {
-      F[3 * L.atom] = L.fx;
-      F[3 * L.atom + 1] = L.fy;
-      F[3 * L.atom + 2] = L.fz;
+      fstage[3 * L.atom] = L.fx;
+      fstage[3 * L.atom + 1] = L.fy;
+      fstage[3 * L.atom + 2] = L.fz;
     }
   } else {
     for (int t = tid; t < C; t += nt) {
-      n3_unpack(ld_cg(sys.lhdr + t), bx, L);
+      n3_unpack(ld_cg(sys.lhdr + t), bx, sys.n3_shift, L);
       L.fx = F[3 * L.atom];
       L.fy = F[3 * L.atom + 1];
       L.fz = F[3 * L.atom + 2];
@@ -622,7 +676,17 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
       F[3 * L.atom + 2] = L.fz;
     }
   }
-  cta_sum2_to0(acc, sm.red);
+  phase_clock(clk, 15);
+  phase_clock_last(clk, 13);
+  cta_sum2_to0(acc, sm.red);  // (its barrier also publishes fstage)
+  phase_clock(clk, 14);
+  if (SINGLE && tid == 32 % nt) {
+    const int D = 3 * sys.N;
+    const int body = (D - fhead) & ~1;
+    if (body > 0) bulk_s2g(F + fhead, fstage + fhead, static_cast<uint32_t>(body) * 8u);
+    if (fhead) F[0] = fstage[0];
+    if (fhead + body < D) F[D - 1] = fstage[D - 1];
+  }
   if (tid == 0) {
     *U = acc[0];
     atomicAdd(&sys.stats[2], 2ULL * static_cast<unsigned long long>(acc[1]));  // ordered in-cutoff pairs
@@ -632,7 +696,7 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
 __device__ __forceinline__ void n3_cold_views(const FusedCold &fc, SysView &sys, Smem &sm) {
   EONB200_DYN_SMEM(smem_raw);
   sys = batch_sys(fc.nl, fc.a, blockIdx.y);
-  sm = carve_smem_n3(smem_raw, fc.a.N, fc.a.maxCells, sys.cellscratch);
+  sm = carve_smem_n3(smem_raw, fc.a.N, fc.a.maxCells, sys.cellscratch, sys.n3_shift);
 }
 
 // The ordered-pair lane functions (filter -> density -> force over the walker's full rows, potentials.cuh) inside this
@@ -693,7 +757,10 @@ __device__ EONB200_NOINLINE int eam_n3_cold(FusedCold *fc, const NlBatch *nl, co
   n3_cold_views(*fc, sys, sm);
   const PotParams &P = *Pp;
   const int N = sys.N;
-  for (int i = tid; i < N; i += nt) sm.pos[i] = make_double4(sm.pxy[i].x, sm.pxy[i].y, sm.pzw[i].x, 0.0);
+  for (int i = tid; i < N; i += nt) {
+    const int i0 = i << (sys.n3_shift - 4);
+    sm.pos[i] = make_double4(sm.pxy[i0].x, sm.pxy[i0].y, sm.pzw[i0].x, 0.0);
+  }
   for (int k = tid; k < 128; k += nt) sm.exp_tab[k] = P.exp_tab[k];
   const double Lbox[3] = {sys.box[0], sys.box[4], sys.box[8]};
   fill_sh27(sm, Lbox[0], Lbox[1], Lbox[2]);
@@ -717,7 +784,7 @@ __device__ EONB200_NOINLINE int eam_n3_cold(FusedCold *fc, const NlBatch *nl, co
   const int h_valid = ld_cg(sys.hl_hdr + N3H_VALID);
   const int h_rowz = ld_cg(sys.hl_hdr + N3H_ROWZ);
   const bool rebuild = fc->a.force_rebuild != 0 || !have || P.skin <= 0.0 || !(disp2 <= lim * lim) ||
-                       h_valid != sys.n3_lpa || (h_rowz >> 8) != z0;
+                       h_valid != n3_valid_tag(sys) || (h_rowz >> 8) != z0;
   const bool near_build = rebuild || disp2 <= dstar * dstar;  // a fresh list is built from these very positions
   if (rebuild) {
     __syncthreads();
@@ -740,7 +807,7 @@ __device__ EONB200_NOINLINE int eam_n3_cold(FusedCold *fc, const NlBatch *nl, co
     if (tid == 0) fc->a.U[blockIdx.y] = nan("");
     return 0;
   }
-  const bool fits = ld_cg(sys.hl_hdr + N3H_VALID) == sys.n3_lpa && ld_cg(sys.hl_hdr + N3H_SLOTS) <= sys.slot_cap &&
+  const bool fits = ld_cg(sys.hl_hdr + N3H_VALID) == n3_valid_tag(sys) && ld_cg(sys.hl_hdr + N3H_SLOTS) <= sys.slot_cap &&
                     ld_cg(sys.hl_hdr + N3H_CONFLICT) == 0 && N <= kN3MaxAtoms;
   if (!near_build || !fits) {
     eam_n3_ordered(fc, r0, near_build);
@@ -757,8 +824,9 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   const int s = blockIdx.y;
   __shared__ FusedCold cold;  // filled only when the cold path is about to run
   __shared__ double coef[18];  // embedding polynomial and its derivative (EamRowDev::c, dc) of the walker's element
+  __shared__ double invL[3];   // 1 / box length per axis
   const SysView sys = batch_sys(nl, a, s);
-  const Smem sm = carve_smem_n3(smem_raw, a.N, a.maxCells, sys.cellscratch);
+  const Smem sm = carve_smem_n3(smem_raw, a.N, a.maxCells, sys.cellscratch, sys.n3_shift);
   const int N = a.N, tid = threadIdx.x, nt = blockDim.x;
   const size_t step = static_cast<size_t>(sys.Np) * sys.n3_lpa;
   long long *clk = a.clocks ? a.clocks + static_cast<size_t>(s) * 16 : nullptr;
@@ -810,6 +878,7 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   bx.Ly = sys.box[4];
   bx.Lz = sys.box[8];
   for (int k = tid; k < 16; k += nt) sm.t16[k] = P.exp_t16[k];
+  for (int k = tid; k < 3; k += nt) invL[k] = 1.0 / sys.box[4 * k];  // (one division per axis, not one per thread)
   const double lo[3] = {ld_cg(sys.lo_build), ld_cg(sys.lo_build + 1), ld_cg(sys.lo_build + 2)};
   const double Lb[3] = {ld_cg(sys.box_build), ld_cg(sys.box_build + 4), ld_cg(sys.box_build + 8)};  // (the fast path
   // is for orthorhombic use: EAM.cpp:31 reads the diagonal only; the cold path compares the whole cell)
@@ -838,7 +907,7 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   const int z0 = hdr.w >> 8;
   const double dstar = 0.25 * P.skin;
   const double Lk[3] = {bx.Lx, bx.Ly, bx.Lz};
-  const double iL[3] = {1.0 / bx.Lx, 1.0 / bx.Ly, 1.0 / bx.Lz};
+  const double iL[3] = {invL[0], invL[1], invL[2]};
   double disp2_max = 0.0;
   int odd = 0;
   for (int i = tid; i < N; i += nt) {
@@ -857,14 +926,14 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
       const double d = q[k] - rb[k];
       d2 = fma(d, d, d2);
     }
-    sm.pxy[i] = make_double2(q[0], q[1]);
-    sm.pzw[i] = make_double2(q[2], 0.0);
+    n3_store_xy(sm.pxy, sys.n3_shift, i, q[0], q[1]);
+    n3_store_zw(sm.pzw, sys.n3_shift, i, q[2], 0.0);
     disp2_max = fmax(disp2_max, d2);
     if (zz != z0) odd |= 1;
   }
   if (tid == 0) {  // the ghost atom of the row padding
-    sm.pxy[N] = make_double2(1e150, 1e150);
-    sm.pzw[N] = make_double2(1e150, 0.0);
+    n3_store_xy(sm.pxy, sys.n3_shift, N, 1e150, 1e150);
+    n3_store_zw(sm.pzw, sys.n3_shift, N, 1e150, 0.0);
   }
   if (!(disp2_max <= dstar * dstar)) odd |= 1;
   const double need = 2.0 * P.rc_list + P.skin;  // stored folds stay the reference's minimum image
@@ -872,7 +941,7 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   const int r0h = hdr.w & 0xff;
   // The common case is decided by ONE barrier; anything else takes the out-of-line path.
   const bool uniform_ok = a.force_rebuild == 0 && P.skin > 0.0 && tab_ok && P.eam_fast_ok != 0 &&
-                          hdr.y == sys.n3_lpa && hdr.x <= sys.slot_cap && r0h < P.n_rows && N <= kN3MaxAtoms &&
+                          hdr.y == n3_valid_tag(sys) && hdr.x <= sys.slot_cap && r0h < P.n_rows && N <= kN3MaxAtoms &&
                           Lb[0] == bx.Lx && Lb[1] == bx.Ly && Lb[2] == bx.Lz;
   {
     const int rq = min(r0h, P.n_rows - 1);
@@ -896,8 +965,8 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
     }
     for (int i = tid; i < N; i += nt) {  // (a rebuild prepared the positions anew)
       const double4 p = sm.pos[i];
-      sm.pxy[i] = make_double2(p.x, p.y);
-      sm.pzw[i] = make_double2(p.z, 0.0);
+      n3_store_xy(sm.pxy, sys.n3_shift, i, p.x, p.y);
+      n3_store_zw(sm.pzw, sys.n3_shift, i, p.z, 0.0);
     }
     __syncthreads();
   }

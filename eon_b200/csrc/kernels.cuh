@@ -189,6 +189,16 @@ __device__ __forceinline__ void phase_clock(long long *clk, int slot) {
 #endif
 }
 
+// Latest arrival of any warp of the CTA at this point (slot must start at 0: the host clears the buffer).
+__device__ __forceinline__ void phase_clock_last(long long *clk, int slot) {
+#ifndef EONB200_EMU
+  if (clk && (threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned long long *>(clk + slot), static_cast<unsigned long long>(clock64()));
+#else
+  (void)clk;
+  (void)slot;
+#endif
+}
+
 constexpr int kConvAtoms = 2;  // atoms a thread converts per round of the prologue
 
 struct FusedFast {  // CTA-uniform inputs of the fast path

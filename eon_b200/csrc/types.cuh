@@ -99,6 +99,7 @@ struct NlBatch {
   double *lo_build; // [S][4]     coordinate shift (EAM.cpp:56-83) the lists were built under
   int slot_cap;     // receiver slots the launch has shared memory for
   int n3_lpa;       // lanes (list columns) per atom of this launch, 1 or 2
+  int n3_shift;     // 4 + log2(copies of every atom in the kernel's shared position arrays): 7, 6, 5 or 4
 };
 
 // One system as seen by its CTA.
@@ -137,6 +138,7 @@ struct SysView {
   double *lo_build;
   int slot_cap;
   int n3_lpa;
+  int n3_shift;
 };
 
 __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, const double *R, const int *Z,
@@ -180,6 +182,7 @@ __device__ __forceinline__ SysView make_sys(const NlBatch &nl, int s, int N, con
   v.lo_build = nl.lo_build ? nl.lo_build + static_cast<size_t>(s) * 4 : nullptr;
   v.slot_cap = nl.slot_cap;
   v.n3_lpa = nl.n3_lpa;
+  v.n3_shift = nl.n3_shift;
   return v;
 }
 
@@ -258,8 +261,8 @@ struct Smem {
   double *rho;       // (unused)
   double *facc;      // (unused)
   // Newton's-third-law EAM kernel (eam_n3.cuh)
-  double2 *pxy;      // [N + 1] (x, y) of the prepared positions: a 16-byte stride spreads a gather over all banks
-  double2 *pzw;      // [N + 1] (z, F'(rho))
+  double2 *pxy;      // [(N + 1) kN3Rep] (x, y) of the prepared positions, kN3Rep copies per atom (one per 16-byte bank group)
+  double2 *pzw;      // [(N + 1) kN3Rep] (z, F'(rho))
   double *t16;       // [16] 2^(j/16), one 128-byte line: any lookup of a warp is conflict free
   double *slots;     // [slot_cap] receiver slots: the partner's share of a pair (g, then the force scalar); landing
                      //            zone of the raw coordinates before that (slot_cap >= 3N + 4)
@@ -394,18 +397,18 @@ __device__ inline Smem carve_smem_fused(unsigned char *base, int N, int maxCells
 
 // Newton's-third-law EAM kernel: the fused kernel's layout (its cold paths and its ordered-pair lane functions run
 // unchanged) followed by the split position arrays, the exp table line and the receiver slots.
-__host__ __device__ inline size_t smem_bytes_n3(int N, int slot_cap) {
-  return align_up(smem_bytes_fused(N), 128) + 2 * align_up(sizeof(double2) * (static_cast<size_t>(N) + 1), 128) + 128 +
+__host__ __device__ inline size_t smem_bytes_n3(int N, int slot_cap, int shift) {  // shift: 4 + log2(copies per atom)
+  return align_up(smem_bytes_fused(N), 128) + 2 * align_up((static_cast<size_t>(N) + 1) << shift, 128) + 128 +
          align_up(sizeof(double) * static_cast<size_t>(slot_cap), 128);
 }
 
-__device__ inline Smem carve_smem_n3(unsigned char *base, int N, int maxCells, int *scratch) {
+__device__ inline Smem carve_smem_n3(unsigned char *base, int N, int maxCells, int *scratch, int shift) {
   Smem s = carve_smem_fused(base, N, maxCells, scratch);
   size_t o = align_up(smem_bytes_fused(N), 128);
   s.pxy = reinterpret_cast<double2 *>(base + o);
-  o += align_up(sizeof(double2) * (static_cast<size_t>(N) + 1), 128);
+  o += align_up((static_cast<size_t>(N) + 1) << shift, 128);
   s.pzw = reinterpret_cast<double2 *>(base + o);
-  o += align_up(sizeof(double2) * (static_cast<size_t>(N) + 1), 128);
+  o += align_up((static_cast<size_t>(N) + 1) << shift, 128);
   s.t16 = reinterpret_cast<double *>(base + o);
   o += 128;
   s.slots = reinterpret_cast<double *>(base + o);

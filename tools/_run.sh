@@ -1,10 +1,2 @@
-python -m pytest tests/test_search.py tests/test_neb.py tests/test_process_search.py -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 10 --warmup 3 --no-c3 --no-c4 --no-c5 --no-cpu > gpurun_out/r2b_bench.json 2> gpurun_out/r2b_bench.err; echo rc=$?; tail -3 gpurun_out/r2b_bench.err
-python - <<EOF2
-import json
-d=json.load(open("gpurun_out/r2b_bench.json"))
-s=d["search"]
-print({k:v for k,v in s.items() if k not in ("config","dimer","streamed")})
-print("dimer", s["dimer"])
-print("streamed", s["streamed"])
-EOF2
+for r in 8 1 4; do echo "== rep $r"; EONB200_N3_REP=$r python tools/eam_bench.py clocks > gpurun_out/r2g_rep$r.txt 2>&1; grep -v "^  ctas\|list decision\|density barrier\|exit  " gpurun_out/r2g_rep$r.txt; done
+echo "== rep 8 steps 100"; python tools/eam_bench.py steps=100 | head -1

@@ -85,6 +85,10 @@ if "clocks" in flags:
                 d = (c[:, slot] - c[:, prev]) / 1.965e3
                 print("  %-22s med %.2f p90 %.2f max %.2f us" % (nm, np.median(d), np.percentile(d, 90), d.max()))
             prev = slot
+        for a_, b_, nm in [(12, 5, "last warp leaves density"), (8, 11, "last warp leaves own force"), (9, 15, "thread 0 leaves recv force"),
+                           (9, 13, "last warp leaves recv force"), (13, 14, "energy reduction"), (14, 10, "exit")]:
+            d = (c[:, b_] - c[:, a_]) / 1.965e3
+            print("  [%-28s] med %.2f p90 %.2f max %.2f us" % (nm, np.median(d), np.percentile(d, 90), d.max()))
         tot = (c[:, 10] - c[:, 2]) / 1.965e3
         print("  cta total med %.1f max %.1f; end (start + total) max %.1f us" % (np.median(tot), tot.max(), (start_us + tot).max()))
     smid = c[:, 1].astype(int)
