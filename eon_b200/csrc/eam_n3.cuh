@@ -545,7 +545,7 @@ __device__ __forceinline__ void n3_force_recv(const SysView &sys, const Smem &sm
 }
 
 // Sum of two per-thread values over the CTA; thread 0 gets the result.  One barrier.
-__device__ __forceinline__ void cta_sum2_to0(double (&v)[2], double *scratch) {
+__device__ __forceinline__ void cta_sum2_to0(double (&v)[2], double *scratch, long long *dbg = nullptr) {
 #ifndef EONB200_EMU
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = (blockDim.x + 31) >> 5;
@@ -555,13 +555,20 @@ __device__ __forceinline__ void cta_sum2_to0(double (&v)[2], double *scratch) {
     scratch[warp] = v[0];
     scratch[kMaxWarps + warp] = v[1];
   }
+#ifdef EONB200_DBG_RED
+  phase_clock_last(dbg, 6);
+#endif
   __syncthreads();
+#ifdef EONB200_DBG_RED
+  phase_clock(dbg, 7);
+#endif
   if (warp == 0) {
     v[0] = warp_sum(lane < nwarps ? scratch[lane] : 0.0);
     v[1] = warp_sum(lane < nwarps ? scratch[kMaxWarps + lane] : 0.0);
   }
 #else
   (void)scratch;
+  (void)dbg;
 #endif
 }
 
@@ -606,9 +613,13 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
     n3_own_prefetch(sys, tid, cq, wq);
     n3_recv_prefetch(sys, tid, rq);
   }
+#ifndef EONB200_DBG_RED
   phase_clock(clk, 6);
+#endif
   __syncthreads();
+#ifndef EONB200_DBG_RED
   phase_clock(clk, 7);
+#endif
   if (SINGLE) {
     double part = tid < C ? n3_rho_part(sm, L) : 0.0;
     if (lpa == 2) part = n3_pair_sum(part);
@@ -678,7 +689,7 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
   }
   phase_clock(clk, 15);
   phase_clock_last(clk, 13);
-  cta_sum2_to0(acc, sm.red);  // (its barrier also publishes fstage)
+  cta_sum2_to0(acc, sm.red, clk);  // (its barrier also publishes fstage)
   phase_clock(clk, 14);
   if (SINGLE && tid == 32 % nt) {
     const int D = 3 * sys.N;
@@ -873,6 +884,21 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
 #pragma unroll
     for (int u = 0; u < kN3UD; u++) cd[u] = ld_cg(sys.own_cs + tid + u * step);
   }
+#ifndef EONB200_EMU
+  // The pair loops read one list row per iteration and request it only one iteration ahead: a row that has to come
+  // from HBM costs every iteration a full miss (~0.8 us measured: the three loops of a walker took 12 + 6 + 5
+  // iterations x that).  One thread asks the memory system to bring the rows in use into L2 now, while the CTA waits
+  // for its coordinates; the loops then see L2 latency.
+  if (tid == nt - 1 && hdr.y == n3_valid_tag(sys)) {
+    const int rows = min(hdr.z, sys.K / sys.n3_lpa);
+    const char *pc = reinterpret_cast<const char *>(sys.own_cs);
+    const char *pr = reinterpret_cast<const char *>(sys.recv_code);
+    const size_t nc = static_cast<size_t>(rows) * step * sizeof(int2), nr = static_cast<size_t>(rows) * step * sizeof(int);
+    constexpr size_t kChunk = 32768;
+    for (size_t o = 0; o < nc; o += kChunk) l2_prefetch_bulk(pc + o, static_cast<uint32_t>(nc - o < kChunk ? nc - o : kChunk));
+    for (size_t o = 0; o < nr; o += kChunk) l2_prefetch_bulk(pr + o, static_cast<uint32_t>(nr - o < kChunk ? nr - o : kChunk));
+  }
+#endif
   N3Box bx;
   bx.Lx = sys.box[0];  // EAM.cpp:31 reads the diagonal only
   bx.Ly = sys.box[4];
