@@ -105,10 +105,11 @@ struct EonB200Pot {
   DevBuf<long long> d_clocks;  // per-CTA phase clocks of the last fused EAM launch (profiling aid)
   int clocks_on = 0;
   long clocks_ctas = 0;
-  DevBuf<int> d_overflow;
+  // counters of a launch: stats[0..3], and the row-capacity flag in the word behind them (d_ovf / h_ovf), so that one
+  // memset clears and one small copy fetches them all
   DevBuf<unsigned long long> d_stats;
   PinBuf<unsigned long long> h_stats;
-  PinBuf<int> h_overflow;
+  int *d_ovf = nullptr, *h_ovf = nullptr;
   // stateless batch staging
   DevBuf<double> dR, dF, dU, dbox;
   DevBuf<int> dZ;
@@ -512,7 +513,7 @@ NlBatch nl_view(EonB200Pot *pot, NlStore &nl) {
   b.state = nl.state.p;
   b.K = nl.K;
   b.Np = nl.Np;
-  b.overflow = pot->d_overflow.p;
+  b.overflow = pot->d_ovf;
   b.stats = pot->d_stats.p;
   b.pairA = nl.pairA.p;
   b.pairB = nl.pairB.p;
@@ -654,8 +655,7 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     if (static_cast<long>(tile_smem) > pot->max_dyn_smem) return fail(pot, 3, "system too large for the tiled force kernels");
   }
   for (int attempt = 0; attempt < 6; attempt++) {
-    CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
-    CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
+    CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 5 * sizeof(unsigned long long), pot->stream));  // (stats and d_ovf)
     NlBatch view = nl_view(pot, nl);
     if (n3) {
       const int shift = pick_n3_shift(pot, nl, N);
@@ -766,9 +766,8 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
       const int rb = enqueue_readback();
       if (rb) return rb;
     }
-    CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
-    CU_TRY(pot, cudaMemcpyAsync(pot->h_stats.p, pot->d_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                pot->stream));
+    CU_TRY(pot, cudaMemcpyAsync(pot->h_stats.p, pot->d_stats.p, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                pot->stream));  // (stats and d_ovf)
     CU_TRY(pot, cudaStreamSynchronize(pot->stream));
     float ms0 = 0, ms1 = 0;
     if (eam) {  // one kernel: no split point
@@ -779,7 +778,7 @@ int run_force_batch(EonB200Pot *pot, NlStore &nl, ForceBatchArgs a, const double
     }
     pot->last_ms[0] = ms0;
     pot->last_ms[1] = ms1;
-    const int need = pot->h_overflow.p[0];
+    const int need = pot->h_ovf[0];
     pot->last_stats[0] = static_cast<long long>(pot->h_stats.p[0]);
     pot->last_stats[1] = eam ? S - static_cast<long long>(pot->h_stats.p[0]) : static_cast<long long>(pot->h_stats.p[1]);
     pot->last_stats[2] = nl.K;
@@ -896,9 +895,12 @@ EonB200Pot *eonb200_create(const EonB200Config *cfg_in, char *errbuf, size_t err
          cudaEventCreateWithFlags(&pot->ev_k[k], cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&pot->ev_out[k], cudaEventDisableTiming) == cudaSuccess;
 #endif
-  ok = ok && pot->dP.reserve(1) == cudaSuccess && pot->d_overflow.reserve(1) == cudaSuccess &&
-       pot->d_stats.reserve(4) == cudaSuccess && pot->h_stats.reserve(4) == cudaSuccess &&
-       pot->h_overflow.reserve(1) == cudaSuccess;
+  ok = ok && pot->dP.reserve(1) == cudaSuccess && pot->d_stats.reserve(5) == cudaSuccess &&
+       pot->h_stats.reserve(5) == cudaSuccess;
+  if (ok) {
+    pot->d_ovf = reinterpret_cast<int *>(pot->d_stats.p + 4);
+    pot->h_ovf = reinterpret_cast<int *>(pot->h_stats.p + 4);
+  }
   ok = ok && cudaMemcpy(pot->dP.p, &pot->hp, sizeof(PotParams), cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok) {
     // opt in to the full shared memory of the SM for the walker kernels
@@ -1252,6 +1254,36 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   // DMA per chunk instead of one descriptor per 9 KB row; the kernels stage rows of any 8-byte alignment), otherwise
   // an even pitch so that every system starts 16-byte aligned
   const size_t strideR = (direct_in && direct_out) ? D : (D + 1) / 2 * 2;
+  // Zero copy: the half-list EAM kernel stages a walker's coordinates with one bulk copy and returns its forces with
+  // one bulk store, so it can work on the caller's page-locked blocks directly -- every CTA fetches its own 9 KB over
+  // PCIe when it starts and writes its row back when it ends, transfers and arithmetic of different walkers overlap
+  // by themselves, and the call is one launch instead of a chunked copy / kernel / copy pipeline driven by ~20 API
+  // calls.  (Other kernels write forces atom by atom and keep the staged path.)
+  const double *zc_R = nullptr;
+  double *zc_F = nullptr;
+#ifndef EONB200_EMU
+  {
+    static const int zc_env = getenv("EONB200_ZERO_COPY") ? atoi(getenv("EONB200_ZERO_COPY")) : 1;  // development aid: 0 off
+    if (zc_env && direct_in && direct_out && use_n3(pot, N) && pot->nl.n3 && pot->nl.N == N && pot->nl.S >= S &&
+        pick_n3_lpa(pot, N) * N <= 1024) {
+      void *pr = nullptr, *pf = nullptr;
+      if (cudaHostGetDevicePointer(&pr, const_cast<double *>(positions[0]), 0) == cudaSuccess &&
+          cudaHostGetDevicePointer(&pf, forces[0], 0) == cudaSuccess) {
+        zc_R = static_cast<const double *>(pr);
+        zc_F = static_cast<double *>(pf);
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
+#endif
+  static const int zc_mode = getenv("EONB200_ZERO_COPY") ? atoi(getenv("EONB200_ZERO_COPY")) : 1;  // 2: coordinates too
+  // Coordinates fetched by the CTAs over PCIe arrive at about half the copy engine's rate (measured on B200: 256 x
+  // 385 atoms 0.174 ms per call against 0.135 ms with copied coordinates), so by default only the forces take the
+  // direct way: posted writes, spread over the kernel's life, no read-back call at all.
+  const bool zero_copy = zc_R != nullptr && zc_mode >= 2;
+  const bool zero_copy_out = zc_F != nullptr;
+  double *zc_U = nullptr;  // energies likewise (set below, once the handle's page-locked block is in place)
   CU_TRY(pot, pot->dR.reserve(S * strideR));
   CU_TRY(pot, pot->dF.reserve(S * strideR));
   CU_TRY(pot, pot->dU.reserve(S));
@@ -1262,6 +1294,15 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   CU_TRY(pot, pot->hR.reserve(S * strideR));
   CU_TRY(pot, pot->hF.reserve(S * strideR));
   CU_TRY(pot, pot->hU.reserve(S));
+#ifndef EONB200_EMU
+  if (zero_copy_out) {  // one 8-byte posted write per walker
+    void *pu = nullptr;
+    if (cudaHostGetDevicePointer(&pu, pot->hU.p, 0) == cudaSuccess)
+      zc_U = static_cast<double *>(pu);
+    else
+      cudaGetLastError();
+  }
+#endif
   CU_TRY(pot, pot->hbox.reserve(S * 9));
   CU_TRY(pot, pot->hZ.reserve(S * N));
   bool box_changed = pot->last_boxes.size() != static_cast<size_t>(SB) * 9;
@@ -1307,7 +1348,9 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   };
   auto copy_out = [&](long s0, long s1, cudaStream_t st) -> int {
     const size_t n = static_cast<size_t>(s1 - s0);
-    if (direct_out && strideR == D)
+    if (zero_copy_out) {  // the kernel wrote the caller's block itself
+      if (zc_U) return 0;
+    } else if (direct_out && strideR == D)
       CU_TRY(pot, cudaMemcpyAsync(forces[s0], pot->dF.p + s0 * D, n * D * sizeof(double), cudaMemcpyDeviceToHost, st));
     else if (direct_out)
       CU_TRY(pot, cudaMemcpy2DAsync(forces[s0], D * sizeof(double), pot->dF.p + s0 * strideR, strideR * sizeof(double),
@@ -1326,7 +1369,9 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   {
     static const int forced = getenv("EONB200_PIPE_CHUNKS") ? atoi(getenv("EONB200_PIPE_CHUNKS")) : 0;  // development aid
     const size_t bytes = static_cast<size_t>(S) * D * sizeof(double);
-    if (forced > 0)
+    if (zero_copy)
+      pipe.chunks = 1;
+    else if (forced > 0)
       pipe.chunks = std::min<long>(std::min(forced, kPipeMax), S);
     else if (S >= 64 && bytes >= (512u << 10))
       pipe.chunks = static_cast<int>(std::min<long>(kPipeMax, std::max<long>(2, S / 128)));  // (C2, 256 x 385 atoms,
@@ -1335,7 +1380,7 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
 #endif
   pipe.in = copy_in;
   pipe.out = copy_out;
-  if (pipe.chunks == 1) {
+  if (pipe.chunks == 1 && !zero_copy) {
     const int rc0 = copy_in(0, S, pot->stream);
     if (rc0) return rc0;
   }
@@ -1343,14 +1388,14 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   memset(&a, 0, sizeof(a));
   a.S = static_cast<int>(S);
   a.N = static_cast<int>(N);
-  a.R = pot->dR.p;
+  a.R = zero_copy ? zc_R : pot->dR.p;
   a.strideR = static_cast<int>(strideR);
   a.Z = pot->dZ.p;
   a.strideZ = same_Z ? 0 : static_cast<int>(N);
   a.box = pot->dbox.p;
   a.strideBox = same_box ? 0 : 9;
-  a.F = pot->dF.p;
-  a.U = pot->dU.p;
+  a.F = zero_copy_out ? zc_F : pot->dF.p;
+  a.U = zc_U ? zc_U : pot->dU.p;
   a.force_rebuild = box_changed ? 1 : 0;
   auto readback = [&]() -> int { return copy_out(0, S, pot->stream); };
   lap("staged");
@@ -1449,16 +1494,16 @@ int eonb200_neighbors(EonB200Pot *pot, long S, long N, const double *positions, 
     if (attempt >= 6) return fail(pot, 100, "neighbors: list capacity did not converge");
     rc = nl_alloc(pot, nl, S, N, K);
     if (rc) return rc;
-    CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), pot->stream));
+    CU_TRY(pot, cudaMemsetAsync(pot->d_ovf, 0, sizeof(int), pot->stream));
     CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), pot->stream));
     NlBatch view = nl_view(pot, nl);
     EONB200_LAUNCH(k_neighbors, static_cast<unsigned>(S), threads, smem, pot->stream, view, np, static_cast<int>(S),
                    static_cast<int>(N), dR.p, dB.p, maxCells, pot->d_exp_tab.p);
     pot->launches += 1;
     CU_TRY(pot, cudaGetLastError());
-    CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
+    CU_TRY(pot, cudaMemcpyAsync(pot->h_ovf, pot->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
     CU_TRY(pot, cudaStreamSynchronize(pot->stream));
-    const int need = pot->h_overflow.p[0];
+    const int need = pot->h_ovf[0];
     if (need >= (1 << 30)) return fail(pot, 100, "neighbors: image shift outside the representable range");
     if (need <= K) break;
     K = (need + 3) / 4 * 4;
@@ -1771,7 +1816,7 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
   // a job that may move atoms needs head-room in the rows: probe the fill with a force-only pass first
   for (int attempt = 0; attempt < 6; attempt++) {
     if (group < 0) {
-      CU_TRY(pot, cudaMemsetAsync(pot->d_overflow.p, 0, sizeof(int), st));
+      CU_TRY(pot, cudaMemsetAsync(pot->d_ovf, 0, sizeof(int), st));
       CU_TRY(pot, cudaMemsetAsync(pot->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
     }
     NlBatch view = nl_view(pot, w->nl);
@@ -1789,14 +1834,14 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
       return 0;
     }
     CU_TRY(pot, cudaEventRecord(pot->ev[2], pot->stream));
-    CU_TRY(pot, cudaMemcpyAsync(pot->h_overflow.p, pot->d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
+    CU_TRY(pot, cudaMemcpyAsync(pot->h_ovf, pot->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, pot->stream));
     CU_TRY(pot, cudaMemcpyAsync(pot->h_stats.p, pot->d_stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                 pot->stream));
     CU_TRY(pot, cudaStreamSynchronize(pot->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, pot->ev[0], pot->ev[2]);
     w->last_ms = ms;
-    const int need = pot->h_overflow.p[0];
+    const int need = pot->h_ovf[0];
     pot->last_stats[0] = static_cast<long long>(pot->h_stats.p[0]);
     pot->last_stats[1] = static_cast<long long>(pot->h_stats.p[1]);
     pot->last_stats[2] = w->nl.K;

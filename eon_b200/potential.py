@@ -101,6 +101,7 @@ class B200Potential:
         self.device = int(device)
         self._pin = bool(cfg.pin_host_buffers)
         self._pin_keepalive = []
+        self._ptr_cache = {}
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -202,10 +203,23 @@ class B200Potential:
                 if not any(arr is k for k in self._pin_keepalive):
                     self._pin_keepalive.append(arr)
         # arrays of per-system pointers (the reference's `const double *const *`), built from base address + row stride
-        pR, pZ, pF, pB = (_row_ptrs(R, C.c_double), _row_ptrs(Z, C.c_int, S), _row_ptrs(F, C.c_double),
-                          _row_ptrs(B, C.c_double, S))
+        pR, pZ, pF, pB = (self._row_ptrs_cached(R, C.c_double), self._row_ptrs_cached(Z, C.c_int, S),
+                          self._row_ptrs_cached(F, C.c_double), self._row_ptrs_cached(B, C.c_double, S))
         self._check(self._lib.eonb200_force_batch(self._h, S, N, pR, pZ, pF, _dp(U), _dp(V), pB))
         return F.reshape(S, N, 3), U, V
+
+    def _row_ptrs_cached(self, a: np.ndarray, ctype, n: int = 0):
+        """_row_ptrs, remembered per (address, rows, pitch): a caller that hands over the same blocks every step (an
+        optimiser stepping its own position / force arrays) does not pay for 4 x nSystems pointers each time."""
+        key = (a.__array_interface__["data"][0], a.shape[0], a.strides[0], n, ctype)
+        p = self._ptr_cache.get(key)
+        if p is None:
+            if len(self._ptr_cache) >= 64:
+                self._ptr_cache.clear()
+            p = _row_ptrs(a, ctype, n)
+            p._keepalive = (p._keepalive[0],)  # the pointer table only; the array itself belongs to the caller
+            self._ptr_cache[key] = p
+        return p
 
     def forceBatchDevice(self, nSystems: int, nAtoms: int, d_positions: int, d_atomicNrs: int, d_forces: int,
                          d_energies: int, d_boxes: int, sync: bool = True):
