@@ -611,6 +611,58 @@ def run_b200(args):
             wk3.close()
             spot3.close()
 
+    # BASELINE.json configs[0]: the LJ13 cluster, LJ, dimer + CG with the reference's own saddle-search fixture
+    # (client/unit_tests/SaddleSearchTest.cpp:33-54: atom 0 displaced by (+0.3, -0.2, 0), a random unit mode).  One
+    # walker is what the reference runs; a queue of the same search from different random modes shows the batched rate.
+    c1 = None
+    if not args.no_c1:
+        s1 = WL.load_structure("lj13.json")
+        N1 = s1.n_atoms
+        R1 = s1.positions.copy()
+        R1[0, 0] += 0.3
+        R1[0, 1] -= 0.2
+        W1 = 4096
+        rng1 = np.random.default_rng(13 + first)
+        M1 = rng1.uniform(-1.0, 1.0, (W1, N1, 3))  # AtomMatrix::Random: uniform in [-1, 1], then normalised
+        M1 /= np.linalg.norm(M1.reshape(W1, -1), axis=1)[:, None, None]
+        prm1 = search_params(opt_method=0, opt_converged_force=0.01, max_move=0.1, dimer_converged_angle=0.01,
+                             minmode_method=0, saddle_max_iterations=100, saddle_converged_force=0.05,
+                             saddle_max_energy=20.0)
+        ljpot = B200Potential("lj", device=local_rank)
+        _, e1, _ = ljpot.forceBatch(1, N1, R1.reshape(1, -1), s1.atomic_nrs, s1.cell.reshape(9))
+        E01 = float(e1[0])  # (the fixture takes the displaced structure's energy as the reactant energy)
+        one = {}
+        for nw, key in ((1, "single_walker"), (W1, "batched")):
+            wk1 = Walkers(ljpot, s1.atomic_nrs, s1.fixed, s1.cell, np.broadcast_to(R1.reshape(1, -1), (nw, 3 * N1)).copy(),
+                          M1[:nw].reshape(nw, -1).copy())
+            if nw > 1:
+                barrier()
+            t0 = time.perf_counter()
+            wk1.saddle_search(prm1, E01)
+            torch.cuda.synchronize()
+            wall1 = time.perf_counter() - t0
+            if nw > 1:
+                wall1 = reduce_max(wall1)
+            h1 = wk1.harvest()
+            wk1.close()
+            if nw == 1:
+                one = {"status": int(h1.status[0]), "iterations": int(h1.iterations[0]), "force_calls": int(h1.force_calls[0]),
+                       "eigenvalue": float(h1.eigenvalues[0]), "energy_eV": float(h1.energies[0]), "wall_ms": 1e3 * wall1}
+            else:
+                good1 = reduce_sum(float((h1.status == 0).sum()))
+                fc1 = reduce_sum(float(h1.force_calls.sum()))
+                cnt1 = np.zeros(24)
+                for k_, v_ in zip(*np.unique(h1.status, return_counts=True)):
+                    cnt1[int(k_)] += v_
+                hist1 = {k_: int(reduce_sum(float(v_))) for k_, v_ in enumerate(cnt1)}
+                c1 = {"workload": "docs/lj13.con: 13-atom LJ cluster, dimer + CG (SaddleSearchTest.cpp:33-54 settings and "
+                                  "displacement), one walker and a queue of %d random start modes per GPU" % W1,
+                      "single_walker": one, "walkers": int(W1 * world), "wall_s": wall1, "status_good": int(good1),
+                      "searches_per_hour": good1 / wall1 * 3600.0, "force_calls": int(fc1),
+                      "atom_force_evals_per_s": fc1 * N1 / wall1,
+                      "status_histogram": {k_: v_ for k_, v_ in hist1.items() if v_ > 0}}
+        ljpot.close()
+
     # BASELINE.json configs[3] as a third data point: examples/akmc-pt, Morse_Pt, dimer + CG saddle searches from the
     # least-coordinated atoms followed by the minimisation of both minima per walker, classified like ProcessSearchJob
     c4 = None
@@ -744,13 +796,16 @@ def run_b200(args):
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "atom-force-evals/s", "h2d_bytes_per_step": h2d,
                                           "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
                                           "how": "B200Potential.forceBatch on caller-owned contiguous numpy blocks, "
-                                                 "page-locked by the handle; copies and kernels chunk-pipelined on "
-                                                 "three streams", "cpp_shim": e2e_shim},
+                                                 "page-locked by the handle; coordinates copied up in two chunks while the "
+                                                 "first chunk's kernel runs, forces and energies written by the kernel "
+                                                 "straight into the caller's page-locked blocks (bulk stores over PCIe, "
+                                                 "no read-back copies); the d2h bytes are those posted writes",
+                                          "cpp_shim": e2e_shim},
                 "gpu_launches": int(launches), "roofline": roofline,
                 "extra": {"wall_s_timed_region": t_wall, "value_hot_l2": units / world / (t_hot * 1e-3),
                           "value_fresh_list_every_step": units / world / (t_fresh * 1e-3),
                           "list_accounting": list_acc, "affinity": affinity,
-                          "fp64_peak_tflops_measured": fp64_peak / 1e12, "c3": c3, "c4": c4, "c5": c5},
+                          "fp64_peak_tflops_measured": fp64_peak / 1e12, "c1": c1, "c3": c3, "c4": c4, "c5": c5},
                 "search": search}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -771,6 +826,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=0, help="CTAs per walker in the force passes (0 = automatic)")
     ap.add_argument("--lpa", type=int, default=0, help="lanes per atom (0 = automatic)")
     ap.add_argument("--no-search", action="store_true")
+    ap.add_argument("--no-c1", action="store_true", help="skip the LJ13 dimer-search data point")
     ap.add_argument("--no-c3", action="store_true", help="skip the 4096 x 2047-atom data point")
     ap.add_argument("--no-c4", action="store_true", help="skip the akmc-pt Morse process-search data point")
     ap.add_argument("--no-c5", action="store_true", help="skip the neb-al band-force data point")

@@ -549,6 +549,9 @@ __device__ __forceinline__ void cta_sum2_to0(double (&v)[2], double *scratch, lo
 #ifndef EONB200_EMU
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = (blockDim.x + 31) >> 5;
+  // The lanes of a warp leave the pair loop before this call at different iterations; without a reconvergence point
+  // the shuffles below take their divergent-warp path (WARPSYNC.COLLECTIVE per shuffle: 5 of 13 warps did, ncu).
+  __syncwarp();
   v[0] = warp_sum(v[0]);
   v[1] = warp_sum(v[1]);
   if (lane == 0) {
@@ -622,6 +625,7 @@ __device__ __forceinline__ void eam_n3_fast(const N3K &K, const double *c, const
 #endif
   if (SINGLE) {
     double part = tid < C ? n3_rho_part(sm, L) : 0.0;
+    __syncwarp();  // (rows of different lengths: meet again before the two polynomials)
     if (lpa == 2) part = n3_pair_sum(part);
     if (tid < C) {
       L.dfd = eam_dembed(dc, part);
@@ -889,14 +893,12 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   // from HBM costs every iteration a full miss (~0.8 us measured: the three loops of a walker took 12 + 6 + 5
   // iterations x that).  One thread asks the memory system to bring the rows in use into L2 now, while the CTA waits
   // for its coordinates; the loops then see L2 latency.
+  // (the first rows now, the rest once the coordinates are converted: 140 KB per CTA requested at once delayed the
+  // prologue's own loads by 2 us)
+  constexpr int kRowsFirst = 6;
   if (tid == nt - 1 && hdr.y == n3_valid_tag(sys)) {
-    const int rows = min(hdr.z, sys.K / sys.n3_lpa);
-    const char *pc = reinterpret_cast<const char *>(sys.own_cs);
-    const char *pr = reinterpret_cast<const char *>(sys.recv_code);
-    const size_t nc = static_cast<size_t>(rows) * step * sizeof(int2), nr = static_cast<size_t>(rows) * step * sizeof(int);
-    constexpr size_t kChunk = 32768;
-    for (size_t o = 0; o < nc; o += kChunk) l2_prefetch_bulk(pc + o, static_cast<uint32_t>(nc - o < kChunk ? nc - o : kChunk));
-    for (size_t o = 0; o < nr; o += kChunk) l2_prefetch_bulk(pr + o, static_cast<uint32_t>(nr - o < kChunk ? nr - o : kChunk));
+    const int rows = min(min(hdr.z, sys.K / sys.n3_lpa), kRowsFirst);
+    l2_prefetch_bulk(sys.own_cs, static_cast<uint32_t>(static_cast<size_t>(rows) * step * sizeof(int2)));
   }
 #endif
   N3Box bx;
@@ -996,6 +998,18 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
     }
     __syncthreads();
   }
+#ifndef EONB200_EMU
+  if (tid == nt - 1 && hdr.y == n3_valid_tag(sys)) {
+    const int rows = min(hdr.z, sys.K / sys.n3_lpa);
+    const char *pc = reinterpret_cast<const char *>(sys.own_cs);
+    const char *pr = reinterpret_cast<const char *>(sys.recv_code);
+    const size_t nc = static_cast<size_t>(rows) * step * sizeof(int2), nr = static_cast<size_t>(rows) * step * sizeof(int);
+    constexpr size_t kChunk = 32768;
+    for (size_t o = static_cast<size_t>(kRowsFirst) * step * sizeof(int2); o < nc; o += kChunk)
+      l2_prefetch_bulk(pc + o, static_cast<uint32_t>(nc - o < kChunk ? nc - o : kChunk));
+    for (size_t o = 0; o < nr; o += kChunk) l2_prefetch_bulk(pr + o, static_cast<uint32_t>(nr - o < kChunk ? nr - o : kChunk));
+  }
+#endif
   phase_clock(clk, 12);
   // spare slots behind the last one: written by ghost pairs, read (times a zero vector) by padded receiver rows
   for (int k = tid; k < kN3UF; k += nt) sm.slots[nslots - kN3UF + k] = 0.0;
