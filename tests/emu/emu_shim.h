@@ -84,6 +84,7 @@ inline void launch(dim3 grid, size_t smem, F &&body) {
 #define gridDim (emu::gdim())
 
 inline void __syncthreads() {}
+inline void __syncwarp() {}
 inline double __dmul_rn(double a, double b) {
   volatile double r = a * b;
   return r;
