@@ -132,6 +132,9 @@ template <int NV>
 __device__ __forceinline__ void block_reduce(double (&v)[NV], const int (&op)[NV], double *scratch) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = (blockDim.x + 31) >> 5;
+  // Callers arrive from loops whose trip count differs between lanes; without a reconvergence point the shuffles take
+  // their divergent-warp path (WARPSYNC.COLLECTIVE per shuffle -- seen in ncu on the EAM kernel's energy reduction).
+  __syncwarp();
 #pragma unroll
   for (int k = 0; k < NV; k++) {
     double r = op[k] == RED_SUM ? warp_sum(v[k]) : (op[k] == RED_MAX ? warp_max(v[k]) : warp_min(v[k]));

@@ -25,6 +25,7 @@ namespace eonb200 {
 
 __device__ __forceinline__ double group_sum_rt(double v, int lpa) {
 #ifndef EONB200_EMU
+  __syncwarp();  // (callers come out of pair loops of lane-dependent length: reconverge before the shuffles)
   for (int o = lpa >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #endif
   return v;
