@@ -41,10 +41,13 @@ JITTER = 0.05
 N_POSITION_SETS = 4
 FLUSH_BYTES = 512 << 20  # > 4x the 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_eam_fused launch of this workload (ncu --set full capture)
-NCU_DRAM_BYTES_PER_LAUNCH = 31.2e6
-NCU_TRAFFIC_SOURCE = ("profiles/r1c_fused_ncu_raw_selected.csv: 27.1 MB read + 4.0 MB written per launch (cold L2); the "
-                      "64 N + 8 P_o = 33.7 MB of SURVEY.md 8d assume every list row is read twice from HBM -- rows certain "
-                      "to be outside the cutoff are not read at all and the pair cache stays in L2")
+NCU_DRAM_BYTES_PER_LAUNCH = 66.6e6
+NCU_TRAFFIC_SOURCE = ("profiles/r2n_n3_ncu_raw_selected.csv (k_eam_n3, one launch of 256 x 385 atoms under ncu --set full, "
+                      "cold L2): 56.4 MB read + 10.1 MB written against 33.7 MB algorithmic (64 N + 8 P_o, SURVEY.md 8d). "
+                      "The surplus: list rows are fetched whole up to the longest row of the walker (lanes with shorter "
+                      "rows never read the tail), and part of the 39 MB pair scratch (g'/r and the Morse term, written "
+                      "by the density pass and read back by the force pass) leaves L2 under the profiler's cache "
+                      "control. 66.6 MB is 10 us at the HBM peak, a sixth of the kernel's duration: not the bound")
 SEARCH_ROW_Z = WL.SEARCH_ROW_Z  # the in-tree Au row: see DESIGN.md "Search workload"
 A0_AU = WL.A0_AU  # equilibrium fcc lattice constant of the in-tree EAM Au row (oracle)
 
