@@ -186,6 +186,27 @@ def test_lj13_band_end_to_end(backend, oracle):
     assert out["climbing"][0] == M + 1 - out["climbing"][1] or np.isclose(*[out["energies"][k][out["climbing"][k]] for k in (0, 1)])
 
 
+def test_reference_neb_lj_golden_endpoint_energies(backend, oracle):
+    """client/unit_tests/data/reference/neb_lj.dat (the job of JobIntegrationTest.cpp:463-515: LJ13 reactant / product,
+    3 images): `energy_reference` -39.965351 and `image4_energy` 631.805887 (product relative to reactant) are what one
+    band evaluation can be held to.  The golden's 69 optimiser iterations are not: it comes from the SVN-era client
+    (no climbing image -- its highest image has |F| = 30.9 but a projected force of 0.003 --, endpoints not minimised),
+    the product lies 632 eV above the reactant, and the band between them is chaotic; the reference's own test only asks
+    for a valid status, <= 209 force calls and energy_reference (JobIntegrationTest.cpp:492-513)."""
+    a = oracle.load_fixture("lj13.json")
+    b = oracle.load_fixture("lj13_product.json")
+    Z, cell = a["atomic_nrs"], a["cell"]
+    M = 3
+    lam = np.linspace(0.0, 1.0, M + 2).reshape(-1, 1, 1)
+    band = a["positions"][None] + lam * ONEB.pbc(b["positions"] - a["positions"], cell)[None]
+    with B200Potential("lj", lib=backend) as pot:
+        out = NEB.band_forces(pot, band.reshape(1, M + 2, -1), Z, cell, climbing_image=1)
+    E = out["energies"][0]
+    assert E[0] == pytest.approx(-39.965351, abs=1e-6)          # energy_reference
+    assert E[M + 1] - E[0] == pytest.approx(631.805887, abs=1e-5)  # image4_energy
+    assert np.all(np.isfinite(E))
+
+
 @pytest.mark.parametrize("system", ["lj13", "morse_pt"])
 def test_resident_band_evaluation_matches_host_path(backend, oracle, system):
     """``eonb200_neb_band_forces`` (one call: all images evaluated and projected on the device) against
