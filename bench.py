@@ -432,8 +432,10 @@ def run_b200(args):
             ms_mean = reduce_max(float(tok[1])) if out.returncode == 0 and len(tok) >= 3 else float("nan")
             e2e_shim = {"ms_per_step": ms_mean, "value": W * N * world / (ms_mean * 1e-3), "unit": "atom-force-evals/s",
                         "how": "tests/host/harness bench: B200Potential::forceBatch with one heap block per system "
-                               "(positions and forces staged through page-locked buffers, chunked copy / kernel / copy "
-                               "pipeline), wall clock around the call"}
+                               "(what Matter objects hand over): the span of the heap that holds the blocks is "
+                               "page-locked once, the kernel gets one device-visible address per system and reads "
+                               "its coordinates / writes its forces there directly (bulk copies over PCIe, no "
+                               "staging memcpy, one launch); wall clock around the call"}
         except Exception as exc:
             e2e_shim = {"error": str(exc)[:120]}
     # bytes the call moves: positions in (one shared topology row and box), forces + energies + list flags out

@@ -118,6 +118,10 @@ struct EonB200Pot {
   std::vector<double> last_boxes;
   long z_cached_S = 0, z_cached_N = 0;  // shape of the atomic numbers held in hZ / dZ (0: none)
   std::vector<std::pair<const char *, size_t>> pinned;  // caller ranges page-locked by this handle (pin_host_buffers)
+  // systems scattered over the caller's heap (one block per Matter): per-system device-visible addresses
+  DevBuf<unsigned long long> d_rowptr;  // [2 S]: coordinates rows, then force rows
+  PinBuf<unsigned long long> h_rowptr;
+  std::vector<unsigned long long> rowptr_sent;
   NlStore nl;  // cache of the stateless batch slots
   DevBuf<double> neb_R, neb_F, neb_E, neb_P, neb_T;  // eonb200_neb_forces staging
   DevBuf<int> neb_C, neb_Z;
@@ -569,18 +573,55 @@ bool pin_range(EonB200Pot *pot, const void *p, size_t bytes) {
 #else
   if (!pot->cfg.pin_host_buffers || bytes == 0) return false;
   const char *b = static_cast<const char *>(p);
+  const char *e = b + bytes;
   for (auto &r : pot->pinned)
-    if (b >= r.first && b + bytes <= r.first + r.second) return true;
+    if (b >= r.first && e <= r.first + r.second) return true;
+  // ranges of ours that overlap the new one are given up and re-registered as one (registrations must not overlap)
+  for (size_t k = 0; k < pot->pinned.size();) {
+    const char *rb = pot->pinned[k].first, *re = rb + pot->pinned[k].second;
+    if (rb < e && b < re) {
+      cudaHostUnregister(const_cast<char *>(rb));
+      b = std::min(b, rb);
+      e = std::max(e, re);
+      pot->pinned.erase(pot->pinned.begin() + k);
+    } else {
+      k++;
+    }
+  }
   if (pot->pinned.size() >= 32) {  // bounded cache: drop the oldest registration
     cudaHostUnregister(const_cast<char *>(pot->pinned.front().first));
     pot->pinned.erase(pot->pinned.begin());
   }
-  if (cudaHostRegister(const_cast<char *>(b), bytes, cudaHostRegisterDefault) != cudaSuccess) {
+  if (cudaHostRegister(const_cast<char *>(b), static_cast<size_t>(e - b), cudaHostRegisterDefault) != cudaSuccess) {
     cudaGetLastError();  // e.g. overlaps a range somebody else registered: fall back to staging
     return false;
   }
-  pot->pinned.emplace_back(b, bytes);
+  pot->pinned.emplace_back(b, static_cast<size_t>(e - b));
   return true;
+#endif
+}
+
+// Page-lock the span of the caller's heap that holds the S rows of `elems` values each (and the rows of a second
+// array), when it is not much larger than the rows themselves: one block per system, allocated one after the other,
+// is what eonclient's Matter objects look like from here.
+template <typename T, typename U>
+bool pin_rows_span(EonB200Pot *pot, T *const *rows, U *const *rows2, long S, size_t elems) {
+#ifdef EONB200_EMU
+  (void)pot; (void)rows; (void)rows2; (void)S; (void)elems;
+  return false;
+#else
+  if (!pot->cfg.pin_host_buffers || S <= 0) return false;
+  uintptr_t lo = ~static_cast<uintptr_t>(0), hi = 0;
+  for (long s = 0; s < S; s++) {
+    const uintptr_t a0 = reinterpret_cast<uintptr_t>(rows[s]), a1 = reinterpret_cast<uintptr_t>(rows2[s]);
+    lo = std::min(lo, std::min(a0, a1));
+    hi = std::max(hi, std::max(a0, a1) + elems * sizeof(double));
+  }
+  const size_t payload = 2 * static_cast<size_t>(S) * elems * sizeof(double);
+  lo &= ~static_cast<uintptr_t>(4095);
+  hi = (hi + 4095) & ~static_cast<uintptr_t>(4095);
+  if (hi - lo > 8 * payload + (4u << 20)) return false;
+  return pin_range(pot, reinterpret_cast<const void *>(lo), hi - lo);
 #endif
 }
 
@@ -1281,8 +1322,48 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   // Coordinates fetched by the CTAs over PCIe arrive at about half the copy engine's rate (measured on B200: 256 x
   // 385 atoms 0.174 ms per call against 0.135 ms with copied coordinates), so by default only the forces take the
   // direct way: posted writes, spread over the kernel's life, no read-back call at all.
-  const bool zero_copy = zc_R != nullptr && zc_mode >= 2;
-  const bool zero_copy_out = zc_F != nullptr;
+  // Systems scattered over the caller's heap (one block per system, what eonclient's Matter objects hand over): the
+  // span that holds them is page-locked once and the kernel gets one device-visible address per row -- both ways
+  // direct, because the alternative is a 2 x 2.4 MB gather / scatter memcpy on the calling thread.
+  bool scattered = false;
+#ifndef EONB200_EMU
+  if (zc_mode >= 1 && !zc_F && !(direct_in && direct_out) && use_n3(pot, N) && pot->nl.n3 && pot->nl.N == N &&
+      pot->nl.S >= S && pick_n3_lpa(pot, N) * N <= 1024 && pin_rows_span(pot, positions, forces, S, D)) {
+    const char *hb = nullptr;
+    size_t hn = 0;
+    for (auto &r : pot->pinned)
+      if (reinterpret_cast<const char *>(positions[0]) >= r.first &&
+          reinterpret_cast<const char *>(positions[0]) < r.first + r.second) {
+        hb = r.first;
+        hn = r.second;
+      }
+    void *db = nullptr;
+    if (pot->d_rowptr.n < static_cast<size_t>(2 * S)) pot->rowptr_sent.clear();  // (regrown: contents lost)
+    if (hb && cudaHostGetDevicePointer(&db, const_cast<char *>(hb), 0) == cudaSuccess &&
+        pot->h_rowptr.reserve(2 * S) == cudaSuccess && pot->d_rowptr.reserve(2 * S) == cudaSuccess) {
+      bool inside = true;
+      for (long s = 0; s < S && inside; s++) {
+        const char *pr = reinterpret_cast<const char *>(positions[s]), *pf = reinterpret_cast<const char *>(forces[s]);
+        inside = pr >= hb && pr + D * sizeof(double) <= hb + hn && pf >= hb && pf + D * sizeof(double) <= hb + hn;
+        pot->h_rowptr.p[s] = reinterpret_cast<unsigned long long>(static_cast<char *>(db) + (pr - hb));
+        pot->h_rowptr.p[S + s] = reinterpret_cast<unsigned long long>(static_cast<char *>(db) + (pf - hb));
+      }
+      if (inside) {
+        if (pot->rowptr_sent.size() != static_cast<size_t>(2 * S) ||
+            memcmp(pot->rowptr_sent.data(), pot->h_rowptr.p, 2 * S * sizeof(unsigned long long)) != 0) {
+          CU_TRY(pot, cudaMemcpyAsync(pot->d_rowptr.p, pot->h_rowptr.p, 2 * S * sizeof(unsigned long long),
+                                      cudaMemcpyHostToDevice, pot->stream));
+          pot->rowptr_sent.assign(pot->h_rowptr.p, pot->h_rowptr.p + 2 * S);
+        }
+        scattered = true;
+      }
+    } else {
+      cudaGetLastError();
+    }
+  }
+#endif
+  const bool zero_copy = (zc_R != nullptr && zc_mode >= 2) || scattered;
+  const bool zero_copy_out = zc_F != nullptr || scattered;
   double *zc_U = nullptr;  // energies likewise (set below, once the handle's page-locked block is in place)
   CU_TRY(pot, pot->dR.reserve(S * strideR));
   CU_TRY(pot, pot->dF.reserve(S * strideR));
@@ -1388,13 +1469,18 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
   memset(&a, 0, sizeof(a));
   a.S = static_cast<int>(S);
   a.N = static_cast<int>(N);
-  a.R = zero_copy ? zc_R : pot->dR.p;
+  a.R = (zero_copy && !scattered) ? zc_R : pot->dR.p;
   a.strideR = static_cast<int>(strideR);
   a.Z = pot->dZ.p;
   a.strideZ = same_Z ? 0 : static_cast<int>(N);
   a.box = pot->dbox.p;
   a.strideBox = same_box ? 0 : 9;
-  a.F = zero_copy_out ? zc_F : pot->dF.p;
+  a.F = (zero_copy_out && !scattered) ? zc_F : pot->dF.p;
+  if (scattered) {
+    a.Rp = reinterpret_cast<const double *const *>(pot->d_rowptr.p);
+    a.Fp = reinterpret_cast<double *const *>(pot->d_rowptr.p + S);
+    a.strideR = static_cast<int>(D);
+  }
   a.U = zc_U ? zc_U : pot->dU.p;
   a.force_rebuild = box_changed ? 1 : 0;
   auto readback = [&]() -> int { return copy_out(0, S, pot->stream); };
@@ -1410,7 +1496,7 @@ int eonb200_force_batch(EonB200Pot *pot, long S, long N, const double *const *po
     if (nc > 1) CU_TRY(pot, cudaEventSynchronize(pot->ev_out[c]));  // chunk c is back; later chunks still in flight
 #endif
     for (long s = s0; s < s1; s++) {
-      if (!direct_out) memcpy(forces[s], pot->hF.p + s * strideR, D * sizeof(double));
+      if (!direct_out && !scattered) memcpy(forces[s], pot->hF.p + s * strideR, D * sizeof(double));
       energies[s] = pot->hU.p[s];
       if (variances) variances[s] = 0.0;
     }

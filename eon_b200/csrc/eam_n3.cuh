@@ -747,7 +747,7 @@ __device__ EONB200_NOINLINE void eam_n3_ordered(const FusedCold *fc, int r0, boo
         cur[u] = ld_cg(sys.nbr + static_cast<size_t>((n0_first & ~(kFilterBatch - 1)) + u) * sys.Np + tid);
     }
   }
-  double *F = fc->a.F + static_cast<size_t>(blockIdx.y) * fc->a.strideR;
+  double *F = batch_F(fc->a, blockIdx.y);
   double *U = fc->a.U + blockIdx.y;
   if (N <= nt)
     eam_fused_fast<true>(P, ff, sys, sm, 0, N, 1u, 0u, F, U, n0_first, kend_first, cur, nullptr);
@@ -816,7 +816,7 @@ __device__ EONB200_NOINLINE int eam_n3_cold(FusedCold *fc, const NlBatch *nl, co
   int r0 = -1;
   for (int q = P.n_rows - 1; q >= 0; q--)
     if (P.rows[q].Z == z0) r0 = q;
-  double *F = fc->a.F + static_cast<size_t>(blockIdx.y) * fc->a.strideR;
+  double *F = batch_F(fc->a, blockIdx.y);
   if (r0 < 0) {  // element without a row: the reference throws 14324 (EAM.cpp:116-123)
     for (int k = tid; k < 3 * N; k += nt) F[k] = 0.0;
     if (tid == 0) fc->a.U[blockIdx.y] = nan("");
@@ -1013,7 +1013,7 @@ __device__ __forceinline__ void eam_n3_body(const PotParams &P, const PotParams 
   phase_clock(clk, 12);
   // spare slots behind the last one: written by ghost pairs, read (times a zero vector) by padded receiver rows
   for (int k = tid; k < kN3UF; k += nt) sm.slots[nslots - kN3UF + k] = 0.0;
-  double *F = a.F + static_cast<size_t>(s) * a.strideR;
+  double *F = batch_F(a, s);
   const EamRowDev &row = P.rows[r0];
   N3K K;
   K.rc2 = row.rc2;

@@ -31,7 +31,14 @@ struct ForceBatchArgs {
   int kmax;          // candidate rows worth prefetching (largest row fill seen so far)
   int force_rebuild;
   long long *clocks;  // [S * tiles][16] per-CTA phase clocks (profiling aid, may be null)
+  // Optional: one pointer per system instead of base + stride (systems scattered in the caller's page-locked memory;
+  // the half-list EAM kernel only).  R / F above are ignored for the rows when these are set.
+  const double *const *Rp;
+  double *const *Fp;
 };
+__device__ __forceinline__ double *batch_F(const ForceBatchArgs &a, int s) {
+  return a.Fp ? a.Fp[s] : a.F + static_cast<size_t>(s) * a.strideR;
+}
 
 __device__ inline NlParams make_nl_params(const PotParams &P) {
   NlParams np;
@@ -47,8 +54,8 @@ __device__ inline NlParams make_nl_params(const PotParams &P) {
 }
 
 __device__ inline SysView batch_sys(const NlBatch &nl, const ForceBatchArgs &a, int s) {
-  SysView sys = make_sys(nl, s, a.N, a.R + static_cast<size_t>(s) * a.strideR, a.Z + static_cast<size_t>(s) * a.strideZ,
-                         a.box + static_cast<size_t>(s) * a.strideBox);
+  SysView sys = make_sys(nl, s, a.N, a.Rp ? a.Rp[s] : a.R + static_cast<size_t>(s) * a.strideR,
+                         a.Z + static_cast<size_t>(s) * a.strideZ, a.box + static_cast<size_t>(s) * a.strideBox);
   sys.Rcap = a.strideR;
   return sys;
 }
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(kMaxThreadsPerWalker) k_pair(const PotParams *
   int i0, i1;
   tile_prologue(P, sys, sm, a.tiles, i0, i1, false);
   double acc[2] = {0.0, 0.0};
-  double *F = a.F + static_cast<size_t>(s) * a.strideR;
+  double *F = batch_F(a, s);
   const bool near_build = (*sys.flags & 4) != 0;
   if (P.kind == POT_MORSE_PT)
     pair_pass_inl<POT_MORSE_PT>(P, sys, sm, a.lpa, i0, i1, F, acc, near_build);
@@ -363,7 +370,7 @@ __device__ EONB200_NOINLINE void eam_fused_general(const FusedCold *fc, bool tab
   const PotParams &P = *fc->Pp;
   const unsigned T = gridDim.x, rank = blockIdx.x;
   const int N = fc->a.N;
-  double *F = fc->a.F + static_cast<size_t>(blockIdx.y) * fc->a.strideR;
+  double *F = batch_F(fc->a, blockIdx.y);
   double *U = fc->a.U + blockIdx.y;
   if (threadIdx.x == 0) {
     Geom &g = *sm.geom;
@@ -599,7 +606,7 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
     }
   }
   phase_clock(clk, 12);
-  double *F = a.F + static_cast<size_t>(s) * a.strideR;
+  double *F = batch_F(a, s);
   if (EONB200_LIKELY(!mixed && tab_ok && P.eam_fast_ok)) {
     int r0 = -1;
     for (int q = 0; q < P.n_rows; q++)

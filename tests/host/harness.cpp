@@ -34,6 +34,8 @@ int main(int argc, char **argv) {
     for (auto &b : B[s]) if (scanf("%lf", &b) != 1) return 2;
   }
   std::shared_ptr<Potential> pot;
+  int repeat = 1;  // "check - pin repeat=K": the batch is evaluated K times (later calls find the lists in place and, with
+                   // pin, take the direct path for systems scattered over the heap) and the forces are poisoned in between
   const bool bench = argc > 6 && std::string(argv[5]) == "bench";
   try {
     const eonc::PotType tag = kind == EONB200_POT_EAM ? eonc::PotType::EAM_AL
@@ -41,6 +43,7 @@ int main(int argc, char **argv) {
     eonc::B200Options opt;
     opt.library = lib;
     for (int k = 7; k < argc; k++) {
+      if (!strncmp(argv[k], "repeat=", 7)) repeat = std::max(1, std::atoi(argv[k] + 7));
       if (!strcmp(argv[k], "pin")) opt.pinHostBuffers = true;
       if (!strcmp(argv[k], "conservative")) opt.eamConservative = true;
       if (!strncmp(argv[k], "device=", 7)) opt.device = std::atoi(argv[k] + 7);
@@ -106,7 +109,11 @@ int main(int argc, char **argv) {
     return 0;
   }
   try {
-    pot->forceBatch(S, N, pR.data(), pZ.data(), pF.data(), E.data(), V.data(), pB.data());
+    for (int k = 0; k < repeat; k++) {
+      for (auto &f : F) std::fill(f.begin(), f.end(), -777.0);
+      std::fill(E.begin(), E.end(), -777.0);
+      pot->forceBatch(S, N, pR.data(), pZ.data(), pF.data(), E.data(), V.data(), pB.data());
+    }
   } catch (int code) {
     printf("thrown %d\n", code);
     return 0;

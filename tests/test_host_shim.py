@@ -63,6 +63,33 @@ def test_shim_matches_oracle(oracle):
 
 
 @pytest.mark.gpu
+def test_shim_scattered_blocks_direct_path(oracle):
+    """pin_host_buffers with one heap block per system (what Matter objects hand over): from the second call on the
+    kernel reads and writes the caller's blocks directly (per-system addresses, page-locked span); forces are poisoned
+    before every call, so whatever comes back was written by the last one."""
+    build_harness()
+    d = oracle.load_fixture("akmc_al.json")
+    rng = np.random.default_rng(9)
+    N = len(d["atomic_nrs"])
+    systems = [(d["positions"] + rng.uniform(-0.05, 0.05, d["positions"].shape), d["atomic_nrs"], d["cell"]) for _ in range(5)]
+    out = run(3, systems, "check", "-", "pin", "repeat=3")
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.split("\n")
+    assert lines[0] == "calls 16"  # 3 x 5 in forceBatch + 1 by the caller
+    vals = lines[1:]
+    opot = oracle.potential(oracle.POT_EAM)
+    p = 0
+    for s in range(5):
+        R, Z, box = systems[s]
+        E, var = map(float, vals[p].split())
+        F = np.array([float(x) for x in vals[p + 1:p + 1 + 3 * N]]).reshape(N, 3)
+        p += 1 + 3 * N
+        U0, F0 = oracle.force(opot, R, Z, box)
+        assert var == 0.0 and abs(E - U0) < 1e-8
+        assert np.abs(F - F0).max() <= 1e-10 * np.abs(F0).max()
+
+
+@pytest.mark.gpu
 def test_shim_rethrows_14324():
     build_harness()
     out = run(3, [(np.random.default_rng(0).uniform(0, 5, (4, 3)), [13, 13, 29, 13], np.eye(3) * 10)])
