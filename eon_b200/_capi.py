@@ -15,7 +15,7 @@ MINMODE_DIMER, MINMODE_LANCZOS = 0, 1
 ROT_SD, ROT_CG, ROT_LBFGS = 0, 1, 2
 METRIC_NORM, METRIC_MAX_ATOM, METRIC_MAX_COMPONENT = 0, 1, 2
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 #: every symbol include/eonb200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -27,6 +27,7 @@ SYMBOLS = [
     "eonb200_walkers_displace_along_mode", "eonb200_walkers_harvest", "eonb200_walkers_last_ms",
     "eonb200_walkers_displace", "eonb200_walkers_set_active", "eonb200_walkers_groups", "eonb200_walkers_submit", "eonb200_walkers_poll",
     "eonb200_walkers_harvest_group",
+    "eonb200_walkers_queue",
     "eonb200_measure_fp64_peak", "eonb200_kernel_launches", "eonb200_nl_stats",
     "eonb200_last_force_ms", "eonb200_phase_clocks", "eonb200_l2_flush",
     "eonb200_neb_params_default", "eonb200_neb_forces", "eonb200_neb_forces_device", "eonb200_neb_band_forces",
@@ -134,6 +135,9 @@ def bind(lib: C.CDLL) -> C.CDLL:
     lib.eonb200_walkers_poll.restype = C.c_int
     lib.eonb200_walkers_harvest_group.argtypes = [_vp, C.c_int, _ip, _lp, _lp, _dp, _dp, _dp, _dp, _dp]
     lib.eonb200_walkers_harvest_group.restype = C.c_int
+    lib.eonb200_walkers_queue.argtypes = [_vp, C.c_int, C.POINTER(SearchParams), C.c_long, _dp, _dp, _dp, _ip, _lp, _lp,
+                                          _dp, _dp, _dp]
+    lib.eonb200_walkers_queue.restype = C.c_int
     lib.eonb200_walkers_last_ms.argtypes = [_vp]
     lib.eonb200_walkers_last_ms.restype = C.c_double
     lib.eonb200_measure_fp64_peak.argtypes = [_vp, C.c_int]

@@ -150,6 +150,10 @@ struct EonB200Walkers {
   std::vector<double> h_box;
   double last_ms = 0.0;
   bool have_modes = false;
+  // in-kernel queue (eonb200_walkers_queue): per-entry inputs / results
+  DevBuf<double> q_pos, q_mode, q_react, q_energy, q_eig, q_conv;
+  DevBuf<int> q_status, q_next;
+  DevBuf<long long> q_iter, q_fcalls;
   DevBuf<int> active;       // [W] 1 = takes part in the next launches
   bool use_active = false;
   // group-wise asynchronous jobs (eonb200_walkers_submit): one stream and one completion event per group
@@ -1824,7 +1828,7 @@ int walkers_workspace(EonB200Walkers *w, const EonB200SearchParams *prm) {
 // group < 0: all walkers (or the slice [first, first + count)) on the handle's stream, synchronous, with the row-capacity
 // check; group >= 0: the slice on that group's stream, asynchronous (rows must have been sized before).
 int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, int remove_net_force, double scalar,
-                   long first = 0, long count = -1, int group = -1) {
+                   long first = 0, long count = -1, int group = -1, const WalkerLaunch *queue = nullptr) {
   EonB200Pot *pot = w->pot;
   CU_TRY(pot, cudaSetDevice(pot->device));
   EonB200SearchParams local;
@@ -1832,11 +1836,12 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
     eonb200_search_params_default(&local);
     prm = &local;
   }
-  if (prm->lanczos_max_iterations > kMaxLanczosIters && prm->minmode_method == EONB200_MINMODE_LANCZOS && job == 1)
+  const bool search_job = job == 1 || job == 5;  // (5 / 6: searches / relaxations taken from a queue inside the launch)
+  if (prm->lanczos_max_iterations > kMaxLanczosIters && prm->minmode_method == EONB200_MINMODE_LANCZOS && search_job)
     return fail(pot, 2, "lanczos_max_iterations above the supported %d", kMaxLanczosIters);
   if (prm->lbfgs_memory > kMaxLbfgsMemory && prm->opt_method == EONB200_OPT_LBFGS && job != 0)
     return fail(pot, 2, "lbfgs_memory above the supported %d", kMaxLbfgsMemory);
-  if (prm->dimer_rotations_max >= kMaxRotHistory && prm->dimer_opt_method == EONB200_ROT_LBFGS && job == 1)
+  if (prm->dimer_rotations_max >= kMaxRotHistory && prm->dimer_opt_method == EONB200_ROT_LBFGS && search_job)
     return fail(pot, 2, "dimer rotations_max above the supported %d for the lbfgs rotation", kMaxRotHistory - 1);
   int rc = walkers_workspace(w, job == 0 ? nullptr : prm);
   if (rc) return rc;
@@ -1850,6 +1855,8 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
     if (rc) return rc;
   }
   WalkerLaunch wl;
+  memset(&wl, 0, sizeof(wl));
+  if (queue) wl = *queue;  // (the q_* fields; everything else is set below)
   wl.maxCells = pick_max_cells(N);
   wl.lpa = pick_lpa(pot, N, 512);
   wl.job = job;
@@ -1936,7 +1943,7 @@ int walkers_launch(EonB200Walkers *w, int job, const EonB200SearchParams *prm, i
     if (need >= (1 << 30)) return fail(pot, 100, "neighbour image shift outside the representable range");
     if ((job != 0 && job != 4) || need <= w->nl.K) {
       // count the force calls the walkers made
-      if (job != 3 && job != 4) {
+      if (job != 3 && job != 4 && job < 5) {
         std::vector<long long> fc(count);
         std::vector<int> act(count, 1);
         CU_TRY(pot, cudaMemcpy(fc.data(), w->fcalls.p + first, sizeof(long long) * count, cudaMemcpyDeviceToHost));
@@ -2004,6 +2011,79 @@ int eonb200_walkers_relax(EonB200Walkers *w, const EonB200SearchParams *prm) {
   int rc = walkers_size_rows(w);
   if (rc) return rc;
   return walkers_launch(w, 2, prm, prm->remove_net_force, 0.0);
+}
+
+int eonb200_walkers_queue(EonB200Walkers *w, int job, const EonB200SearchParams *prm, long nQueue, double *positions,
+                          double *modes, const double *reactant_energies, int *status, long *iterations, long *force_calls,
+                          double *energies, double *eigenvalues, double *convergence) {
+  if (!w || !prm || !positions || nQueue <= 0) return 1;
+  EonB200Pot *pot = w->pot;
+  if (job != 1 && job != 2) return fail(pot, 2, "walkers_queue: job must be 1 (saddle search) or 2 (relax)");
+  if (job == 1 && !modes) return fail(pot, 2, "walkers_queue: saddle searches need initial modes");
+  CU_TRY(pot, cudaSetDevice(pot->device));
+  int rc = walkers_size_rows(w);
+  if (rc) return rc;
+  const size_t Q = static_cast<size_t>(nQueue), D = static_cast<size_t>(w->D), Dp = static_cast<size_t>(w->Dp);
+  CU_TRY(pot, w->q_pos.reserve(Q * Dp));
+  if (job == 1) CU_TRY(pot, w->q_mode.reserve(Q * Dp));
+  CU_TRY(pot, w->q_react.reserve(Q));
+  CU_TRY(pot, w->q_energy.reserve(Q));
+  CU_TRY(pot, w->q_eig.reserve(Q));
+  CU_TRY(pot, w->q_conv.reserve(Q));
+  CU_TRY(pot, w->q_status.reserve(Q));
+  CU_TRY(pot, w->q_iter.reserve(Q));
+  CU_TRY(pot, w->q_fcalls.reserve(Q));
+  CU_TRY(pot, w->q_next.reserve(1));
+  cudaStream_t st = pot->stream;
+  CU_TRY(pot, cudaMemsetAsync(w->q_pos.p, 0, sizeof(double) * Q * Dp, st));
+  CU_TRY(pot, cudaMemcpy2DAsync(w->q_pos.p, Dp * sizeof(double), positions, D * sizeof(double), D * sizeof(double), Q,
+                                cudaMemcpyHostToDevice, st));
+  if (job == 1) {
+    CU_TRY(pot, cudaMemsetAsync(w->q_mode.p, 0, sizeof(double) * Q * Dp, st));
+    CU_TRY(pot, cudaMemcpy2DAsync(w->q_mode.p, Dp * sizeof(double), modes, D * sizeof(double), D * sizeof(double), Q,
+                                  cudaMemcpyHostToDevice, st));
+  }
+  if (reactant_energies)
+    CU_TRY(pot, cudaMemcpyAsync(w->q_react.p, reactant_energies, sizeof(double) * Q, cudaMemcpyHostToDevice, st));
+  else
+    CU_TRY(pot, cudaMemsetAsync(w->q_react.p, 0, sizeof(double) * Q, st));
+  CU_TRY(pot, cudaMemsetAsync(w->q_next.p, 0, sizeof(int), st));
+  CU_TRY(pot, cudaMemsetAsync(w->q_status.p, 0, sizeof(int) * Q, st));
+  CU_TRY(pot, cudaStreamSynchronize(st));
+  WalkerLaunch q;
+  memset(&q, 0, sizeof(q));
+  q.q_next = w->q_next.p;
+  q.q_len = static_cast<int>(nQueue);
+  q.q_pos = w->q_pos.p;
+  q.q_mode = job == 1 ? w->q_mode.p : nullptr;
+  q.q_react = w->q_react.p;
+  q.q_energy = w->q_energy.p;
+  q.q_eig = w->q_eig.p;
+  q.q_conv = w->q_conv.p;
+  q.q_status = w->q_status.p;
+  q.q_iter = w->q_iter.p;
+  q.q_fcalls = w->q_fcalls.p;
+  const long ctas = std::min<long>(w->W, nQueue);
+  rc = walkers_launch(w, job == 1 ? 5 : 6, prm, prm->remove_net_force, 0.0, 0, ctas, -1, &q);
+  if (rc) return rc;
+  std::vector<long long> it(Q), fc(Q);
+  CU_TRY(pot, cudaMemcpy(it.data(), w->q_iter.p, sizeof(long long) * Q, cudaMemcpyDeviceToHost));
+  CU_TRY(pot, cudaMemcpy(fc.data(), w->q_fcalls.p, sizeof(long long) * Q, cudaMemcpyDeviceToHost));
+  for (size_t k = 0; k < Q; k++) {
+    pot->force_calls += static_cast<unsigned long long>(fc[k]);
+    if (iterations) iterations[k] = static_cast<long>(it[k]);
+    if (force_calls) force_calls[k] = static_cast<long>(fc[k]);
+  }
+  if (status) CU_TRY(pot, cudaMemcpy(status, w->q_status.p, sizeof(int) * Q, cudaMemcpyDeviceToHost));
+  if (energies) CU_TRY(pot, cudaMemcpy(energies, w->q_energy.p, sizeof(double) * Q, cudaMemcpyDeviceToHost));
+  if (eigenvalues) CU_TRY(pot, cudaMemcpy(eigenvalues, w->q_eig.p, sizeof(double) * Q, cudaMemcpyDeviceToHost));
+  if (convergence) CU_TRY(pot, cudaMemcpy(convergence, w->q_conv.p, sizeof(double) * Q, cudaMemcpyDeviceToHost));
+  CU_TRY(pot, cudaMemcpy2D(positions, D * sizeof(double), w->q_pos.p, Dp * sizeof(double), D * sizeof(double), Q,
+                           cudaMemcpyDeviceToHost));
+  if (job == 1)
+    CU_TRY(pot, cudaMemcpy2D(modes, D * sizeof(double), w->q_mode.p, Dp * sizeof(double), D * sizeof(double), Q,
+                             cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int eonb200_walkers_displace_along_mode(EonB200Walkers *w, double signed_offset) {

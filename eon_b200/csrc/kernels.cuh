@@ -674,6 +674,16 @@ struct WalkerLaunch {
   double scalar;  // displacement for job 3
   int first;      // walker of CTA 0: a launch may cover the slice [first, first + gridDim.x) of the handle's walkers
   const int *active;  // [W] 0 = leave this walker alone (null: all active)
+  // job 5 / 6 (saddle searches / relaxations from a queue): every CTA keeps taking the next entry of the queue until
+  // it is empty -- a slot is refilled the moment its walker is done, inside one launch, the way
+  // eon/communicator.py:525-559 hands the next job to a free core.  Inputs and results live in per-entry arrays.
+  int *q_next;            // [1] next entry to hand out
+  int q_len;
+  double *q_pos, *q_mode;  // [Q][Dp] start geometry / mode in, final geometry / mode out
+  const double *q_react;   // [Q] reactant energies (null: 0)
+  double *q_energy, *q_eig, *q_conv;
+  int *q_status;
+  long long *q_iter, *q_fcalls;
 };
 
 __device__ inline void setup_ctx(Ctx &c, const PotParams *Pp, const NlBatch &nl, const WalkerArrays &wa,
@@ -732,6 +742,50 @@ __device__ __forceinline__ void walkers_body(const PotParams *__restrict__ Pp, c
   int status = 0;
   long long iterations = 0;
   double eigenvalue = 0.0, conv = 0.0;
+  if (wl.job >= 5) {  // queue mode
+    __shared__ int q_sh;
+    double *pos_w = wa.pos + static_cast<size_t>(w) * wa.Dp;
+    for (;;) {
+      __syncthreads();
+      if (threadIdx.x == 0) q_sh = atomicAdd(wl.q_next, 1);
+      __syncthreads();
+      const int q = q_sh;
+      if (q >= wl.q_len) break;
+      const size_t qo = static_cast<size_t>(q) * wa.Dp;
+      VLOOP(k, wa.Dp) {
+        pos_w[k] = wl.q_pos[qo + k];
+        if (wl.job == 5) mode[k] = wl.q_mode[qo + k];
+      }
+      __syncthreads();
+      c.force_calls = 0;
+      c.failed = 0;
+      MatterS mq{pos_w, wa.frc + static_cast<size_t>(w) * wa.Dp, 0.0, 1};
+      status = 0;
+      iterations = 0;
+      eigenvalue = 0.0;
+      conv = 0.0;
+      matter_set_positions(c, mq, mq.pos, nullptr, 0.0);
+      if (wl.job == 5)
+        saddle_search_walker(c, mq, mode, wl.q_react ? wl.q_react[q] : 0.0, status, iterations, eigenvalue, conv);
+      else
+        relax_walker(c, mq, status, iterations, conv);
+      if (!c.failed) matter_compute(c, mq);
+      __syncthreads();
+      VLOOP(k, wa.Dp) {
+        wl.q_pos[qo + k] = pos_w[k];
+        if (wl.job == 5) wl.q_mode[qo + k] = mode[k];
+      }
+      if (threadIdx.x == 0) {
+        wl.q_energy[q] = mq.energy;
+        wl.q_status[q] = status;
+        wl.q_iter[q] = iterations;
+        wl.q_fcalls[q] = c.force_calls;
+        wl.q_eig[q] = eigenvalue;
+        wl.q_conv[q] = conv;
+      }
+    }
+    return;
+  }
   if (wl.job == 4) {  // size the neighbour rows for the current geometry; no walker state changes
     c.sys.R = matter.pos;
     nl_ensure(c.np, c.sys, c.sm, c.phase, true, Pp->exp_tab);

@@ -154,6 +154,28 @@ class Walkers:
             self._check(self._lib.eonb200_walkers_set_active(self._h, _ip(a)))
 
     # ---- streaming: a queue of searches through the handle's W slots ------------------------------------------
+    def queue_search(self, prm: _capi.SearchParams, positions, modes=None, reactant_energies=None, job: int = 1,
+                     geometry: bool = True) -> Harvest:
+        """Q >= 1 saddle searches (job 1) or relaxations (job 2) through the W resident slots in ONE launch
+        (``eonb200_walkers_queue``): every CTA takes the next queue entry from a device counter as soon as its walker is
+        done.  Results come back in queue order."""
+        R = np.array(positions, dtype=np.float64).reshape(-1, 3 * self.N)  # (copied: the call writes the final geometries)
+        Q = R.shape[0]
+        M = None if modes is None else np.array(modes, dtype=np.float64).reshape(Q, 3 * self.N)
+        E0 = None
+        if reactant_energies is not None:
+            E0 = np.ascontiguousarray(np.broadcast_to(np.asarray(reactant_energies, dtype=np.float64), (Q,)))
+        st = np.zeros(Q, np.int32)
+        it, fc = np.zeros(Q, np.int64), np.zeros(Q, np.int64)
+        E, ev, cv = np.zeros(Q), np.zeros(Q), np.zeros(Q)
+        lp = C.POINTER(C.c_long)
+        self._check(self._lib.eonb200_walkers_queue(
+            self._h, int(job), C.byref(prm), Q, _dp(R), _dp(M) if M is not None else None,
+            _dp(E0) if E0 is not None else None, _ip(st), it.ctypes.data_as(lp), fc.ctypes.data_as(lp), _dp(E), _dp(ev),
+            _dp(cv)))
+        return Harvest(st, it, fc, E, ev, cv, R.reshape(Q, self.N, 3) if geometry else None,
+                       M.reshape(Q, self.N, 3) if (geometry and M is not None) else None)
+
     def stream_search(self, prm: _capi.SearchParams, positions, modes, reactant_energies=None, groups: int = 32,
                       geometry: bool = True, job: int = 1) -> Harvest:
         """Run Q >= 1 searches (job 1) or relaxations (job 2) through the W slots of this handle, Q arbitrary.

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define EONB200_ABI_VERSION 5
+#define EONB200_ABI_VERSION 6
 
 #if defined(_WIN32)
 #define EONB200_API __declspec(dllexport)
@@ -260,6 +260,17 @@ EONB200_API int eonb200_walkers_poll(EonB200Walkers *w, int group, int wait);
 EONB200_API int eonb200_walkers_harvest_group(EonB200Walkers *w, int group, int *status, long *iterations,
                                               long *force_calls, double *energies, double *eigenvalues,
                                               double *convergence, double *positions, double *modes);
+
+/* A queue of nQueue >= 1 saddle searches (job 1) or relaxations (job 2) through the handle's W resident slots in ONE
+ * launch: every CTA takes the next entry of the queue from a device counter the moment its walker is done, so no slot
+ * waits for a straggler -- the device-side counterpart of the server handing the next job to a free core
+ * (eon/communicator.py:525-559).  positions / modes: [nQueue][3N] start geometries and modes in, final ones out (modes
+ * may be NULL for job 2); reactant_energies: [nQueue] or NULL; outputs [nQueue], any may be NULL.  Which slot runs an
+ * entry does not change its result: an entry starts from a freshly loaded Matter, as SaddleSearchJob does. */
+EONB200_API int eonb200_walkers_queue(EonB200Walkers *w, int job, const EonB200SearchParams *prm, long nQueue,
+                                      double *positions, double *modes, const double *reactant_energies, int *status,
+                                      long *iterations, long *force_calls, double *energies, double *eigenvalues,
+                                      double *convergence);
 
 /* Device time in milliseconds of the last walkers_* launch sequence (CUDA events on the
  * handle's stream), for the measurement harness. */

@@ -379,3 +379,45 @@ def test_streamed_searches_equal_one_launch(backend, oracle):
         assert np.array_equal(after.positions[1], before.positions[1]) and after.force_calls[1] == before.force_calls[1]
         assert after.status[0] == 0 and after.status[2] == 0 and after.energies[0] < before.energies[0] - 0.01
         wk.close()
+
+
+def test_in_kernel_queue_equals_one_launch(backend, oracle):
+    """`eonb200_walkers_queue`: seven searches taken from a device-side queue by three resident slots inside ONE launch give
+    what one launch over seven walkers gives, entry by entry; a queue of relaxations likewise."""
+    d = oracle.load_fixture("morse_pt_saddle.json")
+    Z, box, fixed = d["atomic_nrs"], d["cell"], d["fixed"]
+    Q = 7
+    rng = np.random.default_rng(3)
+    free = (1 - fixed).reshape(1, -1, 3)
+    R = d["displacement_positions"][None] + rng.normal(0.0, 0.02, (Q,) + d["positions"].shape) * free
+    M = d["direction"][None] + rng.normal(0.0, 0.05, (Q,) + d["positions"].shape) * free
+    M /= np.linalg.norm(M.reshape(Q, -1), axis=1).reshape(Q, 1, 1)
+    prm = search_params(lib=backend, opt_method=1)
+    rprm = search_params(lib=backend, opt_method=1, opt_converged_force=1e-3)
+    opot = oracle.potential(oracle.POT_MORSE_PT)
+    E0, _ = oracle.force(opot, d["positions"], Z, box)
+    with B200Potential("morse_pt", lib=backend) as pot:
+        wk = Walkers(pot, Z, fixed, box, R.reshape(Q, -1), M.reshape(Q, -1))
+        wk.saddle_search(prm, E0)
+        ref = wk.harvest()
+        wk.set(positions=R.reshape(Q, -1))
+        wk.relax(rprm)
+        ref_relax = wk.harvest()
+        wk.close()
+    with B200Potential("morse_pt", lib=backend) as pot:
+        wk = Walkers(pot, Z, fixed, box, R[:3].reshape(3, -1), M[:3].reshape(3, -1))
+        launches = pot.kernelLaunches
+        h = wk.queue_search(prm, R.reshape(Q, -1), M.reshape(Q, -1), E0)
+        assert pot.kernelLaunches - launches <= 3  # (list-sizing probes the first time, then the ONE launch)
+        assert np.array_equal(h.status, ref.status) and np.array_equal(h.force_calls, ref.force_calls)
+        assert np.array_equal(h.iterations, ref.iterations)
+        assert np.abs(h.energies - ref.energies).max() < 1e-10
+        assert np.abs(h.positions - ref.positions).max() < 1e-10 and np.abs(h.modes - ref.modes).max() < 1e-10
+        assert np.abs(h.eigenvalues - ref.eigenvalues).max() < 1e-9
+        assert pot.forceCallCounter >= int(ref.force_calls.sum())
+        hr = wk.queue_search(rprm, R.reshape(Q, -1), job=2)
+        assert np.array_equal(hr.status, ref_relax.status) and np.array_equal(hr.iterations, ref_relax.iterations)
+        assert np.abs(hr.energies - ref_relax.energies).max() < 1e-10
+        assert np.abs(hr.positions - ref_relax.positions).max() < 1e-10
+        wk.close()
+
