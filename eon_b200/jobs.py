@@ -161,7 +161,8 @@ def run_saddle_search_jobs(job_dirs: Sequence[str], out_dirs: Optional[Sequence[
                            pot: Optional[B200Potential] = None, slots: int = 0, groups: int = 32) -> List[dict]:
     """``SaddleSearchJob::run`` + ``saveData`` for every directory of `job_dirs` (all of one topology and one
     ``config.ini`` content, as the jobs an AKMC step hands out are): one launch over all of them, or -- with
-    ``0 < slots < len(job_dirs)`` -- streamed through that many slots.  Writes ``results.dat``, ``mode.dat`` and
+    ``0 < slots < len(job_dirs)`` -- through that many resident slots: streamed in `groups` groups, or with
+    ``groups <= 0`` taken from a device-side queue inside one launch (``eonb200_walkers_queue``).  Writes ``results.dat``, ``mode.dat`` and
     ``saddle.con`` into the matching `out_dirs` (default: the job directories) and returns the parsed results."""
     if not job_dirs:
         return []
@@ -203,6 +204,8 @@ def run_saddle_search_jobs(job_dirs: Sequence[str], out_dirs: Optional[Sequence[
         if n_slots == W:
             wk.saddle_search(prm, E0)
             h = wk.harvest()
+        elif groups <= 0:  # device-side queue: one launch, every slot takes the next job directory's search when free
+            h = wk.queue_search(prm, R, M, E0)
         else:
             h = wk.stream_search(prm, R, M, E0, groups=groups)
         wk.close()

@@ -164,3 +164,12 @@ max_energy = 10.0
         assert np.all(mode[d["fixed"].astype(bool)] == 0.0) and abs(np.linalg.norm(mode) - 1.0) < 1e-9
     assert np.abs(confile.read_con(os.path.join(dirs[0], "saddle.con")).positions -
                   confile.read_con(os.path.join(dirs[2], "saddle.con")).positions).max() == 0.0
+    # the same three directories through two resident slots and the device-side queue: same results files
+    outs = [str(tmp_path / ("queued%d" % k)) for k in range(3)]
+    with B200Potential("morse_pt", lib=backend) as pot:
+        res_q = jobs.run_saddle_search_jobs(dirs, out_dirs=outs, pot=pot, slots=2, groups=0)
+    for k in range(3):
+        assert res_q[k]["iterations"] == res[k]["iterations"] and res_q[k]["force_calls_saddle"] == res[k]["force_calls_saddle"]
+        assert res_q[k]["potential_energy_saddle"] == pytest.approx(res[k]["potential_energy_saddle"], abs=1e-9)
+        assert np.abs(confile.read_con(os.path.join(outs[k], "saddle.con")).positions -
+                      confile.read_con(os.path.join(dirs[k], "saddle.con")).positions).max() < 1e-9
