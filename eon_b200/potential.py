@@ -11,6 +11,7 @@ caller checks before batching (client/ImprovedDimer.cpp:160, client/NudgedElasti
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -102,9 +103,12 @@ class B200Potential:
         self._pin = bool(cfg.pin_host_buffers)
         self._pin_keepalive = []
         self._ptr_cache = {}
+        self._walkers = weakref.WeakSet()  # Walkers created on this handle
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
+        for wk in list(getattr(self, "_walkers", ())):  # resident walkers go first: they belong to this handle
+            wk.close()
         if getattr(self, "_h", None):
             self._lib.eonb200_destroy(self._h)
             self._h = None

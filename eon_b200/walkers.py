@@ -78,10 +78,12 @@ class Walkers:
         if not self._h:
             raise PotentialError(1, err.value.decode() or "eonb200_walkers_create failed")
         self.W, self.N = W, N
+        pot._walkers.add(self)  # the potential closes its walkers before it goes (they hold device memory of its context)
 
     def close(self):
         if getattr(self, "_h", None):
-            self._lib.eonb200_walkers_destroy(self._h)
+            if getattr(self._pot, "_h", None):  # (a handle whose potential is gone is not touched)
+                self._lib.eonb200_walkers_destroy(self._h)
             self._h = None
 
     def __del__(self):

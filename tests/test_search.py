@@ -421,3 +421,16 @@ def test_in_kernel_queue_equals_one_launch(backend, oracle):
         assert np.abs(hr.positions - ref_relax.positions).max() < 1e-10
         wk.close()
 
+
+def test_potential_closes_its_walkers_first(backend, oracle):
+    """Closing a potential handle closes the resident walkers created on it (they hold memory of its context); a
+    Walkers object outliving its potential must not touch the freed handle when it is collected."""
+    d = oracle.load_fixture("lj13.json")
+    pot = B200Potential("lj", lib=backend)
+    wk = Walkers(pot, d["atomic_nrs"], d["fixed"], d["cell"], d["positions"].reshape(1, -1))
+    wk.matter_forces()
+    pot.close()
+    assert wk._h is None
+    wk.close()
+    del wk
+
