@@ -1,2 +1,2 @@
-for v in eam morse "morse close" both oracle; do echo "== $v"; python tools/_smoke_dbg.py $v 2>&1 | tail -12; echo "rc=$?"; done
-git -C . log --oneline | head -1
+python -c "import __graft_entry__ as g; g.smoke()"; echo "smoke rc=$?"
+python -m pytest tests/test_search.py tests/test_process_search.py -m gpu -x -q 2>&1 | tail -2
