@@ -1,2 +1,3 @@
-python -c "import __graft_entry__ as g; g.smoke()"; echo "smoke rc=$?"
-python -m pytest tests/test_search.py tests/test_process_search.py -m gpu -x -q 2>&1 | tail -2
+for c in 2 3 4; do EONB200_PIPE_CHUNKS=$c timeout 120 python tools/e2e_py.py steps=300 2>&1 | head -1; done
+timeout 120 python tools/e2e_py.py steps=300 2>&1 | head -1
+python -m pytest tests/test_forces.py tests/test_host_shim.py -m gpu -x -q 2>&1 | tail -1
