@@ -452,19 +452,27 @@ __device__ __forceinline__ void eam_fused_body(const PotParams *__restrict__ Pp,
 #endif
 
   // ---- get every HBM access of the prologue in flight at once ----------------------------------------------
-  double *raw = reinterpret_cast<double *>(sm.pos) + (N + (N & 1));  // lands in the tail of the position block
+  // A bulk copy needs 16-byte aligned ends on both sides.  Rows of an odd 3N in a packed [S][3N] array start on odd
+  // multiples of 8 bytes for every second walker (and end on one for the others): the copy moves the aligned interior,
+  // the (at most one) leading and trailing coordinate come by plain loads, and the landing zone is shifted by one
+  // double when the row starts odd so that the interior is aligned in shared memory too.
   const int D = 3 * N;
-  const int nd = ((D & 1) && sys.Rcap > D) ? D + 1 : D;
-  const uint32_t rbytes = static_cast<uint32_t>(nd) * 8u;
-  const bool aligned = ((reinterpret_cast<uintptr_t>(sys.R) & 15u) == 0) && (rbytes % 16u == 0);
+  const uintptr_t raddr = reinterpret_cast<uintptr_t>(sys.R);
+  const bool aligned = (raddr & 7u) == 0;
+  const int head = (raddr & 15u) ? 1 : 0;
+  const int body = (D - head) & ~1;
+  double *raw = reinterpret_cast<double *>(sm.pos) + (N + (N & 1)) + head;  // lands in the tail of the position block
+  const uint32_t rbytes = static_cast<uint32_t>(body) * 8u;
   if (tid == 0) {
     mbar_init(sm.mbar, 1);
     if (aligned) {
       mbar_expect(sm.mbar, rbytes + 1024u);
-      bulk_g2s_issue(raw, sys.R, rbytes, sm.mbar);
+      if (body > 0) bulk_g2s_issue(raw + head, sys.R + head, rbytes, sm.mbar);
       bulk_g2s_issue(sm.exp_tab, Pp->exp_tab, 1024u, sm.mbar);
     }
   }
+  if (aligned && tid == 32 % nt && head) raw[0] = sys.R[0];
+  if (aligned && tid == 33 % nt && head + body < D) raw[D - 1] = sys.R[D - 1];
   const double Lbox[3] = {sys.box[0], sys.box[4], sys.box[8]};  // EAM.cpp:31 reads the diagonal only
   const bool have = nl_have_list(sys);
   const int z0 = sys.Z[0];
