@@ -1,3 +1,3 @@
-python -m pytest tests/test_forces.py tests/test_neb.py -m gpu -x -q 2>&1 | tail -1
-python tools/eam_bench.py c3 steps=10 | head -1
-python tools/eam_bench.py mode=1 steps=20 | head -1
+# scratch script of the last gpurun call (development aid): GPU tests, then the bench line
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo rc=$?
