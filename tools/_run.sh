@@ -1,6 +1,11 @@
-python bench.py --steps 10 --warmup 3 --no-c1 --no-c3 --no-c5 --no-search --no-cpu > gpurun_out/r2w_bench.json 2> gpurun_out/r2w_bench.err; echo rc=$?; tail -3 gpurun_out/r2w_bench.err
-python -c "
-import json; d=json.load(open('gpurun_out/r2w_bench.json')); print(d['extra']['c4'])"
-ncu --set full --clock-control none --import-source on -k regex:k_pair -s 5 -c 1 -o gpurun_out/r2w_pair -f python tools/pair_bench.py > gpurun_out/r2w_pair_ncu.log 2>&1; echo "ncu rc=$?"
-ncu -i gpurun_out/r2w_pair.ncu-rep --page details > gpurun_out/r2w_pair_details.txt 2>/dev/null
-ncu -i gpurun_out/r2w_pair.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/r2w_pair_src.csv 2>/dev/null
+python -c "import __graft_entry__ as g; g.smoke()"; echo "smoke rc=$?"
+python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+python bench.py > gpurun_out/r2x_bench.json 2> gpurun_out/r2x_bench.err; echo bench rc=$?; tail -2 gpurun_out/r2x_bench.err
+python bench.py --impl reference > gpurun_out/r2x_bench_reference.json 2> gpurun_out/r2x_ref.err; echo ref rc=$?
+python - <<EOF2
+import json
+d=json.load(open("gpurun_out/r2x_bench.json")); r=json.load(open("gpurun_out/r2x_bench_reference.json"))
+print(d["value"], d["ms_per_step"], d["roofline"]["frac"], d["e2e"]["ms_per_step"], d["e2e"]["cpp_shim"]["ms_per_step"], "ratio", d["e2e"]["value"]/r["value"], "launches", d["gpu_launches"], d["clocks"])
+print(d["search"]["searches_per_hour"], d["search"]["mode"], d["search"]["queued"]["outcomes_differing_from_streamed"])
+print(d["extra"]["c4"]["force_kernel"]["fp64_roofline_frac"], d["extra"]["c3"]["fp64_roofline_frac"])
+EOF2
