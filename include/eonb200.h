@@ -350,7 +350,10 @@ EONB200_API int eonb200_l2_flush(EonB200Pot *pot, size_t bytes);
 /* Profiling aid of the fused EAM kernel: with `enable` != 0 the next launches record, per CTA, 16 words
  * (0: %globaltimer ns at entry, 1: SM id, 2..10: SM cycle counter at entry / positions landed / conversion and
  * Verlet check done / filter done / density done / CTA density done / cluster barrier passed / force done / exit;
- * thread 0 of the CTA).  Copies the last launch's records (n_ctas = nSystems * CTAs per system) to `out`. */
+ * thread 0 of the CTA).  The half-list kernel (k_eam_n3) uses the words as: 2 entry, 3 coordinates landed, 4 converted,
+ * 12 list decision, 6 / 7 density done / barrier passed, 8 embedding done, 9 owner pass done, 15 thread 0 leaves the
+ * receiver pass, 14 energy reduction done, 10 exit, and 5 / 11 / 13 = the LAST warp of the CTA leaving the density /
+ * owner / receiver loops (atomic max).  Copies the last launch's records (n_ctas = nSystems * CTAs per system) to `out`. */
 EONB200_API int eonb200_phase_clocks(EonB200Pot *pot, int enable, long long *out, long cap_ctas, long *n_ctas);
 
 #ifdef __cplusplus
