@@ -282,7 +282,7 @@ void pick_tiling(const EonB200Pot *pot, long S, long N, int *tiles, int *lpa) {
   if (*tiles > N) *tiles = static_cast<int>(N);
   *lpa = 1;
 #else
-  const long want_ctas = 4L * pot->sm_count;
+  const long want_ctas = 14L * pot->sm_count;  // (Morse_Pt, 256 x 343 atoms on B200: 3 tiles x 2 lanes per atom 205 us, 8 x 4 185 us)
   long t = (want_ctas + S - 1) / S;
   t = std::max<long>(1, std::min<long>(t, kMaxTiles));
   t = std::min<long>(t, std::max<long>(1, N / 32));
