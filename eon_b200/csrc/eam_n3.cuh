@@ -65,14 +65,29 @@ __device__ __forceinline__ int n3_lane_off(int shift) {
 }
 // all copies of atom i (copy order rotated by the lane, so that the lanes of a warp store into different bank groups)
 __device__ __forceinline__ void n3_store_xy(double2 *pxy, int shift, int i, double x, double y) {
+  if (EONB200_LIKELY(shift == 7)) {  // eight copies: unrolled
+#pragma unroll
+    for (int k = 0; k < 8; k++) pxy[(i << 3) + ((k + static_cast<int>(threadIdx.x)) & 7)] = make_double2(x, y);
+    return;
+  }
   const int rep = 1 << (shift - 4);
   for (int k = 0; k < rep; k++) pxy[(i << (shift - 4)) + ((k + static_cast<int>(threadIdx.x)) & (rep - 1))] = make_double2(x, y);
 }
 __device__ __forceinline__ void n3_store_zw(double2 *pzw, int shift, int i, double z, double w) {
+  if (EONB200_LIKELY(shift == 7)) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) pzw[(i << 3) + ((k + static_cast<int>(threadIdx.x)) & 7)] = make_double2(z, w);
+    return;
+  }
   const int rep = 1 << (shift - 4);
   for (int k = 0; k < rep; k++) pzw[(i << (shift - 4)) + ((k + static_cast<int>(threadIdx.x)) & (rep - 1))] = make_double2(z, w);
 }
 __device__ __forceinline__ void n3_store_w(double2 *pzw, int shift, int i, double w) {
+  if (EONB200_LIKELY(shift == 7)) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) pzw[(i << 3) + ((k + static_cast<int>(threadIdx.x)) & 7)].y = w;
+    return;
+  }
   const int rep = 1 << (shift - 4);
   for (int k = 0; k < rep; k++) pzw[(i << (shift - 4)) + ((k + static_cast<int>(threadIdx.x)) & (rep - 1))].y = w;
 }
@@ -550,8 +565,10 @@ __device__ __forceinline__ void cta_sum2_to0(double (&v)[2], double *scratch, lo
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = (blockDim.x + 31) >> 5;
   // The lanes of a warp leave the pair loop before this call at different iterations; without a reconvergence point
-  // the shuffles below take their divergent-warp path (WARPSYNC.COLLECTIVE per shuffle: 5 of 13 warps did, ncu).
-  __syncwarp();
+  // the shuffles below take their divergent-warp path (WARPSYNC.COLLECTIVE per shuffle: 5 of 13 warps did, ncu: 2.6 us
+  // per walker).  A __syncwarp() here is not enough -- ptxas sinks it below the full-mask shuffles in some builds -- so
+  // the CTA meets at a barrier first (the warps would wait at the one below anyway).
+  __syncthreads();
   v[0] = warp_sum(v[0]);
   v[1] = warp_sum(v[1]);
   if (lane == 0) {

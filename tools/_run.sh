@@ -1,2 +1,2 @@
-for t in 9 10 12 14 16; do python tools/pair_bench.py morse_pt 256 $t 2>&1 | tail -1 | cut -c1-150; done
-for t in 12 16; do python tools/pair_bench.py morse_pt 256 $t 2 2>&1 | tail -1 | cut -c1-150; done
+python tools/eam_bench.py clocks steps=40 > gpurun_out/r2y.txt 2>&1; grep -v "^  ctas\|list decision\|density barrier\|exit  " gpurun_out/r2y.txt
+python -m pytest tests/test_forces.py -m gpu -x -q 2>&1 | tail -1
