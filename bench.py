@@ -42,7 +42,7 @@ N_POSITION_SETS = 4
 FLUSH_BYTES = 512 << 20  # > 4x the 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_eam_fused launch of this workload (ncu --set full capture)
 NCU_DRAM_BYTES_PER_LAUNCH = 66.6e6
-NCU_TRAFFIC_SOURCE = ("profiles/r2n_n3_ncu_raw_selected.csv (k_eam_n3, one launch of 256 x 385 atoms under ncu --set full, "
+NCU_TRAFFIC_SOURCE = ("profiles/r2z_n3_ncu_raw_selected.csv (k_eam_n3, one launch of 256 x 385 atoms under ncu --set full, "
                       "cold L2): 56.4 MB read + 10.1 MB written against 33.7 MB algorithmic (64 N + 8 P_o, SURVEY.md 8d). "
                       "The surplus: list rows are fetched whole up to the longest row of the walker (lanes with shorter "
                       "rows never read the tail), and part of the 39 MB pair scratch (g'/r and the Morse term, written "
