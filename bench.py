@@ -358,6 +358,15 @@ def run_b200(args):
     # FP64 roofline denominator, measured live (MEASURED_PEAKS.json has no FP64 figure)
     fp64_peak = pot.measure_fp64_peak(5)
 
+    # Ranks reach the barrier below at different times, and a GPU that waits idle for the others drops its clocks: the
+    # whole timed region (a few milliseconds) then runs at half speed on that rank (seen once at 8 GPUs: 0.135 ms per
+    # step on one rank, 0.062 on the rest).  So: meet once, keep every GPU busy for 0.15 s with untimed steps, meet again.
+    barrier()
+    t_spin = time.perf_counter() + 0.15
+    k_spin = 0
+    while time.perf_counter() < t_spin:
+        step(k_spin)
+        k_spin += 1
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = pot.kernelLaunches
@@ -374,6 +383,8 @@ def run_b200(args):
     launches = pot.kernelLaunches - launches0
     clocks = sampler.stop()
     dev_ms_max = reduce_max(dev_ms)
+    if os.environ.get("EONB200_BENCH_TRACE"):  # development aid: every rank's own device time
+        print("[bench] rank %d: %.4f ms per step (device), nl %s" % (rank, dev_ms / args.steps, pot.nl_stats()), file=sys.stderr, flush=True)
     units = reduce_sum(float(W) * N * args.steps)
     value = units / (dev_ms_max * 1e-3)
 
@@ -411,6 +422,13 @@ def run_b200(args):
     e2e_s = reduce_max(time.perf_counter() - t0)
     # same position set as the last device-resident step above: the host path must return the same energies
     assert np.allclose(e_U, d_U.cpu().numpy(), rtol=0.0, atol=1e-8), "e2e energies differ from the device-resident run"
+    # the same call sustained for 400 more steps: with the GPU idle two thirds of every call its clocks settle lower than
+    # right after the device-resident leg, and the call time with them (reported beside the K timed steps)
+    t0 = time.perf_counter()
+    for k in range(400):
+        epot.forceBatch(W, N, h_R[k % N_POSITION_SETS], struct.atomic_nrs, struct.cell.reshape(9), out=h_F)
+    torch.cuda.synchronize()
+    e2e_sustained_ms = 1e3 * reduce_max(time.perf_counter() - t0) / 400
     epot.close()
     e2e_value = units / e2e_s
     # The same call through the C++ shim an eonclient build would link (eon_b200/host/B200Potential.hpp), every system
@@ -855,6 +873,7 @@ def run_b200(args):
                 "config": workload_config(N, world, args.skin, rebuilt),
                 "clocks": clocks, "e2e": {"value": e2e_value, "unit": "atom-force-evals/s", "h2d_bytes_per_step": h2d,
                                           "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
+                                          "ms_per_step_sustained_400_calls": e2e_sustained_ms,
                                           "how": "B200Potential.forceBatch on caller-owned contiguous numpy blocks, "
                                                  "page-locked by the handle; coordinates copied up in two chunks while the "
                                                  "first chunk's kernel runs, forces and energies written by the kernel "
